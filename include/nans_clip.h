@@ -1,0 +1,185 @@
+/*
+ * nans_clip.h — C-ABI of the B200 (sm_100a) contrastive-loss / top-k retrieval hot path.
+ *
+ * This is the drop-in boundary.  The reference (n571e/NanS-CLIP, a Chinese-CLIP
+ * fork) has no FFI of its own: the path is three Python call sites.  Each entry point below names
+ * the reference lines it replaces; INTEGRATION.md shows the ctypes binding a maintainer adds.
+ *
+ * Conventions (all functions):
+ *   - extern "C", return int: 0 = ok, <0 = error code (NANS_ERR_*); nans_last_error() returns a
+ *     thread-local message for the most recent failure on the calling thread.
+ *   - raw device pointers + explicit sizes; no torch types; a cudaStream_t passed as void*.
+ *   - nothing is allocated: the caller passes outputs and a workspace whose size comes from the
+ *     matching *_workspace_bytes query.  No device synchronisation, no global mutable state
+ *     (one cached driver entry point), CUDA-graph capturable, safe on concurrent streams.
+ *   - scalars that live on the device in the reference (logit_scale.exp(), the upstream grad of
+ *     the loss) are passed as DEVICE pointers so that no call forces a host sync.
+ *   - feature matrices are row-major [rows, D] with a leading dimension in elements.
+ *   - there is NO CPU fallback: every compute call fails with NANS_ERR_DEVICE unless the
+ *     current device is compute capability 10.x (sm_100a code only).
+ */
+#ifndef NANS_CLIP_H_
+#define NANS_CLIP_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NANS_VERSION 100 /* 0.1.0 */
+
+/* element types */
+#define NANS_F32 0
+#define NANS_F16 1
+#define NANS_BF16 2
+
+/* error codes */
+#define NANS_OK 0
+#define NANS_ERR_ARG (-1)       /* bad argument (null pointer, size, alignment, dtype) */
+#define NANS_ERR_DEVICE (-2)    /* current device is not sm_100 / no device */
+#define NANS_ERR_CUDA (-3)      /* a CUDA runtime / driver call failed */
+#define NANS_ERR_WORKSPACE (-4) /* workspace too small */
+
+/* flags for nans_clip_loss_fwd */
+#define NANS_LOSS_WITH_ACC 1 /* also count in-batch top-1 hits (train.py:117-121) */
+
+/* ---- plumbing -------------------------------------------------------------------------- */
+
+int nans_version(void);
+const char* nans_last_error(void);
+/* 0 if the current CUDA device can run this library (cc 10.x), else NANS_ERR_DEVICE. */
+int nans_device_check(void);
+
+/* ---- (1) L2-normalise + 16-bit cast ---------------------------------------------------- */
+/*
+ * Replaces cn_clip/clip/model.py:412-413 (`x / x.norm(dim=-1, keepdim=True)`) fused with the cast
+ * to the tensor-core operand type.  One pass over x.
+ *   x        [rows, D] (ld_x elements between rows), dtype x_dtype (NANS_F32/F16/BF16)
+ *   y16      [rows, D] contiguous, dtype y16_dtype (NANS_F16/BF16), or NULL
+ *   y32      [rows, D] contiguous fp32 normalised copy (what the reference returns), or NULL
+ *   inv_norm [rows] fp32 1/||x||, or NULL (kept for the normalise backward)
+ *   normalize != 0: divide by the row norm; == 0: cast only (features already unit-norm)
+ * D must be a multiple of 8.  Zero rows give inf/nan exactly as the reference's division does.
+ */
+int nans_l2norm_cast(const void* x, int x_dtype, int64_t rows, int64_t D, int64_t ld_x,
+                     void* y16, int y16_dtype, float* y32, float* inv_norm, int normalize,
+                     void* stream);
+
+/*
+ * Backward of the normalisation (autograd of model.py:412-413):
+ *   dx = inv_norm * (dy - y * <dy, y>),  y = x * inv_norm.
+ *   x [rows, D] x_dtype (ld_x), dy [rows, D] fp32 contiguous, dx [rows, D] fp32 contiguous.
+ */
+int nans_l2norm_bwd(const void* x, int x_dtype, int64_t ld_x, const float* inv_norm,
+                    const float* dy, int64_t rows, int64_t D, float* dx, void* stream);
+
+/* ---- (2) fused contrastive forward ------------------------------------------------------ */
+/*
+ * Replaces cn_clip/training/train.py:87-88 (+103-104), 109-121: the (s*I)@T^T logits, both
+ * cross-entropies against arange labels and the optional argmax accuracy — without ever writing
+ * the logits.  Each rank computes two strips: I_loc x T_cols^T (image->text softmax over columns)
+ * and T_loc x I_cols^T (text->image softmax).
+ *
+ * The column sweep may be issued in PHASES (e.g. the local block while the all-gather of the
+ * other ranks' features is still in flight, then the rest).  A phase covers `ncols` columns given
+ * by two column operands; column j of the phase is GLOBAL column col_global_begin + j.
+ * Row r of the local block has its label (the positive pair) at global column label_begin + r.
+ * Every phase writes partial (max, sum) statistics into workspace slots
+ * [slot_begin, slot_begin + nans_clip_loss_fwd_phase_slots(...)); nans_clip_loss_fwd_finalize
+ * merges `total_slots` slots.
+ *
+ *   I_loc, T_loc   [n_loc, D] 16-bit (feat_dtype), leading dims ld_loc
+ *   T_cols, I_cols [ncols, D] 16-bit, leading dim ld_cols
+ *   s_dev          device pointer to the fp32 logit scale s = exp(logit_scale)
+ */
+int64_t nans_clip_loss_fwd_phase_slots(int64_t n_loc, int64_t ncols, int64_t D);
+size_t nans_clip_loss_fwd_workspace_bytes(int64_t n_loc, int64_t total_slots);
+
+int nans_clip_loss_fwd_phase(const void* I_loc, const void* T_loc, int64_t ld_loc,
+                             const void* T_cols, const void* I_cols, int64_t ld_cols,
+                             int feat_dtype, int64_t n_loc, int64_t ncols, int64_t D,
+                             int64_t col_global_begin, int64_t label_begin, const float* s_dev,
+                             int flags, void* ws, size_t ws_bytes, int64_t slot_begin,
+                             void* stream);
+
+/*
+ * Merge the slots.  Outputs (all device, fp32):
+ *   lse_img_loc [n_loc]  log-sum-exp of row i of logits_per_image (natural log)
+ *   lse_txt_loc [n_loc]  log-sum-exp of row j of logits_per_text
+ *   scalars[8]: [0] sum_i (lse_img_i - logit_ii)     (x 1/(2N) summed over ranks = loss, part 1)
+ *               [1] sum_j (lse_txt_j - logit_jj)
+ *               [2] sum_i (E_softmax_img_i[cos] - cos_ii)   (d loss / d s numerator, part 1)
+ *               [3] sum_j (E_softmax_txt_j[cos] - cos_jj)
+ *               [4] #rows whose image->text argmax is the label   (if NANS_LOSS_WITH_ACC)
+ *               [5] #rows whose text->image argmax is the label
+ *               [6],[7] reserved (0)
+ */
+int nans_clip_loss_fwd_finalize(int64_t n_loc, int64_t total_slots, int64_t label_begin,
+                                const float* s_dev, int flags, void* ws, size_t ws_bytes,
+                                float* lse_img_loc, float* lse_txt_loc, float* scalars,
+                                void* stream);
+
+/* Convenience: one phase over all columns + finalize (single-GPU / after a blocking gather). */
+int nans_clip_loss_fwd(const void* I_loc, const void* T_loc, int64_t ld_loc, const void* T_all,
+                       const void* I_all, int64_t ld_all, int feat_dtype, int64_t n_loc,
+                       int64_t N, int64_t D, int64_t label_begin, const float* s_dev, int flags,
+                       float* lse_img_loc, float* lse_txt_loc, float* scalars, void* ws,
+                       size_t ws_bytes, void* stream);
+
+/* ---- (3) fused contrastive backward ------------------------------------------------------ */
+/*
+ * Replaces the autograd backward of train.py:87-115: recomputes the logit tiles, forms
+ * G = softmax_rows + softmax_cols - 2*delta on chip and contracts it with the column features.
+ *   dI_loc[r] = coef * sum_j G[r, j] * T_all[j],   dT_loc[r] = coef * sum_i G[i, r] * I_all[i]
+ *   coef = grad_out * s * grad_mult / (2 N)      (grad_mult = W under --gather-with-grad)
+ * for the rows [grad_row_begin, grad_row_begin + grad_row_count) of the local block (the chunk
+ * rows of the accumulate path, train.py:48-51; pass 0, n_loc for the plain path).
+ * d loss / d s is produced by the forward (scalars[2], [3]) — nothing to do here.
+ *
+ *   lse_img_all, lse_txt_all [N] fp32: the finalize outputs of all ranks, in global row order
+ *                                      (each 16-byte aligned)
+ *   grad_out_dev: device pointer to the fp32 upstream gradient of the loss
+ *   dI_loc, dT_loc [grad_row_count, D] contiguous, dtype out_dtype (NANS_F32/F16/BF16)
+ */
+size_t nans_clip_loss_bwd_workspace_bytes(int64_t grad_row_count, int64_t N, int64_t D);
+
+int nans_clip_loss_bwd(const void* I_loc, const void* T_loc, int64_t ld_loc, const void* T_all,
+                       const void* I_all, int64_t ld_all, int feat_dtype, int64_t n_loc,
+                       int64_t N, int64_t D, int64_t label_begin, const float* s_dev,
+                       const float* lse_img_all, const float* lse_txt_all,
+                       const float* grad_out_dev, float grad_mult, int64_t grad_row_begin,
+                       int64_t grad_row_count, void* dI_loc, void* dT_loc, int out_dtype,
+                       void* ws, size_t ws_bytes, void* stream);
+
+/* ---- (4) top-k inner-product retrieval ---------------------------------------------------- */
+/*
+ * Replaces cn_clip/eval/make_topk_predictions.py:71-85 (and _tr.py): for each query the k gallery
+ * rows with the largest inner product, ordered by (score descending, gallery index ascending) —
+ * the order Python's stable sorted(..., reverse=True) produces.
+ * Pass 1 streams the 16-bit gallery shard through tensor-core tiles keeping k_cand candidates per
+ * query; pass 2 rescores the candidates exactly in fp32 (Q32, G32; pass NULL for both to keep the
+ * 16-bit scores) and emits the top k.
+ *   Q16 [Q, D], G16 [G, D] 16-bit (feat_dtype); Q32 [Q, D], G32 [G, D] fp32 (contiguous)
+ *   k <= k_cand, k_cand in {16, 32}
+ *   out_scores [Q, k] fp32, out_index [Q, k] int64 = gallery_index_offset + row in this shard
+ *   (index -1 / score -inf pad rows when G < k)
+ */
+size_t nans_topk_ip_workspace_bytes(int64_t Q, int64_t G, int64_t D, int k_cand);
+
+int nans_topk_ip(const void* Q16, const void* G16, int feat_dtype, const float* Q32,
+                 const float* G32, int64_t Q, int64_t G, int64_t D, int k, int k_cand,
+                 int64_t gallery_index_offset, float* out_scores, int64_t* out_index, void* ws,
+                 size_t ws_bytes, void* stream);
+
+/*
+ * Merge per-shard results: in_scores/in_index [n_shards, Q, k] -> out [Q, k], same ordering rule.
+ */
+int nans_topk_merge(const float* in_scores, const int64_t* in_index, int n_shards, int64_t Q,
+                    int k, float* out_scores, int64_t* out_index, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NANS_CLIP_H_ */

@@ -1,0 +1,542 @@
+// strip_bwd.cu — kernel (3): fused contrastive backward.
+//
+// Replaces the autograd backward of cn_clip/training/train.py:87-115.  For a block of 128 local
+// rows A (image or text features) and every 64-column tile B_j of the gathered other modality:
+//   MMA1 : S_j = A * B_j^T                      (recomputed logits / s, fp32 in TMEM)
+//   warps: G_j = 2^12 * ( exp(s S - lse_row) + exp(s S - lse_col[j]) - 2 delta_label )  -> fp16,
+//          written back into TMEM over S_j (tcgen05.st), never to shared or global memory
+//   MMA2 : dA[:, slice] += G_j * B_j[:, slice]  (A operand from TMEM, B_j re-used from smem as an
+//          MN-major operand: the same swizzled tile that fed MMA1)
+// The fp32 dA accumulator for 128 rows x D does not fit TMEM next to S (D = 512 alone is all 512
+// columns), so a unit (= one CTA) owns a 256-feature slice of the output and the logits are
+// recomputed once per slice ("pass").  unit = (strip, row block, pass, column split).
+//
+// TMEM: [0,256) dA slice | [256,320) S/G buffer 0 | [320,384) S/G buffer 1.
+// SMEM: A block resident (D <= 512) or streamed in 16 KB chunks; B chunks (64 rows x 64 features,
+//       8 KB) go either through a stream ring (features outside the slice: MMA1 only) or into one
+//       of two 32 KB hold buffers (features of the slice: MMA1, then MMA2 one tile later).
+//
+// Roofline: tensor cores.  Algorithmic flops = 4 * rows * N * D per strip (S recompute excluded).
+#include <stdlib.h>
+
+#include "common.cuh"
+
+namespace nans {
+namespace {
+
+constexpr int BM = 128;
+constexpr int KT = 64;
+constexpr int BK = 64;
+constexpr int SLICE = 256;
+constexpr int A_CHUNK = BM * BK * 2;           // 16 KB
+constexpr int B_CHUNK = KT * BK * 2;           // 8 KB
+constexpr int HOLD_CHUNKS = SLICE / BK;        // 4
+constexpr int HOLD_BYTES = HOLD_CHUNKS * B_CHUNK;  // 32 KB
+constexpr int NH = 2;
+constexpr int MAX_NA = 6;
+constexpr int MAX_NS = 12;
+constexpr int NUM_THREADS = 256;
+constexpr int TMEM_COLS = 512;
+constexpr int TMEM_S = 256;
+constexpr int BAR_BYTES = 512;
+constexpr size_t SMEM_CAP = 227 * 1024;
+constexpr float kGShiftLog2 = 12.0f;  // G is carried as fp16 scaled by 2^12 (|G| <= 2 -> 8192)
+
+struct BwdPlan {
+  bool a_resident;
+  int na, ns;
+  size_t bytes;
+};
+
+BwdPlan plan_bwd(int kchunks) {
+  BwdPlan p;
+  const size_t cap = SMEM_CAP - 1024 - BAR_BYTES;
+  const size_t hold = static_cast<size_t>(NH) * HOLD_BYTES;
+  const size_t a_res = static_cast<size_t>(kchunks) * A_CHUNK;
+  if (a_res + hold + 2 * B_CHUNK <= cap) {
+    p.a_resident = true;
+    p.na = 0;
+    p.ns = static_cast<int>((cap - a_res - hold) / B_CHUNK);
+    if (p.ns > MAX_NS) p.ns = MAX_NS;
+    p.bytes = a_res + hold + static_cast<size_t>(p.ns) * B_CHUNK + BAR_BYTES + 1024;
+  } else {
+    p.a_resident = false;
+    p.na = 4;
+    p.ns = static_cast<int>((cap - hold - static_cast<size_t>(p.na) * A_CHUNK) / B_CHUNK);
+    if (p.ns > MAX_NS) p.ns = MAX_NS;
+    p.bytes = hold + static_cast<size_t>(p.na) * A_CHUNK + static_cast<size_t>(p.ns) * B_CHUNK +
+              BAR_BYTES + 1024;
+  }
+  return p;
+}
+
+struct BwdParams {
+  int row_begin, row_end;  // rows of the local block that receive gradient
+  int ncols, D, kchunks;
+  int nrb, npass, nsplit, ntiles;
+  int na, ns;
+  uint32_t idesc1_fmt;  // operand format bits (0 = f16, 1 = bf16)
+  uint32_t g_fmt;       // format G is written in (0 = f16, 1 = bf16)
+  int label_shift;      // label column of local row r = r + label_shift
+  const float* s_dev;
+  const float* grad_out_dev;
+  float coef_host;  // grad_mult / (2 N) / 2^12
+  const float* lse_row[2];  // per strip: lse of the local rows (indexed by local row)
+  const float* lse_col[2];  // per strip: lse of all columns
+  float* out[2];            // per strip: fp32 [row_end-row_begin, D]
+  int accumulate;           // 1: atomicAdd into out (column splits), 0: plain stores
+};
+
+template <bool A_RES>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+clip_bwd_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmB0,
+                const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
+                const BwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* smA = smem;  // resident block or ring
+  uint8_t* smH = smA + static_cast<size_t>(A_RES ? p.kchunks : p.na) * A_CHUNK;
+  uint8_t* smS = smH + static_cast<size_t>(NH) * HOLD_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smS + static_cast<size_t>(p.ns) * B_CHUNK);
+  uint64_t* fullA = bars;
+  uint64_t* emptyA = fullA + MAX_NA;
+  uint64_t* fullS = emptyA + MAX_NA;
+  uint64_t* emptyS = fullS + MAX_NS;
+  uint64_t* fullH = emptyS + MAX_NS;  // [NH][HOLD_CHUNKS]
+  uint64_t* emptyH = fullH + NH * HOLD_CHUNKS;
+  uint64_t* a_full = emptyH + NH;
+  uint64_t* s_full = a_full + 1;   // [2]
+  uint64_t* g_ready = s_full + 2;  // [2]
+  uint64_t* da_full = g_ready + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(da_full + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // ---- unit decode ----
+  int unit = blockIdx.x;
+  const int split = unit % p.nsplit;
+  unit /= p.nsplit;
+  const int pass = unit % p.npass;
+  unit /= p.npass;
+  const int rb = unit % p.nrb;
+  const int strip = unit / p.nrb;
+
+  const CUtensorMap* tmA = strip == 0 ? &tmA0 : &tmA1;
+  const CUtensorMap* tmB = strip == 0 ? &tmB0 : &tmB1;
+  const int row0 = p.row_begin + rb * BM;
+  const int tile_begin = static_cast<int>(static_cast<long long>(split) * p.ntiles / p.nsplit);
+  const int tile_end = static_cast<int>(static_cast<long long>(split + 1) * p.ntiles / p.nsplit);
+  const int ntiles = tile_end - tile_begin;
+  const int slice_c0 = pass * HOLD_CHUNKS;                      // first chunk of the slice
+  const int slice_nc = min(HOLD_CHUNKS, p.kchunks - slice_c0);  // chunks in the slice
+  const int slice_w = slice_nc * BK;                            // MMA2 N
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(tmA);
+    tma_prefetch_desc(tmB);
+    for (int i = 0; i < MAX_NA; ++i) { mbar_init(&fullA[i], 1); mbar_init(&emptyA[i], 1); }
+    for (int i = 0; i < MAX_NS; ++i) { mbar_init(&fullS[i], 1); mbar_init(&emptyS[i], 1); }
+    for (int i = 0; i < NH * HOLD_CHUNKS; ++i) mbar_init(&fullH[i], 1);
+    for (int i = 0; i < NH; ++i) mbar_init(&emptyH[i], 1);
+    mbar_init(a_full, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&g_ready[i], 4); }
+    mbar_init(da_full, 1);
+    fence_barrier_init();
+  } else if (warp == 2) {
+    tmem_alloc(tmem_ptr, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------- TMA producer ----------------
+      if (A_RES) {
+        mbar_arrive_expect_tx(a_full, static_cast<uint32_t>(p.kchunks) * A_CHUNK);
+        for (int c = 0; c < p.kchunks; ++c)
+          tma_load_2d(smA + static_cast<size_t>(c) * A_CHUNK, tmA, a_full, c * BK, row0);
+      }
+      int sa = 0, ss = 0;
+      uint32_t pa = 0, ps = 0;
+      for (int t = 0; t < ntiles; ++t) {
+        const int col0 = (tile_begin + t) * KT;
+        const int h = t % NH;
+        const uint32_t ph = static_cast<uint32_t>(t / NH) & 1u;
+        for (int c = 0; c < p.kchunks; ++c) {
+          if (c >= slice_c0 && c < slice_c0 + slice_nc) continue;
+          if (!A_RES) {
+            mbar_wait(&emptyA[sa], pa ^ 1u);
+            mbar_arrive_expect_tx(&fullA[sa], A_CHUNK);
+            tma_load_2d(smA + static_cast<size_t>(sa) * A_CHUNK, tmA, &fullA[sa], c * BK, row0);
+            if (++sa == p.na) { sa = 0; pa ^= 1u; }
+          }
+          mbar_wait(&emptyS[ss], ps ^ 1u);
+          mbar_arrive_expect_tx(&fullS[ss], B_CHUNK);
+          tma_load_2d(smS + static_cast<size_t>(ss) * B_CHUNK, tmB, &fullS[ss], c * BK, col0);
+          if (++ss == p.ns) { ss = 0; ps ^= 1u; }
+        }
+        mbar_wait(&emptyH[h], ph ^ 1u);
+        for (int ci = 0; ci < slice_nc; ++ci) {
+          const int c = slice_c0 + ci;
+          if (!A_RES) {
+            mbar_wait(&emptyA[sa], pa ^ 1u);
+            mbar_arrive_expect_tx(&fullA[sa], A_CHUNK);
+            tma_load_2d(smA + static_cast<size_t>(sa) * A_CHUNK, tmA, &fullA[sa], c * BK, row0);
+            if (++sa == p.na) { sa = 0; pa ^= 1u; }
+          }
+          uint64_t* fb = &fullH[h * HOLD_CHUNKS + ci];
+          mbar_arrive_expect_tx(fb, B_CHUNK);
+          tma_load_2d(smH + static_cast<size_t>(h) * HOLD_BYTES + static_cast<size_t>(ci) * B_CHUNK,
+                      tmB, fb, c * BK, col0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ---------------- MMA issuer ----------------
+      const uint32_t fmt = p.idesc1_fmt;
+      const uint32_t idesc1 = make_idesc(fmt, fmt, 0, 0, BM, KT);
+      const uint32_t idesc2 = make_idesc(p.g_fmt, fmt, 0, /*B MN-major*/ 1, BM, slice_w);
+      if (A_RES) {
+        mbar_wait(a_full, 0);
+        tc_fence_after();
+      }
+      int sa = 0, ss = 0;
+      uint32_t pa = 0, ps = 0;
+
+      auto issue_mma2 = [&](int u) {
+        const int gb = u & 1;
+        mbar_wait(&g_ready[gb], static_cast<uint32_t>(u >> 1) & 1u);
+        tc_fence_after();
+        const int h = u % NH;
+        const uint32_t hb = smem_u32(smH + static_cast<size_t>(h) * HOLD_BYTES);
+#pragma unroll
+        for (int kk = 0; kk < KT / 16; ++kk) {
+          const uint64_t bd = make_smem_desc(hb + kk * 16 * 128, B_CHUNK, 1024);
+          mma_ts(tmem_base, tmem_base + TMEM_S + gb * KT + kk * 8, bd, idesc2,
+                 (u > 0 || kk > 0) ? 1u : 0u);
+        }
+        tc_commit(&emptyH[h]);
+      };
+
+      for (int t = 0; t < ntiles; ++t) {
+        const uint32_t d_S = tmem_base + TMEM_S + (t & 1) * KT;
+        const int h = t % NH;
+        const uint32_t ph = static_cast<uint32_t>(t / NH) & 1u;
+        uint32_t acc = 0;
+        for (int c = 0; c < p.kchunks; ++c) {
+          if (c >= slice_c0 && c < slice_c0 + slice_nc) continue;
+          if (!A_RES) {
+            mbar_wait(&fullA[sa], pa);
+          }
+          mbar_wait(&fullS[ss], ps);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smA + static_cast<size_t>(A_RES ? c : sa) * A_CHUNK);
+          const uint32_t b_addr = smem_u32(smS + static_cast<size_t>(ss) * B_CHUNK);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            mma_ss(d_S, make_smem_desc(a_addr + k * 32, 16, 1024),
+                   make_smem_desc(b_addr + k * 32, 16, 1024), idesc1, acc);
+            acc = 1;
+          }
+          tc_commit(&emptyS[ss]);
+          if (++ss == p.ns) { ss = 0; ps ^= 1u; }
+          if (!A_RES) {
+            tc_commit(&emptyA[sa]);
+            if (++sa == p.na) { sa = 0; pa ^= 1u; }
+          }
+        }
+        for (int ci = 0; ci < slice_nc; ++ci) {
+          const int c = slice_c0 + ci;
+          if (!A_RES) {
+            mbar_wait(&fullA[sa], pa);
+          }
+          mbar_wait(&fullH[h * HOLD_CHUNKS + ci], ph);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smA + static_cast<size_t>(A_RES ? c : sa) * A_CHUNK);
+          const uint32_t b_addr = smem_u32(smH + static_cast<size_t>(h) * HOLD_BYTES +
+                                           static_cast<size_t>(ci) * B_CHUNK);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            mma_ss(d_S, make_smem_desc(a_addr + k * 32, 16, 1024),
+                   make_smem_desc(b_addr + k * 32, 16, 1024), idesc1, acc);
+            acc = 1;
+          }
+          if (!A_RES) {
+            tc_commit(&emptyA[sa]);
+            if (++sa == p.na) { sa = 0; pa ^= 1u; }
+          }
+        }
+        tc_commit(&s_full[t & 1]);
+        if (t > 0) issue_mma2(t - 1);
+      }
+      issue_mma2(ntiles - 1);
+      tc_commit(da_full);
+    }
+  } else if (warp >= 4) {
+    // ---------------- softmax-gradient warps: thread = row ----------------
+    const int wq = warp & 3;
+    const uint32_t lane_base = static_cast<uint32_t>(wq * 32) << 16;
+    const int row = row0 + wq * 32 + lane;
+    const bool valid = row < p.row_end;
+    const float s = __ldg(p.s_dev);
+    const float c = s * kLog2e;
+    // 2^12 * exp(s cos - lse) = 2^(cos * c - (lse * log2e - 12))
+    const float lr2 = valid ? fmaf(__ldg(p.lse_row[strip] + row), kLog2e, -kGShiftLog2) : INFINITY;
+    const float* lse_col = p.lse_col[strip];
+    const int label = row + p.label_shift;
+    const int warp_label_lo = label - lane;
+    const bool g_bf16 = p.g_fmt != 0;
+
+    for (int t = 0; t < ntiles; ++t) {
+      const int sb = t & 1;
+      mbar_wait(&s_full[sb], static_cast<uint32_t>(t >> 1) & 1u);
+      tc_fence_after();
+      const int col0 = (tile_begin + t) * KT;
+      const uint32_t s_addr = tmem_base + lane_base + TMEM_S + sb * KT;
+      const bool has_label = (warp_label_lo < col0 + KT) && (warp_label_lo + 31 >= col0);
+      const bool tail = col0 + KT > p.ncols;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t r[32];
+        tmem_ld32(s_addr + half * 32, r);
+        float lc2[32];
+        const int cb = col0 + half * 32;
+        if (!tail) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 f = __ldg(reinterpret_cast<const float4*>(lse_col + cb) + q);
+            lc2[4 * q + 0] = f.x; lc2[4 * q + 1] = f.y; lc2[4 * q + 2] = f.z; lc2[4 * q + 3] = f.w;
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < 32; ++k) lc2[k] = __ldg(lse_col + min(cb + k, p.ncols - 1));
+        }
+        tmem_wait_ld();
+        uint32_t g16[16];
+#pragma unroll
+        for (int k = 0; k < 32; k += 2) {
+          float g[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const float cosv = __uint_as_float(r[k + e]);
+            const float lcv = fmaf(lc2[k + e], kLog2e, -kGShiftLog2);
+            g[e] = fast_exp2(fmaf(cosv, c, -lr2)) + fast_exp2(fmaf(cosv, c, -lcv));
+            if (has_label && cb + k + e == label) g[e] -= 8192.0f;  // 2 * 2^12
+          }
+          if (g_bf16) {
+            const __nv_bfloat162 hh = __floats2bfloat162_rn(g[0], g[1]);
+            g16[k >> 1] = *reinterpret_cast<const uint32_t*>(&hh);
+          } else {
+            const __half2 hh = __floats2half2_rn(g[0], g[1]);
+            g16[k >> 1] = *reinterpret_cast<const uint32_t*>(&hh);
+          }
+        }
+        tmem_st16(s_addr + half * 16, g16);
+      }
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&g_ready[sb]);
+    }
+
+    // ---- write the dA slice ----
+    mbar_wait(da_full, 0);
+    tc_fence_after();
+    const float coef = __ldg(p.grad_out_dev) * s * p.coef_host;
+    float* out = p.out[strip] + static_cast<long long>(row - p.row_begin) * p.D + pass * SLICE;
+    for (int ch = 0; ch < slice_w / 32; ++ch) {
+      uint32_t r[32];
+      tmem_ld32(tmem_base + lane_base + ch * 32, r);
+      tmem_wait_ld();
+      if (valid) {
+        const int f0 = pass * SLICE + ch * 32;
+        if (p.accumulate) {
+#pragma unroll
+          for (int k = 0; k < 32; ++k)
+            if (f0 + k < p.D) atomicAdd(out + ch * 32 + k, __uint_as_float(r[k]) * coef);
+        } else if (f0 + 32 <= p.D) {
+#pragma unroll
+          for (int k = 0; k < 32; k += 4)
+            *reinterpret_cast<float4*>(out + ch * 32 + k) =
+                make_float4(__uint_as_float(r[k]) * coef, __uint_as_float(r[k + 1]) * coef,
+                            __uint_as_float(r[k + 2]) * coef, __uint_as_float(r[k + 3]) * coef);
+        } else {
+#pragma unroll
+          for (int k = 0; k < 32; ++k)
+            if (f0 + k < p.D) out[ch * 32 + k] = __uint_as_float(r[k]) * coef;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// fp32 -> 16-bit cast of the gradient when the caller wants fp16 / bf16 outputs
+__global__ void cast_out_kernel(const float* __restrict__ in, void* __restrict__ out, int out_dtype,
+                                long long n) {
+  const long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 2;
+  if (i + 1 < n) {
+    const float2 v = *reinterpret_cast<const float2*>(in + i);
+    if (out_dtype == NANS_BF16)
+      *reinterpret_cast<__nv_bfloat162*>(static_cast<__nv_bfloat16*>(out) + i) = __floats2bfloat162_rn(v.x, v.y);
+    else
+      *reinterpret_cast<__half2*>(static_cast<__half*>(out) + i) = __floats2half2_rn(v.x, v.y);
+  } else if (i < n) {
+    if (out_dtype == NANS_BF16) static_cast<__nv_bfloat16*>(out)[i] = __float2bfloat16(in[i]);
+    else static_cast<__half*>(out)[i] = __float2half(in[i]);
+  }
+}
+
+int choose_bwd_nsplit(int64_t rows, int64_t N, int npass) {
+  const int64_t base = 2 * ceil_div(rows, BM) * npass;
+  const int64_t ntiles = ceil_div(N, KT);
+  const int sms = sm_count();
+  int best = 1;
+  double best_cost = 1e300;
+  const int64_t max_ns = ntiles / 8 < 1 ? 1 : (ntiles / 8 > 32 ? 32 : ntiles / 8);
+  for (int64_t ns = 1; ns <= max_ns; ++ns) {
+    const double waves = static_cast<double>(ceil_div(base * ns, sms));
+    // per-unit overhead: prologue + A block load + dA write-out, worth about 6 tiles
+    const double cost = waves * (static_cast<double>(ceil_div(ntiles, ns)) + 6.0);
+    if (cost < best_cost - 1e-9) {
+      best_cost = cost;
+      best = static_cast<int>(ns);
+    }
+  }
+  return best;
+}
+
+}  // namespace
+}  // namespace nans
+
+using namespace nans;
+
+extern "C" size_t nans_clip_loss_bwd_workspace_bytes(int64_t grad_row_count, int64_t N, int64_t D) {
+  (void)N;
+  if (grad_row_count <= 0 || D <= 0) return 256;
+  return 2 * align_up(static_cast<size_t>(grad_row_count) * D * 4, 256) + 256;
+}
+
+extern "C" int nans_clip_loss_bwd(const void* I_loc, const void* T_loc, int64_t ld_loc,
+                                  const void* T_all, const void* I_all, int64_t ld_all,
+                                  int feat_dtype, int64_t n_loc, int64_t N, int64_t D,
+                                  int64_t label_begin, const float* s_dev, const float* lse_img_all,
+                                  const float* lse_txt_all, const float* grad_out_dev,
+                                  float grad_mult, int64_t grad_row_begin, int64_t grad_row_count,
+                                  void* dI_loc, void* dT_loc, int out_dtype, void* ws,
+                                  size_t ws_bytes, void* stream) {
+  int rc = check_device();
+  if (rc != NANS_OK) return rc;
+  NANS_REQUIRE(feat_dtype == NANS_F16 || feat_dtype == NANS_BF16,
+               "loss_bwd: feat_dtype must be NANS_F16 or NANS_BF16");
+  NANS_REQUIRE(out_dtype == NANS_F32 || out_dtype == NANS_F16 || out_dtype == NANS_BF16,
+               "loss_bwd: bad out_dtype");
+  NANS_REQUIRE(n_loc > 0 && N > 0 && D > 0 && D % 8 == 0, "loss_bwd: bad sizes (D must be a multiple of 8)");
+  NANS_REQUIRE(n_loc < (1ll << 30) && N < (1ll << 30) && D <= 8192, "loss_bwd: size too large");
+  NANS_REQUIRE(grad_row_begin >= 0 && grad_row_count >= 0 && grad_row_begin + grad_row_count <= n_loc,
+               "loss_bwd: gradient rows [%lld, +%lld) outside the local block of %lld rows",
+               (long long)grad_row_begin, (long long)grad_row_count, (long long)n_loc);
+  NANS_REQUIRE(label_begin >= 0 && label_begin + n_loc <= N, "loss_bwd: labels outside [0, N)");
+  if (grad_row_count == 0) return NANS_OK;
+  NANS_REQUIRE(I_loc && T_loc && T_all && I_all && s_dev && lse_img_all && lse_txt_all &&
+                   grad_out_dev && dI_loc && dT_loc,
+               "loss_bwd: null pointer");
+  NANS_REQUIRE(ld_loc >= D && ld_all >= D, "loss_bwd: leading dimension smaller than D");
+  NANS_REQUIRE((reinterpret_cast<uintptr_t>(lse_img_all) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(lse_txt_all) & 15) == 0,
+               "loss_bwd: lse arrays must be 16-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+
+  const int kchunks = static_cast<int>(ceil_div(D, BK));
+  const int npass = static_cast<int>(ceil_div(kchunks, HOLD_CHUNKS));
+  const BwdPlan plan = plan_bwd(kchunks);
+  const int nsplit = choose_bwd_nsplit(grad_row_count, N, npass);
+
+  const size_t out_bytes = static_cast<size_t>(grad_row_count) * D * 4;
+  float* out32[2];
+  if (out_dtype == NANS_F32) {
+    NANS_REQUIRE((reinterpret_cast<uintptr_t>(dI_loc) & 15) == 0 && (reinterpret_cast<uintptr_t>(dT_loc) & 15) == 0,
+                 "loss_bwd: outputs must be 16-byte aligned");
+    out32[0] = static_cast<float*>(dI_loc);
+    out32[1] = static_cast<float*>(dT_loc);
+  } else {
+    const size_t need = nans_clip_loss_bwd_workspace_bytes(grad_row_count, N, D);
+    if (ws == nullptr || ws_bytes < need) {
+      set_error("loss_bwd: workspace %zu < %zu bytes", ws_bytes, need);
+      return NANS_ERR_WORKSPACE;
+    }
+    NANS_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 15) == 0, "loss_bwd: workspace must be 16-byte aligned");
+    out32[0] = static_cast<float*>(ws);
+    out32[1] = reinterpret_cast<float*>(static_cast<uint8_t*>(ws) + align_up(out_bytes, 256));
+  }
+  if (nsplit > 1) {
+    NANS_CUDA_OK(cudaMemsetAsync(out32[0], 0, out_bytes, st));
+    NANS_CUDA_OK(cudaMemsetAsync(out32[1], 0, out_bytes, st));
+  }
+
+  CUtensorMap tmA0, tmB0, tmA1, tmB1;
+  if ((rc = make_tmap_16b(&tmA0, I_loc, feat_dtype, n_loc, D, ld_loc, BM)) != NANS_OK) return rc;
+  if ((rc = make_tmap_16b(&tmB0, T_all, feat_dtype, N, D, ld_all, KT)) != NANS_OK) return rc;
+  if ((rc = make_tmap_16b(&tmA1, T_loc, feat_dtype, n_loc, D, ld_loc, BM)) != NANS_OK) return rc;
+  if ((rc = make_tmap_16b(&tmB1, I_all, feat_dtype, N, D, ld_all, KT)) != NANS_OK) return rc;
+
+  BwdParams p;
+  p.row_begin = static_cast<int>(grad_row_begin);
+  p.row_end = static_cast<int>(grad_row_begin + grad_row_count);
+  p.ncols = static_cast<int>(N);
+  p.D = static_cast<int>(D);
+  p.kchunks = kchunks;
+  p.nrb = static_cast<int>(ceil_div(grad_row_count, BM));
+  p.npass = npass;
+  p.nsplit = nsplit;
+  p.ntiles = static_cast<int>(ceil_div(N, KT));
+  p.na = plan.na;
+  p.ns = plan.ns;
+  p.idesc1_fmt = static_cast<uint32_t>(idesc_fmt(feat_dtype));
+  // tcgen05.mma kind::f16 wants A and B in the same 16-bit format (a mixed f16 x bf16 descriptor
+  // faults as an illegal instruction on sm_100a), so G is written in the features' format.
+  // NANS_BWD_MIXED_G=1 forces f16 G regardless (bring-up experiment).
+  {
+    const char* e = getenv("NANS_BWD_MIXED_G");
+    p.g_fmt = (e && e[0] == '1') ? 0u : p.idesc1_fmt;
+  }
+  p.label_shift = static_cast<int>(label_begin);
+  p.s_dev = s_dev;
+  p.grad_out_dev = grad_out_dev;
+  p.coef_host = grad_mult / (2.0f * static_cast<float>(N)) / 4096.0f;
+  p.lse_row[0] = lse_img_all + label_begin;
+  p.lse_row[1] = lse_txt_all + label_begin;
+  p.lse_col[0] = lse_txt_all;
+  p.lse_col[1] = lse_img_all;
+  p.out[0] = out32[0];
+  p.out[1] = out32[1];
+  p.accumulate = nsplit > 1 ? 1 : 0;
+
+  auto kern = plan.a_resident ? clip_bwd_kernel<true> : clip_bwd_kernel<false>;
+  NANS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    static_cast<int>(plan.bytes)));
+  const unsigned grid = static_cast<unsigned>(2 * p.nrb * p.npass * p.nsplit);
+  kern<<<grid, NUM_THREADS, plan.bytes, st>>>(tmA0, tmB0, tmA1, tmB1, p);
+  NANS_CUDA_OK(cudaGetLastError());
+
+  if (out_dtype != NANS_F32) {
+    const long long n = static_cast<long long>(grad_row_count) * D;
+    const unsigned g = static_cast<unsigned>(ceil_div(ceil_div(n, 2), 256));
+    cast_out_kernel<<<g, 256, 0, st>>>(out32[0], dI_loc, out_dtype, n);
+    cast_out_kernel<<<g, 256, 0, st>>>(out32[1], dT_loc, out_dtype, n);
+    NANS_CUDA_OK(cudaGetLastError());
+  }
+  return NANS_OK;
+}

@@ -1,0 +1,444 @@
+// strip_fwd.cu — kernel (2): fused contrastive forward.
+//
+// Replaces cn_clip/training/train.py:87-88 / 103-104 (the (s*I)@T^T logits), :109-115 (two
+// CrossEntropyLoss against arange labels) and :117-121 (argmax accuracy).  The logits matrix is
+// never written: every 128x256 tile lives in TMEM and is consumed by an online log-sum-exp.
+//
+// Per rank two strips are swept (strip 0: I_loc x T_cols^T, strip 1: T_loc x I_cols^T); each row
+// keeps, in the log2 domain with t = cos * s * log2(e):
+//     m = running max t,  l = sum 2^(t - m),  w = sum 2^(t - m) * cos        (for d loss / d s)
+// plus cos at the label column and (optionally) the running arg-max.  A unit (= one CTA) is
+// (strip, 128-row block, column split); units write partial statistics into workspace slots, and
+// clip_fwd_finalize_kernel merges the slots into lse, loss / d(scale) sums and hit counts.
+//
+// Roofline: tensor cores.  Algorithmic flops per unit row block = 2 * 128 * ncols * D per strip.
+#include "strip_sweep.cuh"
+
+namespace nans {
+namespace {
+
+using namespace sweep;
+
+constexpr float kMasked = -1e30f;
+
+struct FwdParams {
+  int n_loc, ncols, kchunks, stages;
+  uint32_t idesc;
+  int nrb, nsplit, ntiles;
+  int label_shift;  // label column of row r in phase coordinates = r + label_shift
+  int col_global_begin;  // global column of phase column 0
+  const float* s_dev;
+  float* part_m;
+  float* part_l;
+  float* part_w;
+  float* part_bv;
+  int* part_bi;
+  float* diag;
+  int slot_begin;
+  long long slot_stride;  // floats between consecutive slots
+};
+
+template <bool WITH_ACC>
+struct LseEpi {
+  float c;  // s * log2(e)
+  int ncols;
+  int label;          // this thread's label column (phase coordinates)
+  int warp_label_lo;  // label column of lane 0 of this warp
+  float m, l[4], w[4], diag, bv;
+  int bi;
+
+  __device__ __forceinline__ void init(float c_, int ncols_, int label_, int lane) {
+    c = c_;
+    ncols = ncols_;
+    label = label_;
+    warp_label_lo = label_ - lane;
+    m = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) l[i] = w[i] = 0.f;
+    diag = 0.f;
+    bv = -INFINITY;
+    bi = -1;
+  }
+
+  __device__ __forceinline__ void tile(uint32_t taddr, int tile_idx) {
+    const int col0 = tile_idx * BN;
+    const bool tail = col0 + BN > ncols;
+    const bool has_label = (warp_label_lo < col0 + BN) && (warp_label_lo + 31 >= col0);
+#pragma unroll 1
+    for (int ch = 0; ch < BN / 32; ++ch) {
+      uint32_t r[32];
+      tmem_ld32(taddr + ch * 32, r);
+      tmem_wait_ld();
+      const int cb = col0 + ch * 32;
+      float v[32];
+#pragma unroll
+      for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(r[k]);
+      if (tail) {
+#pragma unroll
+        for (int k = 0; k < 32; ++k)
+          if (cb + k >= ncols) v[k] = kMasked;
+      }
+      if (has_label) {
+#pragma unroll
+        for (int k = 0; k < 32; ++k)
+          if (cb + k == label) diag = v[k];
+      }
+      if (WITH_ACC) {
+#pragma unroll
+        for (int k = 0; k < 32; ++k)
+          if (v[k] > bv) {  // strict: the first maximum wins, as torch.argmax does
+            bv = v[k];
+            bi = cb + k;
+          }
+      }
+      float mx[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) mx[i] = v[i];
+#pragma unroll
+      for (int k = 4; k < 32; ++k) mx[k & 3] = fmaxf(mx[k & 3], v[k]);
+      const float cmax = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+      const float m_new = fmaxf(m, cmax * c);
+      const float alpha = fast_exp2(m - m_new);
+      m = m_new;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        l[i] *= alpha;
+        w[i] *= alpha;
+      }
+#pragma unroll
+      for (int k = 0; k < 32; ++k) {
+        const float e = fast_exp2(fmaf(v[k], c, -m));
+        l[k & 3] += e;
+        w[k & 3] = fmaf(e, v[k], w[k & 3]);
+      }
+    }
+  }
+};
+
+template <bool A_RES, bool WITH_ACC>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+clip_fwd_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmB0,
+                const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
+                const FwdParams p) {
+  const int unit = blockIdx.x;
+  const int split = unit % p.nsplit;
+  const int rb = (unit / p.nsplit) % p.nrb;
+  const int strip = unit / (p.nsplit * p.nrb);
+
+  SweepArgs a;
+  a.tmA = strip == 0 ? &tmA0 : &tmA1;
+  a.tmB = strip == 0 ? &tmB0 : &tmB1;
+  a.row0 = rb * BM;
+  a.tile_begin = static_cast<int>(static_cast<long long>(split) * p.ntiles / p.nsplit);
+  a.tile_end = static_cast<int>(static_cast<long long>(split + 1) * p.ntiles / p.nsplit);
+  a.kchunks = p.kchunks;
+  a.stages = p.stages;
+  a.idesc = p.idesc;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int row = a.row0 + (warp & 3) * 32 + lane;
+
+  LseEpi<WITH_ACC> epi;
+  epi.init(__ldg(p.s_dev) * kLog2e, p.ncols, row + p.label_shift, lane);
+
+  run<A_RES>(a, epi);
+
+  if (warp >= 4 && row < p.n_loc) {
+    const long long idx = static_cast<long long>(p.slot_begin + split) * p.slot_stride +
+                          static_cast<long long>(strip) * p.n_loc + row;
+    p.part_m[idx] = epi.m;
+    p.part_l[idx] = (epi.l[0] + epi.l[1]) + (epi.l[2] + epi.l[3]);
+    p.part_w[idx] = (epi.w[0] + epi.w[1]) + (epi.w[2] + epi.w[3]);
+    if (WITH_ACC) {
+      p.part_bv[idx] = epi.bv;
+      p.part_bi[idx] = epi.bi < 0 ? -1 : epi.bi + p.col_global_begin;
+    }
+    const int cbeg = a.tile_begin * BN;
+    const int cend = min(a.tile_end * BN, p.ncols);
+    if (epi.label >= cbeg && epi.label < cend)
+      p.diag[static_cast<long long>(strip) * p.n_loc + row] = epi.diag;
+  }
+}
+
+// ---- finalize ------------------------------------------------------------------------------
+struct FinParams {
+  int n_loc, total_slots, with_acc;
+  long long slot_stride;
+  int label_begin;  // global label column of local row 0 (arg-max indices are global columns)
+  const float* s_dev;
+  const float* part_m;
+  const float* part_l;
+  const float* part_w;
+  const float* part_bv;
+  const int* part_bi;
+  const float* diag;
+  float* lse_img;
+  float* lse_txt;
+  double* block_part;  // [gridDim.x][6]
+  unsigned* counter;
+  float* scalars;  // [8]
+};
+
+__global__ void __launch_bounds__(256) clip_fwd_finalize_kernel(const FinParams p) {
+  __shared__ double red[6][8];
+  __shared__ bool is_last;
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int total = 2 * p.n_loc;
+  double acc[6] = {0, 0, 0, 0, 0, 0};
+  if (gid < total) {
+    const int strip = gid / p.n_loc;
+    const int row = gid - strip * p.n_loc;
+    float M = -INFINITY;
+    for (int s = 0; s < p.total_slots; ++s) M = fmaxf(M, p.part_m[s * p.slot_stride + gid]);
+    float L = 0.f, Wt = 0.f, bv = -INFINITY;
+    int bi = -1;
+    for (int s = 0; s < p.total_slots; ++s) {
+      const long long i = s * p.slot_stride + gid;
+      const float sc = exp2f(p.part_m[i] - M);
+      L = fmaf(p.part_l[i], sc, L);
+      Wt = fmaf(p.part_w[i], sc, Wt);
+      if (p.with_acc) {
+        const float v = p.part_bv[i];
+        const int b = p.part_bi[i];
+        if (v > bv || (v == bv && b >= 0 && (bi < 0 || b < bi))) {
+          bv = v;
+          bi = b;
+        }
+      }
+    }
+    const float sc = __ldg(p.s_dev);
+    const float lse = (M + log2f(L)) * kLn2;
+    const float cosd = p.diag[gid];
+    (strip == 0 ? p.lse_img : p.lse_txt)[row] = lse;
+    acc[strip] = static_cast<double>(lse) - static_cast<double>(sc) * cosd;
+    acc[2 + strip] = static_cast<double>(Wt) / static_cast<double>(L) - cosd;
+    if (p.with_acc) acc[4 + strip] = (bi == p.label_begin + row) ? 1.0 : 0.0;
+  }
+  // block reduction (fixed order -> deterministic)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int q = 0; q < 6; ++q) {
+    double v = acc[q];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) red[q][warp] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 6) {
+    double v = 0;
+    for (int i = 0; i < 8; ++i) v += red[threadIdx.x][i];
+    p.block_part[blockIdx.x * 6 + threadIdx.x] = v;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned done = atomicAdd(p.counter, 1u);
+    is_last = (done == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    if (threadIdx.x < 8) {
+      double v = 0;
+      if (threadIdx.x < 6)
+        for (unsigned b = 0; b < gridDim.x; ++b)
+          v += *(volatile double*)&p.block_part[b * 6 + threadIdx.x];
+      p.scalars[threadIdx.x] = static_cast<float>(v);
+    }
+    if (threadIdx.x == 0) *p.counter = 0;
+  }
+}
+
+// ---- workspace layout ------------------------------------------------------------------------
+// [diag 2*n_loc][block partials][counter][slot 0][slot 1]...   slot = {m, l, w, bv, bi} x 2*n_loc
+// Slot addresses do not depend on how many slots follow, so phases need not know the total.
+struct FwdWs {
+  float *part_m, *part_l, *part_w, *part_bv, *diag;
+  int* part_bi;
+  double* block_part;
+  unsigned* counter;
+  long long slot_stride;  // floats between the same array of consecutive slots
+  size_t bytes;
+};
+
+FwdWs carve_fwd_ws(void* ws, int64_t n_loc, int64_t total_slots) {
+  FwdWs w;
+  uint8_t* p = static_cast<uint8_t*>(ws);
+  size_t off = 0;
+  auto take = [&](size_t n) {
+    uint8_t* q = p ? p + off : nullptr;
+    off += n;
+    return q;
+  };
+  const size_t part = align_up(static_cast<size_t>(2) * n_loc * 4, 256);
+  w.diag = reinterpret_cast<float*>(take(part));
+  const size_t nblocks = static_cast<size_t>(ceil_div(2 * n_loc, 256));
+  w.block_part = reinterpret_cast<double*>(take(align_up(nblocks * 6 * 8, 256)));
+  w.counter = reinterpret_cast<unsigned*>(take(256));
+  w.part_m = reinterpret_cast<float*>(take(0));
+  w.part_l = w.part_m ? w.part_m + part / 4 : nullptr;
+  w.part_w = w.part_m ? w.part_m + 2 * (part / 4) : nullptr;
+  w.part_bv = w.part_m ? w.part_m + 3 * (part / 4) : nullptr;
+  w.part_bi = w.part_m ? reinterpret_cast<int*>(w.part_m + 4 * (part / 4)) : nullptr;
+  w.slot_stride = static_cast<long long>(5 * (part / 4));
+  off += static_cast<size_t>(total_slots) * 5 * part;
+  w.bytes = off;
+  return w;
+}
+
+int choose_nsplit(int64_t n_loc, int64_t ncols) {
+  const int64_t base = 2 * ceil_div(n_loc, BM);
+  const int64_t ntiles = ceil_div(ncols, BN);
+  const int sms = sm_count();
+  int best = 1;
+  double best_cost = 1e300;
+  const int64_t max_ns = ntiles < 32 ? ntiles : 32;
+  for (int64_t ns = 1; ns <= max_ns; ++ns) {
+    const double waves = static_cast<double>(ceil_div(base * ns, sms));
+    const double cost = waves * (static_cast<double>(ceil_div(ntiles, ns)) + 0.75);
+    if (cost < best_cost - 1e-9) {
+      best_cost = cost;
+      best = static_cast<int>(ns);
+    }
+  }
+  return best;
+}
+
+}  // namespace
+}  // namespace nans
+
+using namespace nans;
+
+extern "C" int64_t nans_clip_loss_fwd_phase_slots(int64_t n_loc, int64_t ncols, int64_t D) {
+  (void)D;
+  if (n_loc <= 0 || ncols <= 0) return 0;
+  return choose_nsplit(n_loc, ncols);
+}
+
+extern "C" size_t nans_clip_loss_fwd_workspace_bytes(int64_t n_loc, int64_t total_slots) {
+  if (n_loc <= 0 || total_slots <= 0) return 256;
+  return carve_fwd_ws(nullptr, n_loc, total_slots).bytes;
+}
+
+extern "C" int nans_clip_loss_fwd_phase(const void* I_loc, const void* T_loc, int64_t ld_loc,
+                                        const void* T_cols, const void* I_cols, int64_t ld_cols,
+                                        int feat_dtype, int64_t n_loc, int64_t ncols, int64_t D,
+                                        int64_t col_global_begin, int64_t label_begin,
+                                        const float* s_dev, int flags, void* ws, size_t ws_bytes,
+                                        int64_t slot_begin, void* stream) {
+  int rc = check_device();
+  if (rc != NANS_OK) return rc;
+  NANS_REQUIRE(feat_dtype == NANS_F16 || feat_dtype == NANS_BF16,
+               "loss_fwd: feat_dtype must be NANS_F16 or NANS_BF16");
+  NANS_REQUIRE(n_loc >= 0 && ncols >= 0 && D > 0 && D % 8 == 0,
+               "loss_fwd: sizes must be non-negative and D a multiple of 8 (D=%lld)", (long long)D);
+  NANS_REQUIRE(n_loc < (1ll << 30) && ncols < (1ll << 30) && D <= 8192, "loss_fwd: size too large");
+  if (n_loc == 0 || ncols == 0) return NANS_OK;
+  NANS_REQUIRE(I_loc && T_loc && T_cols && I_cols && s_dev && ws, "loss_fwd: null pointer");
+  NANS_REQUIRE(ld_loc >= D && ld_cols >= D, "loss_fwd: leading dimension smaller than D");
+  NANS_REQUIRE(slot_begin >= 0, "loss_fwd: negative slot");
+
+  const int nsplit = choose_nsplit(n_loc, ncols);
+  // the caller sized the workspace for total_slots >= slot_begin + nsplit
+  const size_t need = carve_fwd_ws(nullptr, n_loc, slot_begin + nsplit).bytes;
+  if (ws_bytes < need) {
+    set_error("loss_fwd: workspace %zu < %zu bytes", ws_bytes, need);
+    return NANS_ERR_WORKSPACE;
+  }
+  FwdWs w = carve_fwd_ws(ws, n_loc, slot_begin + nsplit);
+
+  const int kchunks = static_cast<int>(ceil_div(D, BK));
+  const SmemPlan plan = plan_smem(kchunks);
+
+  CUtensorMap tmA0, tmB0, tmA1, tmB1;
+  if ((rc = make_tmap_16b(&tmA0, I_loc, feat_dtype, n_loc, D, ld_loc, BM)) != NANS_OK) return rc;
+  if ((rc = make_tmap_16b(&tmB0, T_cols, feat_dtype, ncols, D, ld_cols, BN)) != NANS_OK) return rc;
+  if ((rc = make_tmap_16b(&tmA1, T_loc, feat_dtype, n_loc, D, ld_loc, BM)) != NANS_OK) return rc;
+  if ((rc = make_tmap_16b(&tmB1, I_cols, feat_dtype, ncols, D, ld_cols, BN)) != NANS_OK) return rc;
+
+  FwdParams p;
+  p.n_loc = static_cast<int>(n_loc);
+  p.ncols = static_cast<int>(ncols);
+  p.kchunks = kchunks;
+  p.stages = plan.stages;
+  p.idesc = make_idesc(idesc_fmt(feat_dtype), idesc_fmt(feat_dtype), 0, 0, BM, BN);
+  p.nrb = static_cast<int>(ceil_div(n_loc, BM));
+  p.nsplit = nsplit;
+  p.ntiles = static_cast<int>(ceil_div(ncols, BN));
+  p.label_shift = static_cast<int>(label_begin - col_global_begin);
+  p.col_global_begin = static_cast<int>(col_global_begin);
+  p.s_dev = s_dev;
+  p.part_m = w.part_m;
+  p.part_l = w.part_l;
+  p.part_w = w.part_w;
+  p.part_bv = w.part_bv;
+  p.part_bi = w.part_bi;
+  p.diag = w.diag;
+  p.slot_begin = static_cast<int>(slot_begin);
+  p.slot_stride = w.slot_stride;
+
+  const bool with_acc = (flags & NANS_LOSS_WITH_ACC) != 0;
+  auto kern = plan.a_resident ? (with_acc ? clip_fwd_kernel<true, true> : clip_fwd_kernel<true, false>)
+                              : (with_acc ? clip_fwd_kernel<false, true> : clip_fwd_kernel<false, false>);
+  NANS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    static_cast<int>(plan.bytes)));
+  const unsigned grid = static_cast<unsigned>(2 * p.nrb * p.nsplit);
+  kern<<<grid, NUM_THREADS, plan.bytes, static_cast<cudaStream_t>(stream)>>>(tmA0, tmB0, tmA1, tmB1, p);
+  NANS_CUDA_OK(cudaGetLastError());
+  return NANS_OK;
+}
+
+extern "C" int nans_clip_loss_fwd_finalize(int64_t n_loc, int64_t total_slots, int64_t label_begin,
+                                           const float* s_dev, int flags, void* ws, size_t ws_bytes,
+                                           float* lse_img_loc, float* lse_txt_loc, float* scalars,
+                                           void* stream) {
+  int rc = check_device();
+  if (rc != NANS_OK) return rc;
+  NANS_REQUIRE(n_loc > 0 && total_slots > 0, "loss_fwd_finalize: empty problem");
+  NANS_REQUIRE(s_dev && ws && lse_img_loc && lse_txt_loc && scalars, "loss_fwd_finalize: null pointer");
+  FwdWs w = carve_fwd_ws(ws, n_loc, total_slots);
+  if (w.bytes > ws_bytes) {
+    set_error("loss_fwd_finalize: workspace %zu < %zu bytes", ws_bytes, w.bytes);
+    return NANS_ERR_WORKSPACE;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  NANS_CUDA_OK(cudaMemsetAsync(w.counter, 0, sizeof(unsigned), st));
+  FinParams p;
+  p.n_loc = static_cast<int>(n_loc);
+  p.total_slots = static_cast<int>(total_slots);
+  p.with_acc = (flags & NANS_LOSS_WITH_ACC) ? 1 : 0;
+  p.slot_stride = w.slot_stride;
+  p.label_begin = static_cast<int>(label_begin);
+  p.s_dev = s_dev;
+  p.part_m = w.part_m;
+  p.part_l = w.part_l;
+  p.part_w = w.part_w;
+  p.part_bv = w.part_bv;
+  p.part_bi = w.part_bi;
+  p.diag = w.diag;
+  p.lse_img = lse_img_loc;
+  p.lse_txt = lse_txt_loc;
+  p.block_part = w.block_part;
+  p.counter = w.counter;
+  p.scalars = scalars;
+  const unsigned grid = static_cast<unsigned>(ceil_div(2 * n_loc, 256));
+  clip_fwd_finalize_kernel<<<grid, 256, 0, st>>>(p);
+  NANS_CUDA_OK(cudaGetLastError());
+  return NANS_OK;
+}
+
+extern "C" int nans_clip_loss_fwd(const void* I_loc, const void* T_loc, int64_t ld_loc,
+                                  const void* T_all, const void* I_all, int64_t ld_all,
+                                  int feat_dtype, int64_t n_loc, int64_t N, int64_t D,
+                                  int64_t label_begin, const float* s_dev, int flags,
+                                  float* lse_img_loc, float* lse_txt_loc, float* scalars, void* ws,
+                                  size_t ws_bytes, void* stream) {
+  NANS_REQUIRE(n_loc > 0 && N > 0, "loss_fwd: empty batch");
+  int rc = nans_clip_loss_fwd_phase(I_loc, T_loc, ld_loc, T_all, I_all, ld_all, feat_dtype, n_loc, N,
+                                    D, 0, label_begin, s_dev, flags, ws, ws_bytes, 0, stream);
+  if (rc != NANS_OK) return rc;
+  const int64_t slots = nans_clip_loss_fwd_phase_slots(n_loc, N, D);
+  return nans_clip_loss_fwd_finalize(n_loc, slots, label_begin, s_dev, flags, ws, ws_bytes,
+                                     lse_img_loc, lse_txt_loc, scalars, stream);
+}

@@ -1,0 +1,198 @@
+// strip_sweep.cuh — the shared contraction skeleton of kernels (2) and (4).
+//
+// One CTA owns a block of BM = 128 rows of the row operand A (image or text features of the local
+// batch, or a block of queries) and sweeps a range of BN = 256-column tiles of the column operand B
+// (gathered features / a gallery shard).  For every tile S = A * B^T (fp32, K = D) is formed in
+// TMEM by tcgen05.mma and handed to an epilogue functor; S never goes to shared or global memory.
+//
+//   warp 0    : TMA producer   (A block once if it fits in smem, else per K-chunk; B per K-chunk)
+//   warp 1    : tcgen05.mma issuer (one lane)
+//   warp 2    : TMEM allocator (512 columns = two 128x256 fp32 accumulators, double-buffered)
+//   warps 4-7 : epilogue, thread = row (TMEM lane), tcgen05.ld 32 columns at a time
+//
+// Shared memory (128-byte swizzle, K-major, 64 elements per line):
+//   A resident: kchunks x 16 KB  +  stages x 32 KB (B)      when that fits (D <= 640)
+//   A streamed: stages x (16 KB + 32 KB)
+#pragma once
+#include "common.cuh"
+
+namespace nans {
+namespace sweep {
+
+constexpr int BM = 128;
+constexpr int BN = 256;
+constexpr int BK = 64;
+constexpr int A_CHUNK = BM * BK * 2;  // 16 KB
+constexpr int B_STAGE = BN * BK * 2;  // 32 KB
+constexpr int NUM_THREADS = 256;
+constexpr int MAX_STAGES = 6;
+constexpr int TMEM_COLS = 512;
+constexpr int BAR_BYTES = 256;
+constexpr size_t SMEM_CAP = 227 * 1024;
+
+struct SmemPlan {
+  bool a_resident;
+  int stages;
+  size_t bytes;  // dynamic shared memory to request (includes 1 KB alignment slack)
+};
+
+inline SmemPlan plan_smem(int kchunks) {
+  SmemPlan p;
+  const size_t cap = SMEM_CAP - 1024 - BAR_BYTES;
+  const size_t a_res = static_cast<size_t>(kchunks) * A_CHUNK;
+  if (a_res + 2 * B_STAGE <= cap) {
+    p.a_resident = true;
+    p.stages = static_cast<int>((cap - a_res) / B_STAGE);
+    if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
+    p.bytes = a_res + static_cast<size_t>(p.stages) * B_STAGE + BAR_BYTES + 1024;
+  } else {
+    p.a_resident = false;
+    p.stages = static_cast<int>(cap / (A_CHUNK + B_STAGE));
+    if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
+    p.bytes = static_cast<size_t>(p.stages) * (A_CHUNK + B_STAGE) + BAR_BYTES + 1024;
+  }
+  return p;
+}
+
+#ifdef __CUDACC__
+
+struct SweepArgs {
+  const CUtensorMap* tmA;
+  const CUtensorMap* tmB;
+  int row0;        // first row of this CTA's block in A
+  int tile_begin;  // column tiles [tile_begin, tile_end) of B
+  int tile_end;
+  int kchunks;     // ceil(D / 64)
+  int stages;
+  uint32_t idesc;  // M=128, N=256, K-major A and B, fp32 accumulate
+};
+
+// Epi must provide:  __device__ void tile(uint32_t taddr, int tile_idx)
+//   taddr = TMEM address of this thread's warp lane group at column 0 of the accumulator buffer.
+template <bool A_RES, class Epi>
+__device__ __forceinline__ void run(const SweepArgs& a, Epi& epi) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* smA = smem;
+  uint8_t* smB = smem + static_cast<size_t>(A_RES ? a.kchunks : a.stages) * A_CHUNK;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smB + static_cast<size_t>(a.stages) * B_STAGE);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + MAX_STAGES;
+  uint64_t* a_full = bars + 2 * MAX_STAGES;
+  uint64_t* tfull = a_full + 1;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(a.tmA);
+    tma_prefetch_desc(a.tmB);
+    for (int i = 0; i < a.stages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(a_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 4);
+    }
+    fence_barrier_init();
+  } else if (warp == 2) {
+    tmem_alloc(tmem_ptr, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const int ntiles = a.tile_end - a.tile_begin;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------- TMA producer ----------------
+      if (A_RES) {
+        mbar_arrive_expect_tx(a_full, static_cast<uint32_t>(a.kchunks) * A_CHUNK);
+        for (int c = 0; c < a.kchunks; ++c)
+          tma_load_2d(smA + static_cast<size_t>(c) * A_CHUNK, a.tmA, a_full, c * BK, a.row0);
+      }
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = 0; t < ntiles; ++t) {
+        const int col0 = (a.tile_begin + t) * BN;
+        for (int c = 0; c < a.kchunks; ++c) {
+          mbar_wait(&empty[stage], phase ^ 1u);
+          mbar_arrive_expect_tx(&full[stage], A_RES ? B_STAGE : (A_CHUNK + B_STAGE));
+          if (!A_RES)
+            tma_load_2d(smA + static_cast<size_t>(stage) * A_CHUNK, a.tmA, &full[stage], c * BK,
+                        a.row0);
+          tma_load_2d(smB + static_cast<size_t>(stage) * B_STAGE, a.tmB, &full[stage], c * BK, col0);
+          if (++stage == a.stages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ---------------- MMA issuer ----------------
+      if (A_RES) {
+        mbar_wait(a_full, 0);
+        tc_fence_after();
+      }
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int t = 0; t < ntiles; ++t) {
+        mbar_wait(&tempty[acc], acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
+        for (int c = 0; c < a.kchunks; ++c) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr =
+              smem_u32(smA + static_cast<size_t>(A_RES ? c : stage) * A_CHUNK);
+          const uint32_t b_addr = smem_u32(smB + static_cast<size_t>(stage) * B_STAGE);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t ad = make_smem_desc(a_addr + k * 32, 16, 1024);
+            const uint64_t bd = make_smem_desc(b_addr + k * 32, 16, 1024);
+            mma_ss(d_tmem, ad, bd, a.idesc, (c | k) != 0 ? 1u : 0u);
+          }
+          tc_commit(&empty[stage]);  // frees the smem stage once these MMAs have read it
+          if (++stage == a.stages) { stage = 0; phase ^= 1u; }
+        }
+        tc_commit(&tfull[acc]);  // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ---------------- epilogue ----------------
+    const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = 0; t < ntiles; ++t) {
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      epi.tile(tmem_base + lane_base + static_cast<uint32_t>(acc * BN), a.tile_begin + t);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+#endif  // __CUDACC__
+
+}  // namespace sweep
+}  // namespace nans

@@ -1,0 +1,419 @@
+// topk.cu — kernel (4): top-k inner-product retrieval.
+//
+// Replaces cn_clip/eval/make_topk_predictions.py:71-85 (and make_topk_predictions_tr.py): per
+// query, the k gallery rows with the largest inner product in (score desc, gallery index asc)
+// order — what Python's stable sorted(score_tuples, key=score, reverse=True)[:k] yields.
+//
+// Pass 1 (topk_sweep_kernel): unit = (128-query block, gallery split).  The query block stays in
+//   shared memory; 256-row gallery tiles stream through tcgen05.mma into TMEM (strip_sweep.cuh).
+//   The epilogue thread of a query keeps a sorted k_cand-entry (score, index) list in registers;
+//   a score is compared against the list's current minimum and only the rare winners take the
+//   insertion path.  Lists go to the workspace, one per (split, query).
+// Pass 2 (topk_finalize_kernel): one warp per query merges the splits' lists, keeps the best
+//   k_cand by 16-bit score, recomputes those scores exactly in fp32 from the fp32 copies, and
+//   emits the top k in the reference order.  (16-bit scores alone flip near-ties)
+//
+// Roofline: tensor cores, 2*Q*G*D flops; the candidate lists are O(Q * k_cand) bytes.
+#include <limits.h>
+
+#include "strip_sweep.cuh"
+
+namespace nans {
+namespace {
+
+using namespace sweep;
+
+template <int KC>
+struct TopkEpi {
+  float ls[KC];
+  int li[KC];
+  int ncols;
+
+  __device__ __forceinline__ void init(int ncols_) {
+    ncols = ncols_;
+#pragma unroll
+    for (int i = 0; i < KC; ++i) {
+      ls[i] = -INFINITY;
+      li[i] = -1;
+    }
+  }
+
+  // precondition: s > ls[KC-1].  Entries >= s keep their place (earlier index first on ties).
+  __device__ __forceinline__ void insert(float s, int idx) {
+#pragma unroll
+    for (int k = KC - 1; k >= 1; --k) {
+      const bool keep = ls[k] >= s;
+      const bool here = !keep && (ls[k - 1] >= s);
+      const float ns = keep ? ls[k] : (here ? s : ls[k - 1]);
+      const int ni = keep ? li[k] : (here ? idx : li[k - 1]);
+      ls[k] = ns;
+      li[k] = ni;
+    }
+    if (!(ls[0] >= s)) {
+      ls[0] = s;
+      li[0] = idx;
+    }
+  }
+
+  __device__ __forceinline__ void tile(uint32_t taddr, int tile_idx) {
+    const int col0 = tile_idx * BN;
+    const bool tail = col0 + BN > ncols;
+#pragma unroll 1
+    for (int ch = 0; ch < BN / 32; ++ch) {
+      uint32_t r[32];
+      tmem_ld32(taddr + ch * 32, r);
+      tmem_wait_ld();
+      const int cb = col0 + ch * 32;
+      float v[32];
+#pragma unroll
+      for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(r[k]);
+      if (tail) {
+#pragma unroll
+        for (int k = 0; k < 32; ++k)
+          if (cb + k >= ncols) v[k] = -INFINITY;
+      }
+      const float thr = ls[KC - 1];
+      bool any = false;
+#pragma unroll
+      for (int k = 0; k < 32; ++k) any |= (v[k] > thr);
+      if (any) {
+        // rare path: repeatedly take the chunk's maximum (lowest column on ties)
+        while (true) {
+          float bv = v[0];
+          int bk = 0;
+#pragma unroll
+          for (int k = 1; k < 32; ++k)
+            if (v[k] > bv) {
+              bv = v[k];
+              bk = k;
+            }
+          if (!(bv > ls[KC - 1])) break;
+          insert(bv, cb + bk);
+#pragma unroll
+          for (int k = 0; k < 32; ++k)
+            if (k == bk) v[k] = -INFINITY;
+        }
+      }
+    }
+  }
+};
+
+struct TopkParams {
+  int Q, G, kchunks, stages;
+  uint32_t idesc;
+  int nqb, nsplit, ntiles;
+  float* cand_s;  // [nsplit][Q][KC]
+  int* cand_i;
+};
+
+template <bool A_RES, int KC>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+topk_sweep_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmG,
+                  const TopkParams p) {
+  const int unit = blockIdx.x;
+  const int split = unit % p.nsplit;
+  const int qb = unit / p.nsplit;
+
+  SweepArgs a;
+  a.tmA = &tmQ;
+  a.tmB = &tmG;
+  a.row0 = qb * BM;
+  a.tile_begin = static_cast<int>(static_cast<long long>(split) * p.ntiles / p.nsplit);
+  a.tile_end = static_cast<int>(static_cast<long long>(split + 1) * p.ntiles / p.nsplit);
+  a.kchunks = p.kchunks;
+  a.stages = p.stages;
+  a.idesc = p.idesc;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int row = a.row0 + (warp & 3) * 32 + lane;
+
+  TopkEpi<KC> epi;
+  epi.init(p.G);
+  run<A_RES>(a, epi);
+
+  if (warp >= 4 && row < p.Q) {
+    const long long base = (static_cast<long long>(split) * p.Q + row) * KC;
+#pragma unroll
+    for (int i = 0; i < KC; i += 4) {
+      *reinterpret_cast<float4*>(p.cand_s + base + i) =
+          make_float4(epi.ls[i], epi.ls[i + 1], epi.ls[i + 2], epi.ls[i + 3]);
+      *reinterpret_cast<int4*>(p.cand_i + base + i) =
+          make_int4(epi.li[i], epi.li[i + 1], epi.li[i + 2], epi.li[i + 3]);
+    }
+  }
+}
+
+// (score desc, index asc); invalid entries (index < 0) sort last
+__device__ __forceinline__ bool beats(float sa, long long ia, float sb, long long ib) {
+  const bool va = ia >= 0, vb = ib >= 0;
+  if (va != vb) return va;
+  if (!va) return false;
+  return sa > sb || (sa == sb && ia < ib);
+}
+
+constexpr int FIN_WARPS = 4;
+constexpr int FIN_MAXC = 1024;  // nsplit (<= 32) * k_cand (<= 32)
+constexpr int MERGE_MAXC = 512;  // n_shards * k
+
+struct FinParams {
+  int Q, G, D, k, kc, nsplit;
+  const float* cand_s;
+  const int* cand_i;
+  const float* Q32;
+  const float* G32;
+  long long index_offset;
+  float* out_scores;
+  long long* out_index;
+};
+
+__global__ void __launch_bounds__(FIN_WARPS * 32) topk_finalize_kernel(const FinParams p) {
+  __shared__ float sh_s[FIN_WARPS][FIN_MAXC];
+  __shared__ int sh_i[FIN_WARPS][FIN_MAXC];
+  __shared__ float sel_s[FIN_WARPS][32];
+  __shared__ int sel_i[FIN_WARPS][32];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = blockIdx.x * FIN_WARPS + w;
+  if (q >= p.Q) return;
+  const int C = p.nsplit * p.kc;
+  for (int c = lane; c < C; c += 32) {
+    const int sp = c / p.kc, j = c - sp * p.kc;
+    const long long src = (static_cast<long long>(sp) * p.Q + q) * p.kc + j;
+    sh_s[w][c] = p.cand_s[src];
+    sh_i[w][c] = p.cand_i[src];
+  }
+  if (lane < 32) {
+    sel_s[w][lane] = -INFINITY;
+    sel_i[w][lane] = -1;
+  }
+  __syncwarp();
+  // best kc candidates by 16-bit score: rank counting (valid candidates have distinct indices)
+  for (int c = lane; c < C; c += 32) {
+    const float s = sh_s[w][c];
+    const int i = sh_i[w][c];
+    if (i < 0) continue;
+    int rank = 0;
+    for (int d = 0; d < C; ++d) rank += beats(sh_s[w][d], sh_i[w][d], s, i) ? 1 : 0;
+    if (rank < p.kc) {
+      sel_s[w][rank] = s;
+      sel_i[w][rank] = i;
+    }
+  }
+  __syncwarp();
+  // exact fp32 rescoring of the selected candidates
+  if (p.Q32 != nullptr) {
+    const float4* qv = reinterpret_cast<const float4*>(p.Q32 + static_cast<long long>(q) * p.D);
+    for (int r = 0; r < p.kc; ++r) {
+      const int gi = sel_i[w][r];
+      if (gi < 0) continue;  // warp-uniform
+      const float4* gv = reinterpret_cast<const float4*>(p.G32 + static_cast<long long>(gi) * p.D);
+      float acc = 0.f;
+      for (int v = lane; v < p.D / 4; v += 32) {
+        const float4 a = __ldg(qv + v), b = __ldg(gv + v);
+        acc = fmaf(a.x, b.x, acc);
+        acc = fmaf(a.y, b.y, acc);
+        acc = fmaf(a.z, b.z, acc);
+        acc = fmaf(a.w, b.w, acc);
+      }
+      acc = warp_sum(acc);
+      if (lane == 0) sel_s[w][r] = acc;
+    }
+    __syncwarp();
+  }
+  // final order among the kc rescored candidates
+  if (lane < p.kc) {
+    const float s = sel_s[w][lane];
+    const int i = sel_i[w][lane];
+    if (i >= 0) {
+      int rank = 0;
+      for (int d = 0; d < p.kc; ++d) rank += beats(sel_s[w][d], sel_i[w][d], s, i) ? 1 : 0;
+      if (rank < p.k) {
+        p.out_scores[static_cast<long long>(q) * p.k + rank] = s;
+        p.out_index[static_cast<long long>(q) * p.k + rank] = p.index_offset + i;
+      }
+    }
+  }
+  // pad when the shard has fewer than k rows
+  const int nvalid = p.G < p.k ? p.G : p.k;
+  if (lane >= nvalid && lane < p.k) {
+    p.out_scores[static_cast<long long>(q) * p.k + lane] = -INFINITY;
+    p.out_index[static_cast<long long>(q) * p.k + lane] = -1;
+  }
+}
+
+struct MergeParams {
+  int n_shards, Q, k;
+  const float* in_s;
+  const long long* in_i;
+  float* out_s;
+  long long* out_i;
+};
+
+// one warp per query; n_shards * k <= MERGE_MAXC candidates
+__global__ void __launch_bounds__(FIN_WARPS * 32) topk_merge_kernel(const MergeParams p) {
+  __shared__ float sh_s[FIN_WARPS][MERGE_MAXC];
+  __shared__ long long sh_i[FIN_WARPS][MERGE_MAXC];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = blockIdx.x * FIN_WARPS + w;
+  if (q >= p.Q) return;
+  const int C = p.n_shards * p.k;
+  for (int c = lane; c < C; c += 32) {
+    const int sh = c / p.k, j = c - sh * p.k;
+    const long long src = (static_cast<long long>(sh) * p.Q + q) * p.k + j;
+    sh_s[w][c] = p.in_s[src];
+    sh_i[w][c] = p.in_i[src];
+  }
+  __syncwarp();
+  int nvalid = 0;
+  for (int c = lane; c < C; c += 32) {
+    const float s = sh_s[w][c];
+    const long long i = sh_i[w][c];
+    if (i < 0) continue;
+    ++nvalid;
+    int rank = 0;
+    for (int d = 0; d < C; ++d) rank += beats(sh_s[w][d], sh_i[w][d], s, i) ? 1 : 0;
+    if (rank < p.k) {
+      p.out_s[static_cast<long long>(q) * p.k + rank] = s;
+      p.out_i[static_cast<long long>(q) * p.k + rank] = i;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) nvalid += __shfl_xor_sync(0xffffffffu, nvalid, o);
+  for (int r = nvalid + lane; r < p.k; r += 32) {
+    p.out_s[static_cast<long long>(q) * p.k + r] = -INFINITY;
+    p.out_i[static_cast<long long>(q) * p.k + r] = -1;
+  }
+}
+
+int choose_topk_nsplit(int64_t Q, int64_t G) {
+  const int64_t base = ceil_div(Q, BM);
+  const int64_t ntiles = ceil_div(G, BN);
+  const int sms = sm_count();
+  int best = 1;
+  double best_cost = 1e300;
+  const int64_t max_ns = ntiles < 32 ? ntiles : 32;
+  for (int64_t ns = 1; ns <= max_ns; ++ns) {
+    const double waves = static_cast<double>(ceil_div(base * ns, sms));
+    const double cost = waves * (static_cast<double>(ceil_div(ntiles, ns)) + 0.75);
+    if (cost < best_cost - 1e-9) {
+      best_cost = cost;
+      best = static_cast<int>(ns);
+    }
+  }
+  return best;
+}
+
+}  // namespace
+}  // namespace nans
+
+using namespace nans;
+
+extern "C" size_t nans_topk_ip_workspace_bytes(int64_t Q, int64_t G, int64_t D, int k_cand) {
+  (void)D;
+  if (Q <= 0 || G <= 0 || k_cand <= 0) return 256;
+  const int ns = choose_topk_nsplit(Q, G);
+  return 2 * align_up(static_cast<size_t>(ns) * Q * k_cand * 4, 256) + 256;
+}
+
+extern "C" int nans_topk_ip(const void* Q16, const void* G16, int feat_dtype, const float* Q32,
+                            const float* G32, int64_t Q, int64_t G, int64_t D, int k, int k_cand,
+                            int64_t gallery_index_offset, float* out_scores, int64_t* out_index,
+                            void* ws, size_t ws_bytes, void* stream) {
+  int rc = check_device();
+  if (rc != NANS_OK) return rc;
+  NANS_REQUIRE(feat_dtype == NANS_F16 || feat_dtype == NANS_BF16,
+               "topk_ip: feat_dtype must be NANS_F16 or NANS_BF16");
+  NANS_REQUIRE(k_cand == 16 || k_cand == 32, "topk_ip: k_cand must be 16 or 32 (got %d)", k_cand);
+  NANS_REQUIRE(k >= 1 && k <= k_cand, "topk_ip: need 1 <= k <= k_cand (k=%d)", k);
+  NANS_REQUIRE(Q >= 0 && G >= 0 && D > 0 && D % 8 == 0, "topk_ip: bad sizes (D must be a multiple of 8)");
+  NANS_REQUIRE(Q < (1ll << 30) && G < (1ll << 31) - 512 && D <= 8192, "topk_ip: size too large");
+  NANS_REQUIRE((Q32 == nullptr) == (G32 == nullptr), "topk_ip: pass both fp32 copies or neither");
+  if (Q == 0) return NANS_OK;
+  NANS_REQUIRE(out_scores && out_index, "topk_ip: null output");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (G == 0) {
+    // every slot is padding: -inf / -1 (0xFF bytes are -1 for int64; scores need a kernel -> reuse merge)
+    MergeParams mp{0, static_cast<int>(Q), k, nullptr, nullptr, out_scores,
+                   reinterpret_cast<long long*>(out_index)};
+    topk_merge_kernel<<<static_cast<unsigned>(ceil_div(Q, FIN_WARPS)), FIN_WARPS * 32, 0, st>>>(mp);
+    NANS_CUDA_OK(cudaGetLastError());
+    return NANS_OK;
+  }
+  NANS_REQUIRE(Q16 && G16 && ws, "topk_ip: null pointer");
+  NANS_REQUIRE(Q32 == nullptr || ((reinterpret_cast<uintptr_t>(Q32) & 15) == 0 &&
+                                  (reinterpret_cast<uintptr_t>(G32) & 15) == 0 && D % 4 == 0),
+               "topk_ip: fp32 copies must be 16-byte aligned");
+  const size_t need = nans_topk_ip_workspace_bytes(Q, G, D, k_cand);
+  if (ws_bytes < need) {
+    set_error("topk_ip: workspace %zu < %zu bytes", ws_bytes, need);
+    return NANS_ERR_WORKSPACE;
+  }
+  NANS_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 15) == 0, "topk_ip: workspace must be 16-byte aligned");
+
+  const int nsplit = choose_topk_nsplit(Q, G);
+  const int kchunks = static_cast<int>(ceil_div(D, BK));
+  const SmemPlan plan = plan_smem(kchunks);
+
+  CUtensorMap tmQ, tmG;
+  if ((rc = make_tmap_16b(&tmQ, Q16, feat_dtype, Q, D, D, BM)) != NANS_OK) return rc;
+  if ((rc = make_tmap_16b(&tmG, G16, feat_dtype, G, D, D, BN)) != NANS_OK) return rc;
+
+  TopkParams p;
+  p.Q = static_cast<int>(Q);
+  p.G = static_cast<int>(G);
+  p.kchunks = kchunks;
+  p.stages = plan.stages;
+  p.idesc = make_idesc(idesc_fmt(feat_dtype), idesc_fmt(feat_dtype), 0, 0, BM, BN);
+  p.nqb = static_cast<int>(ceil_div(Q, BM));
+  p.nsplit = nsplit;
+  p.ntiles = static_cast<int>(ceil_div(G, BN));
+  p.cand_s = static_cast<float*>(ws);
+  p.cand_i = reinterpret_cast<int*>(static_cast<uint8_t*>(ws) +
+                                    align_up(static_cast<size_t>(nsplit) * Q * k_cand * 4, 256));
+
+  void (*kern)(const CUtensorMap, const CUtensorMap, const TopkParams);
+  if (k_cand == 16) kern = plan.a_resident ? topk_sweep_kernel<true, 16> : topk_sweep_kernel<false, 16>;
+  else kern = plan.a_resident ? topk_sweep_kernel<true, 32> : topk_sweep_kernel<false, 32>;
+  NANS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    static_cast<int>(plan.bytes)));
+  const unsigned grid = static_cast<unsigned>(p.nqb * p.nsplit);
+  kern<<<grid, NUM_THREADS, plan.bytes, st>>>(tmQ, tmG, p);
+  NANS_CUDA_OK(cudaGetLastError());
+
+  FinParams f;
+  f.Q = p.Q;
+  f.G = p.G;
+  f.D = static_cast<int>(D);
+  f.k = k;
+  f.kc = k_cand;
+  f.nsplit = nsplit;
+  f.cand_s = p.cand_s;
+  f.cand_i = p.cand_i;
+  f.Q32 = Q32;
+  f.G32 = G32;
+  f.index_offset = gallery_index_offset;
+  f.out_scores = out_scores;
+  f.out_index = reinterpret_cast<long long*>(out_index);
+  topk_finalize_kernel<<<static_cast<unsigned>(ceil_div(Q, FIN_WARPS)), FIN_WARPS * 32, 0, st>>>(f);
+  NANS_CUDA_OK(cudaGetLastError());
+  return NANS_OK;
+}
+
+extern "C" int nans_topk_merge(const float* in_scores, const int64_t* in_index, int n_shards,
+                               int64_t Q, int k, float* out_scores, int64_t* out_index,
+                               void* stream) {
+  int rc = check_device();
+  if (rc != NANS_OK) return rc;
+  NANS_REQUIRE(n_shards >= 1 && k >= 1 && static_cast<int64_t>(n_shards) * k <= MERGE_MAXC,
+               "topk_merge: need n_shards * k <= %d", MERGE_MAXC);
+  NANS_REQUIRE(Q >= 0 && Q < (1ll << 30), "topk_merge: bad Q");
+  if (Q == 0) return NANS_OK;
+  NANS_REQUIRE(in_scores && in_index && out_scores && out_index, "topk_merge: null pointer");
+  MergeParams p{n_shards, static_cast<int>(Q), k, in_scores,
+                reinterpret_cast<const long long*>(in_index), out_scores,
+                reinterpret_cast<long long*>(out_index)};
+  topk_merge_kernel<<<static_cast<unsigned>(ceil_div(Q, FIN_WARPS)), FIN_WARPS * 32, 0,
+                      static_cast<cudaStream_t>(stream)>>>(p);
+  NANS_CUDA_OK(cudaGetLastError());
+  return NANS_OK;
+}

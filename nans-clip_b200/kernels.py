@@ -1,0 +1,193 @@
+"""Thin torch-tensor wrappers over the C-ABI (one function per exported kernel entry point).
+
+Everything here takes CUDA tensors, hands raw device pointers and the current stream to
+libnans_clip.so and returns tensors.  No arithmetic happens in Python and nothing falls back to
+PyTorch ops: a missing library or a non-sm_100 device raises.
+
+The distributed orchestration (loss.py, retrieval.py) only talks to the functions of this module,
+so the CPU test-suite can substitute them to exercise the multi-rank host logic under gloo.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from ._lib import NANS_BF16, NANS_F16, NANS_F32, NANS_LOSS_WITH_ACC, check
+
+_DT = {torch.float32: NANS_F32, torch.float16: NANS_F16, torch.bfloat16: NANS_BF16}
+
+
+def dtype_code(dt: torch.dtype) -> int:
+    try:
+        return _DT[dt]
+    except KeyError:
+        raise TypeError(f"unsupported dtype {dt}: expected float32, float16 or bfloat16") from None
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: torch.Tensor | None) -> int | None:
+    return None if t is None else t.data_ptr()
+
+
+def _require_cuda(*ts: torch.Tensor) -> None:
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("nans_clip_b200 kernels need CUDA tensors (there is no CPU path)")
+
+
+def _rowmajor(t: torch.Tensor) -> torch.Tensor:
+    """2-D tensor with unit inner stride (a row pitch is allowed)."""
+    if t.dim() != 2:
+        raise ValueError(f"expected a 2-D feature matrix, got shape {tuple(t.shape)}")
+    if t.stride(1) != 1 or (t.shape[0] > 1 and t.stride(0) < t.shape[1]):
+        t = t.contiguous()
+    return t
+
+
+# --------------------------------------------------------------------------------------------
+# (1) L2 normalise + cast
+# --------------------------------------------------------------------------------------------
+def l2norm_cast(x: torch.Tensor, out_dtype: torch.dtype | None = torch.bfloat16, *,
+                normalize: bool = True, want_fp32: bool = False, want_inv_norm: bool = False):
+    """Returns (y16 | None, y32 | None, inv_norm | None).  Reference: model.py:412-413."""
+    _require_cuda(x)
+    x = _rowmajor(x)
+    rows, D = x.shape
+    y16 = torch.empty((rows, D), dtype=out_dtype, device=x.device) if out_dtype is not None else None
+    y32 = torch.empty((rows, D), dtype=torch.float32, device=x.device) if want_fp32 else None
+    inv = torch.empty((rows,), dtype=torch.float32, device=x.device) if want_inv_norm else None
+    with torch.cuda.device(x.device):
+        check(_lib.load().nans_l2norm_cast(
+            x.data_ptr(), dtype_code(x.dtype), rows, D, x.stride(0) if rows > 1 else D,
+            _ptr(y16), dtype_code(out_dtype) if out_dtype is not None else NANS_BF16,
+            _ptr(y32), _ptr(inv), 1 if normalize else 0, _stream()))
+    return y16, y32, inv
+
+
+def l2norm_bwd(x: torch.Tensor, inv_norm: torch.Tensor, dy: torch.Tensor) -> torch.Tensor:
+    _require_cuda(x, inv_norm, dy)
+    x = _rowmajor(x)
+    dy = dy.to(torch.float32).contiguous()
+    rows, D = x.shape
+    dx = torch.empty((rows, D), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(_lib.load().nans_l2norm_bwd(x.data_ptr(), dtype_code(x.dtype),
+                                          x.stride(0) if rows > 1 else D, inv_norm.data_ptr(),
+                                          dy.data_ptr(), rows, D, dx.data_ptr(), _stream()))
+    return dx
+
+
+# --------------------------------------------------------------------------------------------
+# (2) fused forward
+# --------------------------------------------------------------------------------------------
+def fwd_phase_slots(n_loc: int, ncols: int, D: int) -> int:
+    return int(_lib.load().nans_clip_loss_fwd_phase_slots(n_loc, ncols, D))
+
+
+def fwd_workspace(n_loc: int, total_slots: int, device) -> torch.Tensor:
+    nbytes = int(_lib.load().nans_clip_loss_fwd_workspace_bytes(n_loc, total_slots))
+    return torch.empty(nbytes, dtype=torch.uint8, device=device)
+
+
+def fwd_phase(I_loc, T_loc, T_cols, I_cols, *, col_global_begin: int, label_begin: int,
+              s_dev: torch.Tensor, with_acc: bool, ws: torch.Tensor, slot_begin: int) -> None:
+    _require_cuda(I_loc, T_loc, T_cols, I_cols, s_dev, ws)
+    n_loc, D = I_loc.shape
+    ncols = T_cols.shape[0]
+    assert I_loc.dtype == T_loc.dtype == T_cols.dtype == I_cols.dtype
+    assert I_loc.stride(0) == T_loc.stride(0) and T_cols.stride(0) == I_cols.stride(0)
+    with torch.cuda.device(I_loc.device):
+        check(_lib.load().nans_clip_loss_fwd_phase(
+            I_loc.data_ptr(), T_loc.data_ptr(), I_loc.stride(0), T_cols.data_ptr(),
+            I_cols.data_ptr(), T_cols.stride(0), dtype_code(I_loc.dtype), n_loc, ncols, D,
+            col_global_begin, label_begin, s_dev.data_ptr(),
+            NANS_LOSS_WITH_ACC if with_acc else 0, ws.data_ptr(), ws.numel(), slot_begin,
+            _stream()))
+
+
+def fwd_finalize(n_loc: int, total_slots: int, label_begin: int, s_dev: torch.Tensor,
+                 with_acc: bool, ws: torch.Tensor):
+    """Returns (lse [2, n_loc] (row 0 image->text, row 1 text->image), scalars [8])."""
+    pad = (n_loc + 3) // 4 * 4  # keeps row 1 16-byte aligned (the backward loads float4)
+    lse = torch.empty((2, pad), dtype=torch.float32, device=ws.device)[:, :n_loc]
+    scalars = torch.empty((8,), dtype=torch.float32, device=ws.device)
+    with torch.cuda.device(ws.device):
+        check(_lib.load().nans_clip_loss_fwd_finalize(
+            n_loc, total_slots, label_begin, s_dev.data_ptr(),
+            NANS_LOSS_WITH_ACC if with_acc else 0, ws.data_ptr(), ws.numel(),
+            lse[0].data_ptr(), lse[1].data_ptr(), scalars.data_ptr(), _stream()))
+    return lse, scalars
+
+
+# --------------------------------------------------------------------------------------------
+# (3) fused backward
+# --------------------------------------------------------------------------------------------
+def bwd(I_loc, T_loc, T_all, I_all, *, label_begin: int, s_dev: torch.Tensor,
+        lse_all: torch.Tensor, grad_out: torch.Tensor, grad_mult: float, row_begin: int,
+        row_count: int, out_dtype: torch.dtype):
+    """lse_all: [2, N] fp32 (image->text, text->image) in global row order.  Returns (dI, dT)."""
+    _require_cuda(I_loc, T_loc, T_all, I_all, s_dev, lse_all, grad_out)
+    n_loc, D = I_loc.shape
+    N = T_all.shape[0]
+    dev = I_loc.device
+    dI = torch.empty((row_count, D), dtype=out_dtype, device=dev)
+    dT = torch.empty((row_count, D), dtype=out_dtype, device=dev)
+    lib = _lib.load()
+    nbytes = int(lib.nans_clip_loss_bwd_workspace_bytes(row_count, N, D))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    assert lse_all.shape == (2, N) and lse_all.dtype == torch.float32
+    if lse_all.stride(1) != 1 or lse_all[0].data_ptr() % 16 or lse_all[1].data_ptr() % 16:
+        pad = (N + 3) // 4 * 4
+        buf = torch.empty((2, pad), dtype=torch.float32, device=dev)[:, :N]
+        buf.copy_(lse_all)
+        lse_all = buf
+    assert grad_out.dtype == torch.float32 and grad_out.numel() == 1
+    with torch.cuda.device(dev):
+        check(lib.nans_clip_loss_bwd(
+            I_loc.data_ptr(), T_loc.data_ptr(), I_loc.stride(0), T_all.data_ptr(),
+            I_all.data_ptr(), T_all.stride(0), dtype_code(I_loc.dtype), n_loc, N, D, label_begin,
+            s_dev.data_ptr(), lse_all[0].data_ptr(), lse_all[1].data_ptr(), grad_out.data_ptr(),
+            float(grad_mult), row_begin, row_count, dI.data_ptr(), dT.data_ptr(),
+            dtype_code(out_dtype), ws.data_ptr(), ws.numel(), _stream()))
+    return dI, dT
+
+
+# --------------------------------------------------------------------------------------------
+# (4) retrieval
+# --------------------------------------------------------------------------------------------
+def topk_ip(Q16, G16, Q32, G32, k: int, k_cand: int, gallery_index_offset: int = 0):
+    """Returns (scores [Q, k] fp32, index [Q, k] int64).  Reference: make_topk_predictions.py:71-85."""
+    _require_cuda(Q16, G16, Q32, G32)
+    Qn, D = Q16.shape
+    Gn = G16.shape[0]
+    dev = Q16.device
+    Q16, G16 = Q16.contiguous(), G16.contiguous()
+    if Q32 is not None:
+        Q32, G32 = Q32.contiguous(), G32.contiguous()
+    scores = torch.empty((Qn, k), dtype=torch.float32, device=dev)
+    index = torch.empty((Qn, k), dtype=torch.int64, device=dev)
+    lib = _lib.load()
+    ws = torch.empty(int(lib.nans_topk_ip_workspace_bytes(Qn, Gn, D, k_cand)), dtype=torch.uint8,
+                     device=dev)
+    with torch.cuda.device(dev):
+        check(lib.nans_topk_ip(Q16.data_ptr(), G16.data_ptr(), dtype_code(Q16.dtype), _ptr(Q32),
+                               _ptr(G32), Qn, Gn, D, k, k_cand, gallery_index_offset,
+                               scores.data_ptr(), index.data_ptr(), ws.data_ptr(), ws.numel(),
+                               _stream()))
+    return scores, index
+
+
+def topk_merge(scores: torch.Tensor, index: torch.Tensor):
+    """[n_shards, Q, k] x2 -> ([Q, k], [Q, k]) in (score desc, index asc) order."""
+    _require_cuda(scores, index)
+    n_shards, Qn, k = scores.shape
+    scores, index = scores.contiguous(), index.contiguous()
+    out_s = torch.empty((Qn, k), dtype=torch.float32, device=scores.device)
+    out_i = torch.empty((Qn, k), dtype=torch.int64, device=scores.device)
+    with torch.cuda.device(scores.device):
+        check(_lib.load().nans_topk_merge(scores.data_ptr(), index.data_ptr(), n_shards, Qn, k,
+                                          out_s.data_ptr(), out_i.data_ptr(), _stream()))
+    return out_s, out_i
