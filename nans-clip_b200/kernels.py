@@ -16,6 +16,14 @@ from ._lib import NANS_BF16, NANS_F16, NANS_F32, NANS_LOSS_WITH_ACC, check
 
 _DT = {torch.float32: NANS_F32, torch.float16: NANS_F16, torch.bfloat16: NANS_BF16}
 
+# Number of kernels of libnans_clip.so launched through this module (bench.py reports it).
+LAUNCHES = 0
+
+
+def _count(n: int) -> None:
+    global LAUNCHES
+    LAUNCHES += n
+
 
 def dtype_code(dt: torch.dtype) -> int:
     try:
@@ -64,6 +72,7 @@ def l2norm_cast(x: torch.Tensor, out_dtype: torch.dtype | None = torch.bfloat16,
             x.data_ptr(), dtype_code(x.dtype), rows, D, x.stride(0) if rows > 1 else D,
             _ptr(y16), dtype_code(out_dtype) if out_dtype is not None else NANS_BF16,
             _ptr(y32), _ptr(inv), 1 if normalize else 0, _stream()))
+    _count(1 if rows else 0)
     return y16, y32, inv
 
 
@@ -77,6 +86,7 @@ def l2norm_bwd(x: torch.Tensor, inv_norm: torch.Tensor, dy: torch.Tensor) -> tor
         check(_lib.load().nans_l2norm_bwd(x.data_ptr(), dtype_code(x.dtype),
                                           x.stride(0) if rows > 1 else D, inv_norm.data_ptr(),
                                           dy.data_ptr(), rows, D, dx.data_ptr(), _stream()))
+    _count(1 if rows else 0)
     return dx
 
 
@@ -106,6 +116,7 @@ def fwd_phase(I_loc, T_loc, T_cols, I_cols, *, col_global_begin: int, label_begi
             col_global_begin, label_begin, s_dev.data_ptr(),
             NANS_LOSS_WITH_ACC if with_acc else 0, ws.data_ptr(), ws.numel(), slot_begin,
             _stream()))
+    _count(1)
 
 
 def fwd_finalize(n_loc: int, total_slots: int, label_begin: int, s_dev: torch.Tensor,
@@ -119,6 +130,7 @@ def fwd_finalize(n_loc: int, total_slots: int, label_begin: int, s_dev: torch.Te
             n_loc, total_slots, label_begin, s_dev.data_ptr(),
             NANS_LOSS_WITH_ACC if with_acc else 0, ws.data_ptr(), ws.numel(),
             lse[0].data_ptr(), lse[1].data_ptr(), scalars.data_ptr(), _stream()))
+    _count(1)
     return lse, scalars
 
 
@@ -152,6 +164,7 @@ def bwd(I_loc, T_loc, T_all, I_all, *, label_begin: int, s_dev: torch.Tensor,
             s_dev.data_ptr(), lse_all[0].data_ptr(), lse_all[1].data_ptr(), grad_out.data_ptr(),
             float(grad_mult), row_begin, row_count, dI.data_ptr(), dT.data_ptr(),
             dtype_code(out_dtype), ws.data_ptr(), ws.numel(), _stream()))
+    _count(1 if out_dtype == torch.float32 else 3)
     return dI, dT
 
 
@@ -177,6 +190,7 @@ def topk_ip(Q16, G16, Q32, G32, k: int, k_cand: int, gallery_index_offset: int =
                                _ptr(G32), Qn, Gn, D, k, k_cand, gallery_index_offset,
                                scores.data_ptr(), index.data_ptr(), ws.data_ptr(), ws.numel(),
                                _stream()))
+    _count(2 if Gn else 1)
     return scores, index
 
 
@@ -190,4 +204,5 @@ def topk_merge(scores: torch.Tensor, index: torch.Tensor):
     with torch.cuda.device(scores.device):
         check(_lib.load().nans_topk_merge(scores.data_ptr(), index.data_ptr(), n_shards, Qn, k,
                                           out_s.data_ptr(), out_i.data_ptr(), _stream()))
+    _count(1)
     return out_s, out_i

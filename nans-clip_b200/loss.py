@@ -106,11 +106,11 @@ class _ClipLossFn(torch.autograd.Function):
 
         # ---- the two small exchanges --------------------------------------------------------
         if W > 1:
-            lse_g = torch.empty((W, 2, n_loc), dtype=torch.float32, device=dev)
-            h = dist.all_gather_into_tensor(lse_g, lse, group=cfg.group, async_op=True)
+            lse_g = torch.empty((W * 2, n_loc), dtype=torch.float32, device=dev)
+            h = dist.all_gather_into_tensor(lse_g, lse.contiguous(), group=cfg.group, async_op=True)
             dist.all_reduce(scalars, op=dist.ReduceOp.SUM, group=cfg.group)
             h.wait()
-            lse_all = lse_g.permute(1, 0, 2).reshape(2, N)
+            lse_all = lse_g.view(W, 2, n_loc).permute(1, 0, 2).reshape(2, N)
         else:
             lse_all = lse
 

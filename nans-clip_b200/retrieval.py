@@ -1,0 +1,100 @@
+"""Top-k inner-product retrieval on the sm_100a kernels (host orchestration).
+
+Functional core of cn_clip/eval/make_topk_predictions.py:57-85 (and _tr.py): for every query the k
+gallery rows with the largest fp32 inner product — no renormalisation (the reference does none,
+SURVEY.md §3.4) — ordered by (score descending, gallery position ascending), which is what the
+reference's stable `sorted(..., reverse=True)[:k]` yields.
+
+With a process group the GALLERY is sharded by contiguous row ranges (rank r holds rows
+[offset_r, offset_r + G_r)), the queries are replicated, every rank runs the two-pass kernel on its
+shard and the per-shard lists are all-gathered and merged with the same ordering rule
+(nans_topk_merge); contiguous sharding makes the tie rule a plain index compare.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+
+from . import kernels as K
+
+MAX_K = 32
+
+
+def _pick_k_cand(k: int, k_cand: Optional[int]) -> int:
+    if k < 1 or k > MAX_K:
+        raise ValueError(f"top-k must be in [1, {MAX_K}] (got {k})")
+    if k_cand is None:
+        k_cand = 16 if k <= 10 else 32
+    if k_cand not in (16, 32) or k_cand < k:
+        raise ValueError("k_cand must be 16 or 32 and >= k")
+    return k_cand
+
+
+class GalleryShard:
+    """A gallery shard resident in HBM: the fp32 rows (exact rescoring) and their 16-bit copy
+    (tensor-core candidate pass).  Build once, query many times."""
+
+    def __init__(self, gallery: torch.Tensor, device=None, feat_dtype: torch.dtype = torch.float16,
+                 index_offset: int = 0):
+        device = torch.device(device) if device is not None else (
+            gallery.device if gallery.is_cuda else torch.device("cuda", torch.cuda.current_device()))
+        self.g32 = gallery.to(device=device, dtype=torch.float32, non_blocking=True).contiguous()
+        self.feat_dtype = feat_dtype
+        self.index_offset = int(index_offset)
+        if self.g32.shape[0] > 0:
+            self.g16, _, _ = K.l2norm_cast(self.g32, feat_dtype, normalize=False)
+        else:
+            self.g16 = torch.empty_like(self.g32, dtype=feat_dtype)
+
+    @property
+    def rows(self) -> int:
+        return self.g32.shape[0]
+
+    def search(self, queries: torch.Tensor, k: int = 10, k_cand: Optional[int] = None,
+               query_block: int = 32768):
+        """queries [Q, D] (any float dtype, host or device) -> (scores [Q, k], index [Q, k])."""
+        k_cand = _pick_k_cand(k, k_cand)
+        dev = self.g32.device
+        out_s, out_i = [], []
+        for b in range(0, max(queries.shape[0], 1), query_block):
+            q32 = queries[b:b + query_block].to(device=dev, dtype=torch.float32, non_blocking=True).contiguous()
+            if q32.shape[0] == 0:
+                break
+            q16, _, _ = K.l2norm_cast(q32, self.feat_dtype, normalize=False)
+            s, i = K.topk_ip(q16, self.g16, q32, self.g32, k, k_cand, self.index_offset)
+            out_s.append(s)
+            out_i.append(i)
+        if not out_s:
+            return (torch.empty((0, k), dtype=torch.float32, device=dev),
+                    torch.empty((0, k), dtype=torch.int64, device=dev))
+        return torch.cat(out_s), torch.cat(out_i)
+
+
+def topk_retrieve(queries: torch.Tensor, gallery_shard: torch.Tensor, k: int = 10, *,
+                  k_cand: Optional[int] = None, group=None, index_offset: Optional[int] = None,
+                  feat_dtype: torch.dtype = torch.float16, device=None):
+    """Global top-k of `queries` against the gallery whose local shard is `gallery_shard`.
+
+    Without `group`: single GPU, `index_offset` (default 0) is added to the returned positions.
+    With `group`: rank r passes its contiguous shard; offsets default to the exclusive prefix sum
+    of the shard sizes in rank order.  Every rank returns the merged global result."""
+    if group is None:
+        shard = GalleryShard(gallery_shard, device, feat_dtype, index_offset or 0)
+        return shard.search(queries, k, k_cand)
+    W, rank = dist.get_world_size(group), dist.get_rank(group)
+    dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+    if index_offset is None:
+        sizes = torch.zeros(W, dtype=torch.int64, device=dev)
+        sizes[rank] = gallery_shard.shape[0]
+        dist.all_reduce(sizes, group=group)
+        index_offset = int(sizes[:rank].sum().item())
+    shard = GalleryShard(gallery_shard, dev, feat_dtype, index_offset)
+    s, i = shard.search(queries, k, k_cand)
+    Qn = s.shape[0]
+    all_s = torch.empty((W * Qn, k), dtype=s.dtype, device=dev)
+    all_i = torch.empty((W * Qn, k), dtype=i.dtype, device=dev)
+    dist.all_gather_into_tensor(all_s, s.contiguous(), group=group)
+    dist.all_gather_into_tensor(all_i, i.contiguous(), group=group)
+    return K.topk_merge(all_s.view(W, Qn, k), all_i.view(W, Qn, k))

@@ -1,0 +1,68 @@
+"""The C-ABI boundary without a GPU: the library builds/loads, exports every symbol the header
+declares, and fails loudly (never silently) when no sm_100 device is present."""
+import ctypes
+import re
+from pathlib import Path
+
+import pytest
+import torch
+
+from nans_clip_b200 import _lib
+
+ROOT = Path(__file__).resolve().parent.parent
+HEADER = ROOT / "include" / "nans_clip.h"
+
+
+def declared_functions():
+    text = re.sub(r"/\*.*?\*/", "", HEADER.read_text(), flags=re.S)
+    return sorted(set(re.findall(r"\b(nans_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_declares_the_expected_entry_points():
+    names = declared_functions()
+    for must in ["nans_l2norm_cast", "nans_l2norm_bwd", "nans_clip_loss_fwd_phase",
+                 "nans_clip_loss_fwd_finalize", "nans_clip_loss_fwd", "nans_clip_loss_bwd",
+                 "nans_topk_ip", "nans_topk_merge", "nans_last_error", "nans_version",
+                 "nans_device_check"]:
+        assert must in names
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    raw = ctypes.CDLL(str(_lib.LIB_PATH))
+    for name in declared_functions():
+        assert hasattr(raw, name), f"{name} declared in include/nans_clip.h but not exported"
+    assert sorted(_lib.EXPORTS) == declared_functions(), "ctypes signatures out of sync with the header"
+    assert lib.nans_version() == 100
+
+
+def test_workspace_queries_need_no_device():
+    lib = _lib.load()
+    assert lib.nans_clip_loss_fwd_phase_slots(4096, 32768, 512) >= 1
+    assert lib.nans_clip_loss_fwd_workspace_bytes(4096, 4) > 4 * 5 * 2 * 4096 * 4
+    assert lib.nans_clip_loss_bwd_workspace_bytes(4096, 32768, 512) >= 2 * 4096 * 512 * 4
+    assert lib.nans_topk_ip_workspace_bytes(30000, 125000, 512, 16) >= 2 * 30000 * 16 * 4
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_compute_calls_fail_loudly_without_a_gpu():
+    lib = _lib.load()
+    assert lib.nans_device_check() == -2
+    assert "no CPU path" in _lib.last_error() or "sm_100" in _lib.last_error()
+    rc = lib.nans_l2norm_cast(None, 0, 4, 64, 64, None, 1, None, None, 1, None)
+    assert rc == -2
+    with pytest.raises(_lib.NansError):
+        _lib.check(rc)
+    rc = lib.nans_topk_merge(None, None, 1, 4, 10, None, None, None)
+    assert rc == -2
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_product_path_refuses_cpu_tensors():
+    from nans_clip_b200.loss import clip_contrastive_loss
+    x = torch.nn.functional.normalize(torch.randn(8, 64), dim=-1)
+    with pytest.raises(RuntimeError):
+        clip_contrastive_loss(x, x, torch.tensor(10.0))
+    from nans_clip_b200.retrieval import GalleryShard
+    with pytest.raises(Exception):
+        GalleryShard(x).search(x, 5)
