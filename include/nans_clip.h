@@ -106,8 +106,10 @@ int nans_clip_loss_fwd_phase(const void* I_loc, const void* T_loc, int64_t ld_lo
 
 /*
  * Merge the slots.  Outputs (all device, fp32):
- *   lse_img_loc [n_loc]  log-sum-exp of row i of logits_per_image (natural log)
- *   lse_txt_loc [n_loc]  log-sum-exp of row j of logits_per_text
+ *   lse_img_loc [n_loc]  log-sum-exp of row i of logits_per_image, in the kernels' BASE-2 domain:
+ *                        lse2_i = log2 sum_j 2^(s * log2(e) * cos_ij) = logsumexp_j(logits_ij) / ln 2
+ *   lse_txt_loc [n_loc]  the same for row j of logits_per_text
+ *                        (base 2 so that the backward reuses them without a rounding round trip)
  *   scalars[8]: [0] sum_i (lse_img_i - logit_ii)     (x 1/(2N) summed over ranks = loss, part 1)
  *               [1] sum_j (lse_txt_j - logit_jj)
  *               [2] sum_i (E_softmax_img_i[cos] - cos_ii)   (d loss / d s numerator, part 1)
@@ -138,8 +140,8 @@ int nans_clip_loss_fwd(const void* I_loc, const void* T_loc, int64_t ld_loc, con
  * rows of the accumulate path, train.py:48-51; pass 0, n_loc for the plain path).
  * d loss / d s is produced by the forward (scalars[2], [3]) — nothing to do here.
  *
- *   lse_img_all, lse_txt_all [N] fp32: the finalize outputs of all ranks, in global row order
- *                                      (each 16-byte aligned)
+ *   lse_img_all, lse_txt_all [N] fp32: the finalize outputs (base-2 lse) of all ranks, in global
+ *                                      row order (each array 16-byte aligned)
  *   grad_out_dev: device pointer to the fp32 upstream gradient of the loss
  *   dI_loc, dT_loc [grad_row_count, D] contiguous, dtype out_dtype (NANS_F32/F16/BF16)
  */

@@ -11,7 +11,7 @@
 // columns), so a unit (= one CTA) owns a 256-feature slice of the output and the logits are
 // recomputed once per slice ("pass").  unit = (strip, row block, pass, column split).
 //
-// TMEM: [0,256) dA slice | [256,320) S/G buffer 0 | [320,384) S/G buffer 1.
+// TMEM: [0,256) dA slice | [256,384) S buffers 0/1 | [384,448) G buffers 0/1 (16-bit, 32 columns).
 // SMEM: A block resident (D <= 512) or streamed in 16 KB chunks; B chunks (64 rows x 64 features,
 //       8 KB) go either through a stream ring (features outside the slice: MMA1 only) or into one
 //       of two 32 KB hold buffers (features of the slice: MMA1, then MMA2 one tile later).
@@ -35,9 +35,11 @@ constexpr int HOLD_BYTES = HOLD_CHUNKS * B_CHUNK;  // 32 KB
 constexpr int NH = 2;
 constexpr int MAX_NA = 6;
 constexpr int MAX_NS = 12;
-constexpr int NUM_THREADS = 256;
+constexpr int SM_WARPS = 8;  // softmax-gradient warps: 4 lane groups x 2 column halves
+constexpr int NUM_THREADS = 128 + SM_WARPS * 32;
 constexpr int TMEM_COLS = 512;
-constexpr int TMEM_S = 256;
+constexpr int TMEM_S = 256;   // two 64-column S buffers
+constexpr int TMEM_G = 384;   // two 32-column G buffers (64 x 16-bit per row)
 constexpr int BAR_BYTES = 512;
 constexpr size_t SMEM_CAP = 227 * 1024;
 constexpr float kGShiftLog2 = 12.0f;  // G is carried as fp16 scaled by 2^12 (|G| <= 2 -> 8192)
@@ -133,17 +135,19 @@ clip_bwd_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
   const int slice_nc = min(HOLD_CHUNKS, p.kchunks - slice_c0);  // chunks in the slice
   const int slice_w = slice_nc * BK;                            // MMA2 N
 
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(tmA);
-    tma_prefetch_desc(tmB);
-    for (int i = 0; i < MAX_NA; ++i) { mbar_init(&fullA[i], 1); mbar_init(&emptyA[i], 1); }
-    for (int i = 0; i < MAX_NS; ++i) { mbar_init(&fullS[i], 1); mbar_init(&emptyS[i], 1); }
-    for (int i = 0; i < NH * HOLD_CHUNKS; ++i) mbar_init(&fullH[i], 1);
-    for (int i = 0; i < NH; ++i) mbar_init(&emptyH[i], 1);
-    mbar_init(a_full, 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&g_ready[i], 4); }
-    mbar_init(da_full, 1);
-    fence_barrier_init();
+  if (warp == 0) {
+    if (elect_one()) {
+      tma_prefetch_desc(tmA);
+      tma_prefetch_desc(tmB);
+      for (int i = 0; i < MAX_NA; ++i) { mbar_init(&fullA[i], 1); mbar_init(&emptyA[i], 1); }
+      for (int i = 0; i < MAX_NS; ++i) { mbar_init(&fullS[i], 1); mbar_init(&emptyS[i], 1); }
+      for (int i = 0; i < NH * HOLD_CHUNKS; ++i) mbar_init(&fullH[i], 1);
+      for (int i = 0; i < NH; ++i) mbar_init(&emptyH[i], 1);
+      mbar_init(a_full, 1);
+      for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&g_ready[i], SM_WARPS); }
+      mbar_init(da_full, 1);
+      fence_barrier_init();
+    }
   } else if (warp == 2) {
     tmem_alloc(tmem_ptr, TMEM_COLS);
     tmem_relinquish();
@@ -154,140 +158,141 @@ clip_bwd_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ---------------- TMA producer ----------------
-      if (A_RES) {
+    // ---------------- TMA producer (warp-uniform loop, one elected lane issues) ----------------
+    if (A_RES) {
+      if (elect_one()) {
         mbar_arrive_expect_tx(a_full, static_cast<uint32_t>(p.kchunks) * A_CHUNK);
         for (int c = 0; c < p.kchunks; ++c)
           tma_load_2d(smA + static_cast<size_t>(c) * A_CHUNK, tmA, a_full, c * BK, row0);
       }
-      int sa = 0, ss = 0;
-      uint32_t pa = 0, ps = 0;
-      for (int t = 0; t < ntiles; ++t) {
-        const int col0 = (tile_begin + t) * KT;
-        const int h = t % NH;
-        const uint32_t ph = static_cast<uint32_t>(t / NH) & 1u;
-        for (int c = 0; c < p.kchunks; ++c) {
-          if (c >= slice_c0 && c < slice_c0 + slice_nc) continue;
+      __syncwarp();
+    }
+    int sa = 0, ss = 0;
+    uint32_t pa = 0, ps = 0;
+    for (int t = 0; t < ntiles; ++t) {
+      const int col0 = (tile_begin + t) * KT;
+      const int h = t % NH;
+      const uint32_t ph = static_cast<uint32_t>(t / NH) & 1u;
+      for (int c = 0; c < p.kchunks; ++c) {
+        if (c >= slice_c0 && c < slice_c0 + slice_nc) continue;
+        if (!A_RES) mbar_wait(&emptyA[sa], pa ^ 1u);
+        mbar_wait(&emptyS[ss], ps ^ 1u);
+        if (elect_one()) {
           if (!A_RES) {
-            mbar_wait(&emptyA[sa], pa ^ 1u);
             mbar_arrive_expect_tx(&fullA[sa], A_CHUNK);
             tma_load_2d(smA + static_cast<size_t>(sa) * A_CHUNK, tmA, &fullA[sa], c * BK, row0);
-            if (++sa == p.na) { sa = 0; pa ^= 1u; }
           }
-          mbar_wait(&emptyS[ss], ps ^ 1u);
           mbar_arrive_expect_tx(&fullS[ss], B_CHUNK);
           tma_load_2d(smS + static_cast<size_t>(ss) * B_CHUNK, tmB, &fullS[ss], c * BK, col0);
-          if (++ss == p.ns) { ss = 0; ps ^= 1u; }
         }
-        mbar_wait(&emptyH[h], ph ^ 1u);
-        for (int ci = 0; ci < slice_nc; ++ci) {
-          const int c = slice_c0 + ci;
+        __syncwarp();
+        if (!A_RES) { if (++sa == p.na) { sa = 0; pa ^= 1u; } }
+        if (++ss == p.ns) { ss = 0; ps ^= 1u; }
+      }
+      mbar_wait(&emptyH[h], ph ^ 1u);
+      for (int ci = 0; ci < slice_nc; ++ci) {
+        const int c = slice_c0 + ci;
+        if (!A_RES) mbar_wait(&emptyA[sa], pa ^ 1u);
+        if (elect_one()) {
           if (!A_RES) {
-            mbar_wait(&emptyA[sa], pa ^ 1u);
             mbar_arrive_expect_tx(&fullA[sa], A_CHUNK);
             tma_load_2d(smA + static_cast<size_t>(sa) * A_CHUNK, tmA, &fullA[sa], c * BK, row0);
-            if (++sa == p.na) { sa = 0; pa ^= 1u; }
           }
           uint64_t* fb = &fullH[h * HOLD_CHUNKS + ci];
           mbar_arrive_expect_tx(fb, B_CHUNK);
           tma_load_2d(smH + static_cast<size_t>(h) * HOLD_BYTES + static_cast<size_t>(ci) * B_CHUNK,
                       tmB, fb, c * BK, col0);
         }
+        __syncwarp();
+        if (!A_RES) { if (++sa == p.na) { sa = 0; pa ^= 1u; } }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ---------------- MMA issuer ----------------
-      const uint32_t fmt = p.idesc1_fmt;
-      const uint32_t idesc1 = make_idesc(fmt, fmt, 0, 0, BM, KT);
-      const uint32_t idesc2 = make_idesc(p.g_fmt, fmt, 0, /*B MN-major*/ 1, BM, slice_w);
-      if (A_RES) {
-        mbar_wait(a_full, 0);
-        tc_fence_after();
-      }
-      int sa = 0, ss = 0;
-      uint32_t pa = 0, ps = 0;
-
-      auto issue_mma2 = [&](int u) {
-        const int gb = u & 1;
-        mbar_wait(&g_ready[gb], static_cast<uint32_t>(u >> 1) & 1u);
-        tc_fence_after();
-        const int h = u % NH;
-        const uint32_t hb = smem_u32(smH + static_cast<size_t>(h) * HOLD_BYTES);
-#pragma unroll
-        for (int kk = 0; kk < KT / 16; ++kk) {
-          const uint64_t bd = make_smem_desc(hb + kk * 16 * 128, B_CHUNK, 1024);
-          mma_ts(tmem_base, tmem_base + TMEM_S + gb * KT + kk * 8, bd, idesc2,
-                 (u > 0 || kk > 0) ? 1u : 0u);
-        }
-        tc_commit(&emptyH[h]);
-      };
-
-      for (int t = 0; t < ntiles; ++t) {
-        const uint32_t d_S = tmem_base + TMEM_S + (t & 1) * KT;
-        const int h = t % NH;
-        const uint32_t ph = static_cast<uint32_t>(t / NH) & 1u;
-        uint32_t acc = 0;
-        for (int c = 0; c < p.kchunks; ++c) {
-          if (c >= slice_c0 && c < slice_c0 + slice_nc) continue;
-          if (!A_RES) {
-            mbar_wait(&fullA[sa], pa);
-          }
-          mbar_wait(&fullS[ss], ps);
-          tc_fence_after();
-          const uint32_t a_addr = smem_u32(smA + static_cast<size_t>(A_RES ? c : sa) * A_CHUNK);
-          const uint32_t b_addr = smem_u32(smS + static_cast<size_t>(ss) * B_CHUNK);
-#pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            mma_ss(d_S, make_smem_desc(a_addr + k * 32, 16, 1024),
-                   make_smem_desc(b_addr + k * 32, 16, 1024), idesc1, acc);
-            acc = 1;
-          }
-          tc_commit(&emptyS[ss]);
-          if (++ss == p.ns) { ss = 0; ps ^= 1u; }
-          if (!A_RES) {
-            tc_commit(&emptyA[sa]);
-            if (++sa == p.na) { sa = 0; pa ^= 1u; }
-          }
-        }
-        for (int ci = 0; ci < slice_nc; ++ci) {
-          const int c = slice_c0 + ci;
-          if (!A_RES) {
-            mbar_wait(&fullA[sa], pa);
-          }
-          mbar_wait(&fullH[h * HOLD_CHUNKS + ci], ph);
-          tc_fence_after();
-          const uint32_t a_addr = smem_u32(smA + static_cast<size_t>(A_RES ? c : sa) * A_CHUNK);
-          const uint32_t b_addr = smem_u32(smH + static_cast<size_t>(h) * HOLD_BYTES +
-                                           static_cast<size_t>(ci) * B_CHUNK);
-#pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            mma_ss(d_S, make_smem_desc(a_addr + k * 32, 16, 1024),
-                   make_smem_desc(b_addr + k * 32, 16, 1024), idesc1, acc);
-            acc = 1;
-          }
-          if (!A_RES) {
-            tc_commit(&emptyA[sa]);
-            if (++sa == p.na) { sa = 0; pa ^= 1u; }
-          }
-        }
-        tc_commit(&s_full[t & 1]);
-        if (t > 0) issue_mma2(t - 1);
-      }
-      issue_mma2(ntiles - 1);
-      tc_commit(da_full);
+    // ---------------- MMA issuer (warp-uniform loop, one elected lane issues) ----------------
+    const uint32_t fmt = p.idesc1_fmt;
+    const uint32_t idesc1 = make_idesc(fmt, fmt, 0, 0, BM, KT);
+    const uint32_t idesc2 = make_idesc(p.g_fmt, fmt, 0, /*B MN-major*/ 1, BM, slice_w);
+    const uint32_t smA_addr = smem_u32(smA), smH_addr = smem_u32(smH), smS_addr = smem_u32(smS);
+    if (A_RES) {
+      mbar_wait(a_full, 0);
+      tc_fence_after();
     }
+    int sa = 0, ss = 0;
+    uint32_t pa = 0, ps = 0;
+
+    auto issue_mma2 = [&](int u) {
+      const int gb = u & 1;
+      mbar_wait(&g_ready[gb], static_cast<uint32_t>(u >> 1) & 1u);
+      tc_fence_after();
+      const int h = u % NH;
+      if (elect_one()) {
+        const uint64_t bd = make_smem_desc(smH_addr + static_cast<uint32_t>(h) * HOLD_BYTES, B_CHUNK, 1024);
+#pragma unroll
+        for (int kk = 0; kk < KT / 16; ++kk)  // 16 K-rows = 16 x 128 B = 2048 B (>> 4 = 128) per step
+          mma_ts(tmem_base, tmem_base + TMEM_G + gb * (KT / 2) + kk * 8, bd + 128 * kk, idesc2,
+                 (u > 0 || kk > 0) ? 1u : 0u);
+        tc_commit(&emptyH[h]);
+      }
+      __syncwarp();
+    };
+
+    for (int t = 0; t < ntiles; ++t) {
+      const uint32_t d_S = tmem_base + TMEM_S + (t & 1) * KT;
+      const int h = t % NH;
+      const uint32_t ph = static_cast<uint32_t>(t / NH) & 1u;
+      uint32_t acc = 0;
+      for (int c = 0; c < p.kchunks; ++c) {
+        if (c >= slice_c0 && c < slice_c0 + slice_nc) continue;
+        if (!A_RES) mbar_wait(&fullA[sa], pa);
+        mbar_wait(&fullS[ss], ps);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t ad = make_smem_desc(smA_addr + static_cast<uint32_t>(A_RES ? c : sa) * A_CHUNK, 16, 1024);
+          const uint64_t bd = make_smem_desc(smS_addr + static_cast<uint32_t>(ss) * B_CHUNK, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) mma_ss(d_S, ad + 2 * k, bd + 2 * k, idesc1, (acc | k) != 0 ? 1u : 0u);
+          tc_commit(&emptyS[ss]);
+          if (!A_RES) tc_commit(&emptyA[sa]);
+        }
+        __syncwarp();
+        acc = 1;
+        if (++ss == p.ns) { ss = 0; ps ^= 1u; }
+        if (!A_RES) { if (++sa == p.na) { sa = 0; pa ^= 1u; } }
+      }
+      for (int ci = 0; ci < slice_nc; ++ci) {
+        const int c = slice_c0 + ci;
+        if (!A_RES) mbar_wait(&fullA[sa], pa);
+        mbar_wait(&fullH[h * HOLD_CHUNKS + ci], ph);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t ad = make_smem_desc(smA_addr + static_cast<uint32_t>(A_RES ? c : sa) * A_CHUNK, 16, 1024);
+          const uint64_t bd = make_smem_desc(
+              smH_addr + static_cast<uint32_t>(h) * HOLD_BYTES + static_cast<uint32_t>(ci) * B_CHUNK, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) mma_ss(d_S, ad + 2 * k, bd + 2 * k, idesc1, (acc | k) != 0 ? 1u : 0u);
+          if (!A_RES) tc_commit(&emptyA[sa]);
+          if (ci == slice_nc - 1) tc_commit(&s_full[t & 1]);
+        }
+        __syncwarp();
+        acc = 1;
+        if (!A_RES) { if (++sa == p.na) { sa = 0; pa ^= 1u; } }
+      }
+      if (t > 0) issue_mma2(t - 1);
+    }
+    issue_mma2(ntiles - 1);
+    if (elect_one()) tc_commit(da_full);
+    __syncwarp();
   } else if (warp >= 4) {
-    // ---------------- softmax-gradient warps: thread = row ----------------
+    // ---------------- softmax-gradient warps: thread = (row, 32-column half) ----------------
     const int wq = warp & 3;
+    const int half = (warp - 4) >> 2;
     const uint32_t lane_base = static_cast<uint32_t>(wq * 32) << 16;
     const int row = row0 + wq * 32 + lane;
     const bool valid = row < p.row_end;
     const float s = __ldg(p.s_dev);
     const float c = s * kLog2e;
-    // 2^12 * exp(s cos - lse) = 2^(cos * c - (lse * log2e - 12))
-    const float lr2 = valid ? fmaf(__ldg(p.lse_row[strip] + row), kLog2e, -kGShiftLog2) : INFINITY;
+    // 2^12 * exp(s cos - lse) = 2^(cos * c - (lse2 - 12)), lse2 = base-2 lse from the forward
+    const float lr2 = valid ? __ldg(p.lse_row[strip] + row) - kGShiftLog2 : INFINITY;
     const float* lse_col = p.lse_col[strip];
     const int label = row + p.label_shift;
     const int warp_label_lo = label - lane;
@@ -297,60 +302,54 @@ clip_bwd_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
       const int sb = t & 1;
       mbar_wait(&s_full[sb], static_cast<uint32_t>(t >> 1) & 1u);
       tc_fence_after();
-      const int col0 = (tile_begin + t) * KT;
-      const uint32_t s_addr = tmem_base + lane_base + TMEM_S + sb * KT;
-      const bool has_label = (warp_label_lo < col0 + KT) && (warp_label_lo + 31 >= col0);
-      const bool tail = col0 + KT > p.ncols;
+      const int cb = (tile_begin + t) * KT + half * 32;
+      const bool has_label = (warp_label_lo < cb + 32) && (warp_label_lo + 31 >= cb);
+      uint32_t r[32];
+      tmem_ld32(tmem_base + lane_base + TMEM_S + sb * KT + half * 32, r);
+      float lc2[32];
+      if (cb + 32 <= p.ncols) {
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        uint32_t r[32];
-        tmem_ld32(s_addr + half * 32, r);
-        float lc2[32];
-        const int cb = col0 + half * 32;
-        if (!tail) {
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const float4 f = __ldg(reinterpret_cast<const float4*>(lse_col + cb) + q);
-            lc2[4 * q + 0] = f.x; lc2[4 * q + 1] = f.y; lc2[4 * q + 2] = f.z; lc2[4 * q + 3] = f.w;
-          }
-        } else {
-#pragma unroll
-          for (int k = 0; k < 32; ++k) lc2[k] = __ldg(lse_col + min(cb + k, p.ncols - 1));
+        for (int q = 0; q < 8; ++q) {
+          const float4 f = __ldg(reinterpret_cast<const float4*>(lse_col + cb) + q);
+          lc2[4 * q + 0] = f.x; lc2[4 * q + 1] = f.y; lc2[4 * q + 2] = f.z; lc2[4 * q + 3] = f.w;
         }
-        tmem_wait_ld();
-        uint32_t g16[16];
+      } else {
 #pragma unroll
-        for (int k = 0; k < 32; k += 2) {
-          float g[2];
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const float cosv = __uint_as_float(r[k + e]);
-            const float lcv = fmaf(lc2[k + e], kLog2e, -kGShiftLog2);
-            g[e] = fast_exp2(fmaf(cosv, c, -lr2)) + fast_exp2(fmaf(cosv, c, -lcv));
-            if (has_label && cb + k + e == label) g[e] -= 8192.0f;  // 2 * 2^12
-          }
-          if (g_bf16) {
-            const __nv_bfloat162 hh = __floats2bfloat162_rn(g[0], g[1]);
-            g16[k >> 1] = *reinterpret_cast<const uint32_t*>(&hh);
-          } else {
-            const __half2 hh = __floats2half2_rn(g[0], g[1]);
-            g16[k >> 1] = *reinterpret_cast<const uint32_t*>(&hh);
-          }
-        }
-        tmem_st16(s_addr + half * 16, g16);
+        for (int k = 0; k < 32; ++k) lc2[k] = __ldg(lse_col + min(cb + k, p.ncols - 1));
       }
+      tmem_wait_ld();
+      uint32_t g16[16];
+#pragma unroll
+      for (int k = 0; k < 32; k += 2) {
+        float g[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const float cosv = __uint_as_float(r[k + e]);
+          const float lcv = lc2[k + e] - kGShiftLog2;
+          g[e] = fast_exp2(fmaf(cosv, c, -lr2)) + fast_exp2(fmaf(cosv, c, -lcv));
+          if (has_label && cb + k + e == label) g[e] -= 8192.0f;  // 2 * 2^12
+        }
+        if (g_bf16) {
+          const __nv_bfloat162 hh = __floats2bfloat162_rn(g[0], g[1]);
+          g16[k >> 1] = *reinterpret_cast<const uint32_t*>(&hh);
+        } else {
+          const __half2 hh = __floats2half2_rn(g[0], g[1]);
+          g16[k >> 1] = *reinterpret_cast<const uint32_t*>(&hh);
+        }
+      }
+      tmem_st16(tmem_base + lane_base + TMEM_G + sb * (KT / 2) + half * 16, g16);
       tmem_wait_st();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&g_ready[sb]);
     }
 
-    // ---- write the dA slice ----
+    // ---- write the dA slice: the two halves take alternate 32-column chunks ----
     mbar_wait(da_full, 0);
     tc_fence_after();
     const float coef = __ldg(p.grad_out_dev) * s * p.coef_host;
     float* out = p.out[strip] + static_cast<long long>(row - p.row_begin) * p.D + pass * SLICE;
-    for (int ch = 0; ch < slice_w / 32; ++ch) {
+    for (int ch = half; ch < slice_w / 32; ch += 2) {
       uint32_t r[32];
       tmem_ld32(tmem_base + lane_base + ch * 32, r);
       tmem_wait_ld();

@@ -60,16 +60,19 @@ struct LseEpi {
     bi = -1;
   }
 
-  __device__ __forceinline__ void tile(uint32_t taddr, int tile_idx) {
+  __device__ __forceinline__ void tile(uint32_t taddr, int tile_idx, int ch_begin, int ch_end) {
     const int col0 = tile_idx * BN;
     const bool tail = col0 + BN > ncols;
     const bool has_label = (warp_label_lo < col0 + BN) && (warp_label_lo + 31 >= col0);
 #pragma unroll 1
-    for (int ch = 0; ch < BN / 32; ++ch) {
+    for (int ch = ch_begin; ch < ch_end; ++ch) {
+      const int cb = col0 + ch * 32;
+      if (cb >= ncols) break;  // whole chunk past the last column: the running max must only
+                               // ever come from real columns (an all-masked max would make
+                               // exp2(v*c - m) a rounding-error lottery)
       uint32_t r[32];
       tmem_ld32(taddr + ch * 32, r);
       tmem_wait_ld();
-      const int cb = col0 + ch * 32;
       float v[32];
 #pragma unroll
       for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(r[k]);
@@ -142,22 +145,56 @@ clip_fwd_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
   LseEpi<WITH_ACC> epi;
   epi.init(__ldg(p.s_dev) * kLog2e, p.ncols, row + p.label_shift, lane);
 
-  run<A_RES>(a, epi);
+  uint8_t* scratch = run<A_RES>(a, epi);
 
-  if (warp >= 4 && row < p.n_loc) {
+  // The two column halves of a row live in two threads (warps 4-7 and 8-11): merge through
+  // shared memory (the pipeline buffers are dead after run()).
+  float* xm = reinterpret_cast<float*>(scratch);  // [6][128]
+  const int r = (warp & 3) * 32 + lane;
+  float L = (epi.l[0] + epi.l[1]) + (epi.l[2] + epi.l[3]);
+  float Wt = (epi.w[0] + epi.w[1]) + (epi.w[2] + epi.w[3]);
+  const int cbeg = a.tile_begin * BN;
+  const int cend = min(a.tile_end * BN, p.ncols);
+  const bool has_diag = epi.label >= cbeg && epi.label < cend;
+  if (warp >= 8) {
+    xm[0 * 128 + r] = epi.m;
+    xm[1 * 128 + r] = L;
+    xm[2 * 128 + r] = Wt;
+    xm[3 * 128 + r] = epi.diag;
+    xm[4 * 128 + r] = epi.bv;
+    reinterpret_cast<int*>(xm)[5 * 128 + r] = epi.bi;
+  }
+  __syncthreads();
+  if (warp >= 4 && warp < 8 && row < p.n_loc) {
+    const float m2 = xm[0 * 128 + r];
+    const float M = fmaxf(epi.m, m2);
+    const float s1 = fast_exp2(epi.m - M), s2 = fast_exp2(m2 - M);
+    L = L * s1 + xm[1 * 128 + r] * s2;
+    Wt = Wt * s1 + xm[2 * 128 + r] * s2;
+    // the label column lies in exactly one half: whichever thread saw it holds cos there
+    const int half_cols = BN / 2;
+    const int lab_in_tile = epi.label - (epi.label / BN) * BN;
+    const float diag = (lab_in_tile < half_cols) ? epi.diag : xm[3 * 128 + r];
+    float bv = epi.bv;
+    int bi = epi.bi;
+    if (WITH_ACC) {
+      const float bv2 = xm[4 * 128 + r];
+      const int bi2 = reinterpret_cast<const int*>(xm)[5 * 128 + r];
+      if (bv2 > bv || (bv2 == bv && bi2 >= 0 && (bi < 0 || bi2 < bi))) {
+        bv = bv2;
+        bi = bi2;
+      }
+    }
     const long long idx = static_cast<long long>(p.slot_begin + split) * p.slot_stride +
                           static_cast<long long>(strip) * p.n_loc + row;
-    p.part_m[idx] = epi.m;
-    p.part_l[idx] = (epi.l[0] + epi.l[1]) + (epi.l[2] + epi.l[3]);
-    p.part_w[idx] = (epi.w[0] + epi.w[1]) + (epi.w[2] + epi.w[3]);
+    p.part_m[idx] = M;
+    p.part_l[idx] = L;
+    p.part_w[idx] = Wt;
     if (WITH_ACC) {
-      p.part_bv[idx] = epi.bv;
-      p.part_bi[idx] = epi.bi < 0 ? -1 : epi.bi + p.col_global_begin;
+      p.part_bv[idx] = bv;
+      p.part_bi[idx] = bi < 0 ? -1 : bi + p.col_global_begin;
     }
-    const int cbeg = a.tile_begin * BN;
-    const int cend = min(a.tile_end * BN, p.ncols);
-    if (epi.label >= cbeg && epi.label < cend)
-      p.diag[static_cast<long long>(strip) * p.n_loc + row] = epi.diag;
+    if (has_diag) p.diag[static_cast<long long>(strip) * p.n_loc + row] = diag;
   }
 }
 
@@ -208,9 +245,10 @@ __global__ void __launch_bounds__(256) clip_fwd_finalize_kernel(const FinParams 
       }
     }
     const float sc = __ldg(p.s_dev);
-    const float lse = (M + log2f(L)) * kLn2;
+    const float lse2 = M + log2f(L);  // base-2 domain: log2 sum_j 2^(cos_ij * s * log2 e)
+    const float lse = lse2 * kLn2;
     const float cosd = p.diag[gid];
-    (strip == 0 ? p.lse_img : p.lse_txt)[row] = lse;
+    (strip == 0 ? p.lse_img : p.lse_txt)[row] = lse2;
     acc[strip] = static_cast<double>(lse) - static_cast<double>(sc) * cosd;
     acc[2 + strip] = static_cast<double>(Wt) / static_cast<double>(L) - cosd;
     if (p.with_acc) acc[4 + strip] = (bi == p.label_begin + row) ? 1.0 : 0.0;

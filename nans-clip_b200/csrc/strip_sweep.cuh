@@ -8,7 +8,7 @@
 //   warp 0    : TMA producer   (A block once if it fits in smem, else per K-chunk; B per K-chunk)
 //   warp 1    : tcgen05.mma issuer (one lane)
 //   warp 2    : TMEM allocator (512 columns = two 128x256 fp32 accumulators, double-buffered)
-//   warps 4-7 : epilogue, thread = row (TMEM lane), tcgen05.ld 32 columns at a time
+//   warps 4-11: epilogue, thread = (row = TMEM lane, column half), tcgen05.ld 32 columns at a time
 //
 // Shared memory (128-byte swizzle, K-major, 64 elements per line):
 //   A resident: kchunks x 16 KB  +  stages x 32 KB (B)      when that fits (D <= 640)
@@ -24,7 +24,8 @@ constexpr int BN = 256;
 constexpr int BK = 64;
 constexpr int A_CHUNK = BM * BK * 2;  // 16 KB
 constexpr int B_STAGE = BN * BK * 2;  // 32 KB
-constexpr int NUM_THREADS = 256;
+constexpr int EPI_WARPS = 8;
+constexpr int NUM_THREADS = 128 + EPI_WARPS * 32;
 constexpr int MAX_STAGES = 6;
 constexpr int TMEM_COLS = 512;
 constexpr int BAR_BYTES = 256;
@@ -67,10 +68,13 @@ struct SweepArgs {
   uint32_t idesc;  // M=128, N=256, K-major A and B, fp32 accumulate
 };
 
-// Epi must provide:  __device__ void tile(uint32_t taddr, int tile_idx)
-//   taddr = TMEM address of this thread's warp lane group at column 0 of the accumulator buffer.
+// Epi must provide:  __device__ void tile(uint32_t taddr, int tile_idx, int chunk_begin, int chunk_end)
+//   taddr = TMEM address of this thread's warp lane group at column 0 of the accumulator buffer;
+//   the thread handles the 32-column chunks [chunk_begin, chunk_end) of the tile.
+// Returns the 1 KB-aligned base of the dynamic shared memory, free for reuse after the call
+// (all TMA loads and MMAs of this CTA have completed and every thread has passed a barrier).
 template <bool A_RES, class Epi>
-__device__ __forceinline__ void run(const SweepArgs& a, Epi& epi) {
+__device__ __forceinline__ uint8_t* run(const SweepArgs& a, Epi& epi) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -87,19 +91,21 @@ __device__ __forceinline__ void run(const SweepArgs& a, Epi& epi) {
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(a.tmA);
-    tma_prefetch_desc(a.tmB);
-    for (int i = 0; i < a.stages; ++i) {
-      mbar_init(&full[i], 1);
-      mbar_init(&empty[i], 1);
+  if (warp == 0) {
+    if (elect_one()) {
+      tma_prefetch_desc(a.tmA);
+      tma_prefetch_desc(a.tmB);
+      for (int i = 0; i < a.stages; ++i) {
+        mbar_init(&full[i], 1);
+        mbar_init(&empty[i], 1);
+      }
+      mbar_init(a_full, 1);
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&tfull[i], 1);
+        mbar_init(&tempty[i], EPI_WARPS);
+      }
+      fence_barrier_init();
     }
-    mbar_init(a_full, 1);
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 4);
-    }
-    fence_barrier_init();
   } else if (warp == 2) {
     tmem_alloc(tmem_ptr, TMEM_COLS);
     tmem_relinquish();
@@ -112,71 +118,79 @@ __device__ __forceinline__ void run(const SweepArgs& a, Epi& epi) {
   const int ntiles = a.tile_end - a.tile_begin;
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ---------------- TMA producer ----------------
-      if (A_RES) {
+    // ---------------- TMA producer (whole warp in the loop, one elected lane issues) ----------
+    if (A_RES) {
+      if (elect_one()) {
         mbar_arrive_expect_tx(a_full, static_cast<uint32_t>(a.kchunks) * A_CHUNK);
         for (int c = 0; c < a.kchunks; ++c)
           tma_load_2d(smA + static_cast<size_t>(c) * A_CHUNK, a.tmA, a_full, c * BK, a.row0);
       }
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int t = 0; t < ntiles; ++t) {
-        const int col0 = (a.tile_begin + t) * BN;
-        for (int c = 0; c < a.kchunks; ++c) {
-          mbar_wait(&empty[stage], phase ^ 1u);
+      __syncwarp();
+    }
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int t = 0; t < ntiles; ++t) {
+      const int col0 = (a.tile_begin + t) * BN;
+      for (int c = 0; c < a.kchunks; ++c) {
+        mbar_wait(&empty[stage], phase ^ 1u);
+        if (elect_one()) {
           mbar_arrive_expect_tx(&full[stage], A_RES ? B_STAGE : (A_CHUNK + B_STAGE));
           if (!A_RES)
             tma_load_2d(smA + static_cast<size_t>(stage) * A_CHUNK, a.tmA, &full[stage], c * BK,
                         a.row0);
           tma_load_2d(smB + static_cast<size_t>(stage) * B_STAGE, a.tmB, &full[stage], c * BK, col0);
-          if (++stage == a.stages) { stage = 0; phase ^= 1u; }
         }
+        __syncwarp();
+        if (++stage == a.stages) { stage = 0; phase ^= 1u; }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ---------------- MMA issuer ----------------
-      if (A_RES) {
-        mbar_wait(a_full, 0);
+    // ---------------- MMA issuer ----------------
+    if (A_RES) {
+      mbar_wait(a_full, 0);
+      tc_fence_after();
+    }
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const uint32_t smA_addr = smem_u32(smA);
+    const uint32_t smB_addr = smem_u32(smB);
+    for (int t = 0; t < ntiles; ++t) {
+      mbar_wait(&tempty[acc], acc_phase ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
+      for (int c = 0; c < a.kchunks; ++c) {
+        mbar_wait(&full[stage], phase);
         tc_fence_after();
-      }
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (int t = 0; t < ntiles; ++t) {
-        mbar_wait(&tempty[acc], acc_phase ^ 1u);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
-        for (int c = 0; c < a.kchunks; ++c) {
-          mbar_wait(&full[stage], phase);
-          tc_fence_after();
-          const uint32_t a_addr =
-              smem_u32(smA + static_cast<size_t>(A_RES ? c : stage) * A_CHUNK);
-          const uint32_t b_addr = smem_u32(smB + static_cast<size_t>(stage) * B_STAGE);
+        if (elect_one()) {
+          const uint32_t a_addr = smA_addr + static_cast<uint32_t>(A_RES ? c : stage) * A_CHUNK;
+          const uint32_t b_addr = smB_addr + static_cast<uint32_t>(stage) * B_STAGE;
+          const uint64_t ad = make_smem_desc(a_addr, 16, 1024);
+          const uint64_t bd = make_smem_desc(b_addr, 16, 1024);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            const uint64_t ad = make_smem_desc(a_addr + k * 32, 16, 1024);
-            const uint64_t bd = make_smem_desc(b_addr + k * 32, 16, 1024);
-            mma_ss(d_tmem, ad, bd, a.idesc, (c | k) != 0 ? 1u : 0u);
-          }
+          for (int k = 0; k < BK / 16; ++k)  // +32 bytes (>> 4 = 2) per K step inside the swizzle atom
+            mma_ss(d_tmem, ad + 2 * k, bd + 2 * k, a.idesc, (c | k) != 0 ? 1u : 0u);
           tc_commit(&empty[stage]);  // frees the smem stage once these MMAs have read it
-          if (++stage == a.stages) { stage = 0; phase ^= 1u; }
+          if (c == a.kchunks - 1) tc_commit(&tfull[acc]);  // accumulator complete -> epilogue
         }
-        tc_commit(&tfull[acc]);  // accumulator complete -> epilogue
-        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        __syncwarp();
+        if (++stage == a.stages) { stage = 0; phase ^= 1u; }
       }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
   } else if (warp >= 4) {
-    // ---------------- epilogue ----------------
+    // ---------------- epilogue: 8 warps, lane group = warp % 4, column half = (warp - 4) / 4 ----
     const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    const int half = (warp - 4) >> 2;
+    constexpr int CH = BN / 32 / 2;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int t = 0; t < ntiles; ++t) {
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
-      epi.tile(tmem_base + lane_base + static_cast<uint32_t>(acc * BN), a.tile_begin + t);
+      epi.tile(tmem_base + lane_base + static_cast<uint32_t>(acc * BN), a.tile_begin + t, half * CH,
+               half * CH + CH);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);
@@ -190,6 +204,7 @@ __device__ __forceinline__ void run(const SweepArgs& a, Epi& epi) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
   }
+  return smem;
 }
 
 #endif  // __CUDACC__

@@ -55,15 +55,16 @@ struct TopkEpi {
     }
   }
 
-  __device__ __forceinline__ void tile(uint32_t taddr, int tile_idx) {
+  __device__ __forceinline__ void tile(uint32_t taddr, int tile_idx, int ch_begin, int ch_end) {
     const int col0 = tile_idx * BN;
     const bool tail = col0 + BN > ncols;
 #pragma unroll 1
-    for (int ch = 0; ch < BN / 32; ++ch) {
+    for (int ch = ch_begin; ch < ch_end; ++ch) {
+      const int cb = col0 + ch * 32;
+      if (cb >= ncols) break;
       uint32_t r[32];
       tmem_ld32(taddr + ch * 32, r);
       tmem_wait_ld();
-      const int cb = col0 + ch * 32;
       float v[32];
 #pragma unroll
       for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(r[k]);
@@ -72,26 +73,21 @@ struct TopkEpi {
         for (int k = 0; k < 32; ++k)
           if (cb + k >= ncols) v[k] = -INFINITY;
       }
-      const float thr = ls[KC - 1];
-      bool any = false;
+      // common case: nothing in the chunk beats the list's minimum -> one max tree + one compare
+      float mx[8];
 #pragma unroll
-      for (int k = 0; k < 32; ++k) any |= (v[k] > thr);
-      if (any) {
-        // rare path: repeatedly take the chunk's maximum (lowest column on ties)
-        while (true) {
-          float bv = v[0];
-          int bk = 0;
+      for (int i = 0; i < 8; ++i) mx[i] = fmaxf(fmaxf(v[i], v[i + 8]), fmaxf(v[i + 16], v[i + 24]));
+      const float m = fmaxf(fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])),
+                            fmaxf(fmaxf(mx[4], mx[5]), fmaxf(mx[6], mx[7])));
+      if (__any_sync(0xffffffffu, m > ls[KC - 1])) {
+        // rare path (entered by the whole warp): ascending column order so that equal scores keep
+        // the lower index first; a column is skipped with one vote unless some row wants it
 #pragma unroll
-          for (int k = 1; k < 32; ++k)
-            if (v[k] > bv) {
-              bv = v[k];
-              bk = k;
-            }
-          if (!(bv > ls[KC - 1])) break;
-          insert(bv, cb + bk);
-#pragma unroll
-          for (int k = 0; k < 32; ++k)
-            if (k == bk) v[k] = -INFINITY;
+        for (int k = 0; k < 32; ++k) {
+          const bool q = v[k] > ls[KC - 1];
+          if (__any_sync(0xffffffffu, q)) {
+            if (q) insert(v[k], cb + k);
+          }
         }
       }
     }
@@ -102,7 +98,7 @@ struct TopkParams {
   int Q, G, kchunks, stages;
   uint32_t idesc;
   int nqb, nsplit, ntiles;
-  float* cand_s;  // [nsplit][Q][KC]
+  float* cand_s;  // [nsplit * 2][Q][KC]  (one list per gallery split and column half)
   int* cand_i;
 };
 
@@ -133,7 +129,8 @@ topk_sweep_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   run<A_RES>(a, epi);
 
   if (warp >= 4 && row < p.Q) {
-    const long long base = (static_cast<long long>(split) * p.Q + row) * KC;
+    const int half = (warp - 4) >> 2;  // each row has one list per column half
+    const long long base = (static_cast<long long>(split * 2 + half) * p.Q + row) * KC;
 #pragma unroll
     for (int i = 0; i < KC; i += 4) {
       *reinterpret_cast<float4*>(p.cand_s + base + i) =
@@ -153,7 +150,7 @@ __device__ __forceinline__ bool beats(float sa, long long ia, float sb, long lon
 }
 
 constexpr int FIN_WARPS = 4;
-constexpr int FIN_MAXC = 1024;  // nsplit (<= 32) * k_cand (<= 32)
+constexpr int FIN_MAXC = 1024;  // nsplit (<= 16) * 2 halves * k_cand (<= 32)
 constexpr int MERGE_MAXC = 512;  // n_shards * k
 
 struct FinParams {
@@ -175,7 +172,7 @@ __global__ void __launch_bounds__(FIN_WARPS * 32) topk_finalize_kernel(const Fin
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q = blockIdx.x * FIN_WARPS + w;
   if (q >= p.Q) return;
-  const int C = p.nsplit * p.kc;
+  const int C = p.nsplit * 2 * p.kc;
   for (int c = lane; c < C; c += 32) {
     const int sp = c / p.kc, j = c - sp * p.kc;
     const long long src = (static_cast<long long>(sp) * p.Q + q) * p.kc + j;
@@ -291,7 +288,7 @@ int choose_topk_nsplit(int64_t Q, int64_t G) {
   const int sms = sm_count();
   int best = 1;
   double best_cost = 1e300;
-  const int64_t max_ns = ntiles < 32 ? ntiles : 32;
+  const int64_t max_ns = ntiles < 16 ? ntiles : 16;  // 16 splits x 2 halves x 32 candidates = FIN_MAXC
   for (int64_t ns = 1; ns <= max_ns; ++ns) {
     const double waves = static_cast<double>(ceil_div(base * ns, sms));
     const double cost = waves * (static_cast<double>(ceil_div(ntiles, ns)) + 0.75);
@@ -312,7 +309,7 @@ extern "C" size_t nans_topk_ip_workspace_bytes(int64_t Q, int64_t G, int64_t D, 
   (void)D;
   if (Q <= 0 || G <= 0 || k_cand <= 0) return 256;
   const int ns = choose_topk_nsplit(Q, G);
-  return 2 * align_up(static_cast<size_t>(ns) * Q * k_cand * 4, 256) + 256;
+  return 2 * align_up(static_cast<size_t>(ns) * 2 * Q * k_cand * 4, 256) + 256;
 }
 
 extern "C" int nans_topk_ip(const void* Q16, const void* G16, int feat_dtype, const float* Q32,
@@ -369,7 +366,7 @@ extern "C" int nans_topk_ip(const void* Q16, const void* G16, int feat_dtype, co
   p.ntiles = static_cast<int>(ceil_div(G, BN));
   p.cand_s = static_cast<float*>(ws);
   p.cand_i = reinterpret_cast<int*>(static_cast<uint8_t*>(ws) +
-                                    align_up(static_cast<size_t>(nsplit) * Q * k_cand * 4, 256));
+                                    align_up(static_cast<size_t>(nsplit) * 2 * Q * k_cand * 4, 256));
 
   void (*kern)(const CUtensorMap, const CUtensorMap, const TopkParams);
   if (k_cand == 16) kern = plan.a_resident ? topk_sweep_kernel<true, 16> : topk_sweep_kernel<false, 16>;

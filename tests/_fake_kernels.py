@@ -75,9 +75,9 @@ def fwd_finalize(n_loc, total_slots, label_begin, s_dev, with_acc, ws):
         best = bv.max(0).values
         cand = torch.where(bv == best[None], bi, torch.full_like(bi, 1 << 60))
         arg = cand.min(0).values
-        lse[strip] = (M + torch.log2(L)) * math.log(2)
+        lse[strip] = M + torch.log2(L)  # base-2 domain, as the kernel returns it
         d = st["diag"][strip]
-        sc[strip] = (lse[strip].double() - s * d.double()).sum()
+        sc[strip] = (lse[strip].double() * math.log(2) - s * d.double()).sum()
         sc[2 + strip] = ((Wt / L).double() - d.double()).sum()
         if with_acc:
             sc[4 + strip] = (arg == torch.arange(n_loc) + label_begin).sum()
@@ -91,8 +91,8 @@ def bwd(I_loc, T_loc, T_all, I_all, *, label_begin, s_dev, lse_all, grad_out, gr
     rows = slice(row_begin, row_begin + row_count)
     outs = []
     for strip, (A, B) in enumerate(((I_loc, T_all), (T_loc, I_all))):
-        lr = lse_all[strip][label_begin + row_begin: label_begin + row_begin + row_count]
-        lc = lse_all[1 - strip]
+        lr = lse_all[strip][label_begin + row_begin: label_begin + row_begin + row_count] * math.log(2)
+        lc = lse_all[1 - strip] * math.log(2)
         S = s * A[rows].float() @ B.float().t()
         G = torch.exp(S - lr[:, None]) + torch.exp(S - lc[None, :])
         idx = torch.arange(row_count)

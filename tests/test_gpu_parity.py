@@ -43,9 +43,14 @@ def relerr(got, want, floor=0.0):
     return float((got.double() - want.double()).norm() / max(float(want.double().norm()), floor))
 
 
-def grad_floor(n, d, s):
-    """Norm of a gradient whose entries are 1e-7 * s / (2n): fp32 exp() noise on a saturated softmax."""
-    return 1e-4 * s / (2 * n) * math.sqrt(n * d) + 1e-30
+def grad_ok(got, want, n, s, tol=TOL):
+    """||got - want|| <= tol * ||want|| + absolute floor.  The floor covers a saturated softmax, where
+    the true gradient is ~1e-13 of its usual size: G = p_row + p_col - 2*delta is then a cancellation
+    of numbers near 2 computed with fp32 exp2 (argument error ~ s * 2^-23), i.e. |dG| ~ 3e-5 per row,
+    and a gradient row is s / (2n) * G @ B with unit-norm rows of B."""
+    err = float((got.double() - want.double()).norm())
+    floor = 3e-5 * s / (2 * n) * math.sqrt(n)
+    return err <= tol * float(want.double().norm()) + floor
 
 
 # --------------------------------------------------------------------------------------------
@@ -113,13 +118,14 @@ def test_loss_matches_reference_get_loss(dev, golden_dir, name):
     I, T, s = torch.from_numpy(g["img"]), torch.from_numpy(g["txt"]), float(g["s"])
     n, d = I.shape
     loss, acc, dI, dT, ds = run_loss(dev, I, T, s, torch.bfloat16 if name != "d" else torch.float16)
-    assert abs(float(loss) - float(g["loss"])) <= TOL * max(abs(float(g["loss"])), 1e-4)
+    # absolute floor: the loss is a mean of (lse - logit) with |logit| <= s, i.e. fp32 ulp(s) noise
+    assert abs(float(loss) - float(g["loss"])) <= TOL * abs(float(g["loss"])) + 1e-6 * s
     assert abs(float(acc["i2t"]) - float(g["i2t"])) < 1e-6 and abs(float(acc["t2i"]) - float(g["t2i"])) < 1e-6
     tol = TOL if name == "d" else 3e-3  # bf16 operand for G: see DESIGN.md "Precision"
-    assert relerr(dI, torch.from_numpy(g["dI"]), grad_floor(n, d, s)) < tol
-    assert relerr(dT, torch.from_numpy(g["dT"]), grad_floor(n, d, s)) < tol
+    assert grad_ok(dI, torch.from_numpy(g["dI"]), n, s, tol)
+    assert grad_ok(dT, torch.from_numpy(g["dT"]), n, s, tol)
     want_ds = float(g["dlogit_scale_log"]) / s
-    assert abs(float(ds) - want_ds) <= TOL * abs(want_ds) + 1e-7
+    assert abs(float(ds) - want_ds) <= TOL * abs(want_ds) + 1e-6
 
 
 CASES = [(1, 64, 14.2857), (2, 8, 5.0), (127, 64, 14.2857), (128, 64, 1.0), (129, 72, 20.0), (300, 512, 14.2857),
@@ -134,12 +140,11 @@ def test_loss_fwd_bwd_vs_oracle_fp16(dev, n, d, s, corr):
     I, T = synth(n, d, 100 * n + d, corr)
     want = OL.global_loss_and_grads(I, T, s, torch.float64)
     loss, acc, dI, dT, ds = run_loss(dev, I, T, s)
-    assert abs(float(loss) - float(want["loss"])) <= TOL * max(abs(float(want["loss"])), 1e-4)
+    assert abs(float(loss) - float(want["loss"])) <= TOL * abs(float(want["loss"])) + 1e-6 * s
     assert abs(float(acc["i2t"]) - float(want["i2t"])) <= 1.5 / n
     assert abs(float(acc["t2i"]) - float(want["t2i"])) <= 1.5 / n
-    fl = grad_floor(n, d, s)
-    assert relerr(dI, want["dI"], fl) < TOL, "dI"
-    assert relerr(dT, want["dT"], fl) < TOL, "dT"
+    assert grad_ok(dI, want["dI"], n, s), f"dI rel {relerr(dI, want['dI']):.3e}"
+    assert grad_ok(dT, want["dT"], n, s), f"dT rel {relerr(dT, want['dT']):.3e}"
     assert abs(float(ds) - float(want["ds"])) <= TOL * abs(float(want["ds"])) + 1e-6
 
 
@@ -199,9 +204,10 @@ def test_rank_strip_kernels_vs_oracle(dev, W, rank, gwg):
         sb += ns
     lse, sc = K.fwd_finalize(n_loc, sb, lo, s_dev, True, ws)
     torch.cuda.synchronize()
-    assert torch.allclose(lse[0].cpu(), glob["lse_img"][lo:hi], rtol=1e-5, atol=1e-4)
-    assert torch.allclose(lse[1].cpu(), glob["lse_txt"][lo:hi], rtol=1e-5, atol=1e-4)
-    lse_all = torch.stack([glob["lse_img"], glob["lse_txt"]]).to(dev)
+    LN2 = math.log(2.0)  # the kernels carry log-sum-exp in base 2
+    assert torch.allclose(lse[0].cpu() * LN2, glob["lse_img"][lo:hi], rtol=1e-5, atol=1e-4)
+    assert torch.allclose(lse[1].cpu() * LN2, glob["lse_txt"][lo:hi], rtol=1e-5, atol=1e-4)
+    lse_all = (torch.stack([glob["lse_img"], glob["lse_txt"]]) / LN2).to(dev)
     dI, dT = K.bwd(I16[lo:hi], T16[lo:hi], T16, I16, label_begin=lo, s_dev=s_dev, lse_all=lse_all,
                    grad_out=torch.ones(1, device=dev), grad_mult=float(W) if gwg else 1.0, row_begin=0,
                    row_count=n_loc, out_dtype=torch.float32)
@@ -286,6 +292,7 @@ def test_full_size_properties(dev):
     lse, sc = K.fwd_finalize(n, slots, 0, s_dev, False, ws)
     rows = torch.arange(0, n, 128, device=dev)  # 256 rows spread over all row blocks
     S = s0 * I[rows] @ T.t()
+    lse = lse * math.log(2.0)  # kernels carry base-2 lse
     assert torch.allclose(lse[0][rows], torch.logsumexp(S, dim=1), rtol=1e-5, atol=2e-4)
     assert torch.allclose(lse[1][rows], torch.logsumexp(s0 * T[rows] @ I.t(), dim=1), rtol=1e-5, atol=2e-4)
     assert abs(float((sc[0] + sc[1]) / (2 * n)) - float(l1)) < 1e-6 * float(l1) + 1e-7
