@@ -1,20 +1,26 @@
 // strip_bwd.cu — kernel (3): fused contrastive backward.
 //
 // Replaces the autograd backward of cn_clip/training/train.py:87-115.  For a block of 128 local
-// rows A (image or text features) and every 64-column tile B_j of the gathered other modality:
-//   MMA1 : S_j = A * B_j^T                      (recomputed logits / s, fp32 in TMEM)
-//   warps: G_j = 2^12 * ( exp(s S - lse_row) + exp(s S - lse_col[j]) - 2 delta_label )  -> fp16,
+// rows A (image or text features) and every 128-column tile B_j of the gathered other modality:
+//   MMA1 : S_j = A * B_j^T                      (recomputed logits / s, fp32 in TMEM; SS, N = 128)
+//   warps: G_j = 2^12 * ( exp(s S - lse_row) + exp(s S - lse_col[j]) - 2 delta_label )  -> 16 bit,
 //          written back into TMEM over S_j (tcgen05.st), never to shared or global memory
-//   MMA2 : dA[:, slice] += G_j * B_j[:, slice]  (A operand from TMEM, B_j re-used from smem as an
-//          MN-major operand: the same swizzled tile that fed MMA1)
+//   MMA2 : dA[:, slice] += G_j * B_j[:, slice]  (A operand from TMEM; B_j streamed a second time
+//          from L2 and read as an MN-major operand: rows of B_j are the K dimension)
 // The fp32 dA accumulator for 128 rows x D does not fit TMEM next to S (D = 512 alone is all 512
 // columns), so a unit (= one CTA) owns a 256-feature slice of the output and the logits are
 // recomputed once per slice ("pass").  unit = (strip, row block, pass, column split).
 //
-// TMEM: [0,256) dA slice | [256,384) S buffers 0/1 | [384,448) G buffers 0/1 (16-bit, 32 columns).
-// SMEM: A block resident (D <= 512) or streamed in 16 KB chunks; B chunks (64 rows x 64 features,
-//       8 KB) go either through a stream ring (features outside the slice: MMA1 only) or into one
-//       of two 32 KB hold buffers (features of the slice: MMA1, then MMA2 one tile later).
+// Shapes follow the measured cost of tcgen05.mma on B200 (tools/mma_bench.cu, M = 128, K = 16):
+//   SS (A from smem): 68.5 clk for N <= 64, 74.8 for N = 128, 138.8 for N = 256 (the A tile is
+//   read from shared memory at 64 B/clk);  TS (A from TMEM): 44.3 / 64.0 / 128.0.
+// so S uses N = 128 tiles and the gradient contraction runs as TS with N = 128.
+//
+// TMEM: [0,256) dA slice | [256,384) S buffer 0 | [384,512) S buffer 1; G_j overwrites columns
+//       [0,64) of its own S buffer (two 16-bit values per column).
+// SMEM: A block resident (D <= 512), a ring of stages each holding a PAIR of 64-feature chunks of
+//       a B tile (2 x 16 KB; + 2 x 16 KB of A when A is streamed).  One mbarrier per stage = 8
+//       MMAs per wait, which keeps the single issuing thread off the critical path.
 //
 // Roofline: tensor cores.  Algorithmic flops = 4 * rows * N * D per strip (S recompute excluded).
 #include <stdlib.h>
@@ -25,49 +31,44 @@ namespace nans {
 namespace {
 
 constexpr int BM = 128;
-constexpr int KT = 64;
+constexpr int KT = 128;
 constexpr int BK = 64;
 constexpr int SLICE = 256;
-constexpr int A_CHUNK = BM * BK * 2;           // 16 KB
-constexpr int B_CHUNK = KT * BK * 2;           // 8 KB
-constexpr int HOLD_CHUNKS = SLICE / BK;        // 4
-constexpr int HOLD_BYTES = HOLD_CHUNKS * B_CHUNK;  // 32 KB
-constexpr int NH = 2;
-constexpr int MAX_NA = 6;
-constexpr int MAX_NS = 12;
+constexpr int A_CHUNK = BM * BK * 2;        // 16 KB
+constexpr int B_CHUNK = KT * BK * 2;        // 16 KB
+constexpr int PAIR = 2;                     // chunks per ring stage
+constexpr int SLICE_PAIRS = SLICE / BK / PAIR;  // 2
+constexpr int MAX_NR = 6;
 constexpr int SM_WARPS = 8;  // softmax-gradient warps: 4 lane groups x 2 column halves
 constexpr int NUM_THREADS = 128 + SM_WARPS * 32;
 constexpr int TMEM_COLS = 512;
-constexpr int TMEM_S = 256;   // two 64-column S buffers
-constexpr int TMEM_G = 384;   // two 32-column G buffers (64 x 16-bit per row)
-constexpr int BAR_BYTES = 512;
+constexpr int TMEM_S = 256;  // two 128-column S buffers; G aliases the first 64 columns of each
+constexpr int BAR_BYTES = 256;
 constexpr size_t SMEM_CAP = 227 * 1024;
 constexpr float kGShiftLog2 = 12.0f;  // G is carried as fp16 scaled by 2^12 (|G| <= 2 -> 8192)
 
 struct BwdPlan {
   bool a_resident;
-  int na, ns;
+  int nr;           // ring stages
   size_t bytes;
 };
 
 BwdPlan plan_bwd(int kchunks) {
   BwdPlan p;
   const size_t cap = SMEM_CAP - 1024 - BAR_BYTES;
-  const size_t hold = static_cast<size_t>(NH) * HOLD_BYTES;
   const size_t a_res = static_cast<size_t>(kchunks) * A_CHUNK;
-  if (a_res + hold + 2 * B_CHUNK <= cap) {
+  const size_t stage_b = static_cast<size_t>(PAIR) * B_CHUNK;
+  const size_t stage_ab = static_cast<size_t>(PAIR) * (A_CHUNK + B_CHUNK);
+  if (a_res + 2 * stage_b <= cap) {
     p.a_resident = true;
-    p.na = 0;
-    p.ns = static_cast<int>((cap - a_res - hold) / B_CHUNK);
-    if (p.ns > MAX_NS) p.ns = MAX_NS;
-    p.bytes = a_res + hold + static_cast<size_t>(p.ns) * B_CHUNK + BAR_BYTES + 1024;
+    p.nr = static_cast<int>((cap - a_res) / stage_b);
+    if (p.nr > MAX_NR) p.nr = MAX_NR;
+    p.bytes = a_res + static_cast<size_t>(p.nr) * stage_b + BAR_BYTES + 1024;
   } else {
     p.a_resident = false;
-    p.na = 4;
-    p.ns = static_cast<int>((cap - hold - static_cast<size_t>(p.na) * A_CHUNK) / B_CHUNK);
-    if (p.ns > MAX_NS) p.ns = MAX_NS;
-    p.bytes = hold + static_cast<size_t>(p.na) * A_CHUNK + static_cast<size_t>(p.ns) * B_CHUNK +
-              BAR_BYTES + 1024;
+    p.nr = static_cast<int>(cap / stage_ab);
+    if (p.nr > MAX_NR) p.nr = MAX_NR;
+    p.bytes = static_cast<size_t>(p.nr) * stage_ab + BAR_BYTES + 1024;
   }
   return p;
 }
@@ -76,38 +77,40 @@ struct BwdParams {
   int row_begin, row_end;  // rows of the local block that receive gradient
   int ncols, D, kchunks;
   int nrb, npass, nsplit, ntiles;
-  int na, ns;
+  int nr;
   uint32_t idesc1_fmt;  // operand format bits (0 = f16, 1 = bf16)
   uint32_t g_fmt;       // format G is written in (0 = f16, 1 = bf16)
   int label_shift;      // label column of local row r = r + label_shift
   const float* s_dev;
   const float* grad_out_dev;
   float coef_host;  // grad_mult / (2 N) / 2^12
-  const float* lse_row[2];  // per strip: lse of the local rows (indexed by local row)
-  const float* lse_col[2];  // per strip: lse of all columns
+  const float* lse_row[2];  // per strip: base-2 lse of the local rows (indexed by local row)
+  const float* lse_col[2];  // per strip: base-2 lse of all columns
   float* out[2];            // per strip: fp32 [row_end-row_begin, D]
-  int accumulate;           // 1: atomicAdd into out (column splits), 0: plain stores
+  int accumulate;           // 1: red.add into out (column splits), 0: plain stores
 };
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
+               : "memory");
+}
 
 template <bool A_RES>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 clip_bwd_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmB0,
                 const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
                 const BwdParams p) {
+  constexpr int STAGE = A_RES ? PAIR * B_CHUNK : PAIR * (A_CHUNK + B_CHUNK);
+  constexpr int STAGE_B_OFF = A_RES ? 0 : PAIR * A_CHUNK;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  uint8_t* smA = smem;  // resident block or ring
-  uint8_t* smH = smA + static_cast<size_t>(A_RES ? p.kchunks : p.na) * A_CHUNK;
-  uint8_t* smS = smH + static_cast<size_t>(NH) * HOLD_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smS + static_cast<size_t>(p.ns) * B_CHUNK);
-  uint64_t* fullA = bars;
-  uint64_t* emptyA = fullA + MAX_NA;
-  uint64_t* fullS = emptyA + MAX_NA;
-  uint64_t* emptyS = fullS + MAX_NS;
-  uint64_t* fullH = emptyS + MAX_NS;  // [NH][HOLD_CHUNKS]
-  uint64_t* emptyH = fullH + NH * HOLD_CHUNKS;
-  uint64_t* a_full = emptyH + NH;
+  uint8_t* smA = smem;  // resident block (A_RES only)
+  uint8_t* smR = smA + (A_RES ? static_cast<size_t>(p.kchunks) * A_CHUNK : 0);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smR + static_cast<size_t>(p.nr) * STAGE);
+  uint64_t* fullR = bars;
+  uint64_t* emptyR = fullR + MAX_NR;
+  uint64_t* a_full = emptyR + MAX_NR;
   uint64_t* s_full = a_full + 1;   // [2]
   uint64_t* g_ready = s_full + 2;  // [2]
   uint64_t* da_full = g_ready + 2;
@@ -131,18 +134,17 @@ clip_bwd_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
   const int tile_begin = static_cast<int>(static_cast<long long>(split) * p.ntiles / p.nsplit);
   const int tile_end = static_cast<int>(static_cast<long long>(split + 1) * p.ntiles / p.nsplit);
   const int ntiles = tile_end - tile_begin;
-  const int slice_c0 = pass * HOLD_CHUNKS;                      // first chunk of the slice
-  const int slice_nc = min(HOLD_CHUNKS, p.kchunks - slice_c0);  // chunks in the slice
-  const int slice_w = slice_nc * BK;                            // MMA2 N
+  const int npairs = (p.kchunks + PAIR - 1) / PAIR;            // ring stages per MMA1 sweep
+  const int slice_c0 = pass * (SLICE / BK);                    // first chunk of the slice
+  const int slice_nc = min(SLICE / BK, p.kchunks - slice_c0);  // chunks in the slice (1..4)
+  const int slice_np = (slice_nc + PAIR - 1) / PAIR;           // ring stages per MMA2 sweep
+  const int slice_w = slice_nc * BK;
 
   if (warp == 0) {
     if (elect_one()) {
       tma_prefetch_desc(tmA);
       tma_prefetch_desc(tmB);
-      for (int i = 0; i < MAX_NA; ++i) { mbar_init(&fullA[i], 1); mbar_init(&emptyA[i], 1); }
-      for (int i = 0; i < MAX_NS; ++i) { mbar_init(&fullS[i], 1); mbar_init(&emptyS[i], 1); }
-      for (int i = 0; i < NH * HOLD_CHUNKS; ++i) mbar_init(&fullH[i], 1);
-      for (int i = 0; i < NH; ++i) mbar_init(&emptyH[i], 1);
+      for (int i = 0; i < MAX_NR; ++i) { mbar_init(&fullR[i], 1); mbar_init(&emptyR[i], 1); }
       mbar_init(a_full, 1);
       for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&g_ready[i], SM_WARPS); }
       mbar_init(da_full, 1);
@@ -157,6 +159,8 @@ clip_bwd_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
+  // Both the producer and the MMA issuer walk the same schedule:
+  //   step tau = 0 .. ntiles :  [tau < ntiles] MMA1 stages of tile tau ; [tau >= 1] MMA2 stages of tile tau-1
   if (warp == 0) {
     // ---------------- TMA producer (warp-uniform loop, one elected lane issues) ----------------
     if (A_RES) {
@@ -167,123 +171,108 @@ clip_bwd_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
       }
       __syncwarp();
     }
-    int sa = 0, ss = 0;
-    uint32_t pa = 0, ps = 0;
-    for (int t = 0; t < ntiles; ++t) {
-      const int col0 = (tile_begin + t) * KT;
-      const int h = t % NH;
-      const uint32_t ph = static_cast<uint32_t>(t / NH) & 1u;
-      for (int c = 0; c < p.kchunks; ++c) {
-        if (c >= slice_c0 && c < slice_c0 + slice_nc) continue;
-        if (!A_RES) mbar_wait(&emptyA[sa], pa ^ 1u);
-        mbar_wait(&emptyS[ss], ps ^ 1u);
-        if (elect_one()) {
-          if (!A_RES) {
-            mbar_arrive_expect_tx(&fullA[sa], A_CHUNK);
-            tma_load_2d(smA + static_cast<size_t>(sa) * A_CHUNK, tmA, &fullA[sa], c * BK, row0);
+    int sr = 0;
+    uint32_t pr = 0;
+    for (int tau = 0; tau <= ntiles; ++tau) {
+      if (tau < ntiles) {
+        const int col0 = (tile_begin + tau) * KT;
+        for (int j = 0; j < npairs; ++j) {
+          const int nck = min(PAIR, p.kchunks - j * PAIR);
+          mbar_wait(&emptyR[sr], pr ^ 1u);
+          if (elect_one()) {
+            uint8_t* st = smR + static_cast<size_t>(sr) * STAGE;
+            mbar_arrive_expect_tx(&fullR[sr], static_cast<uint32_t>(nck) * (B_CHUNK + (A_RES ? 0 : A_CHUNK)));
+            for (int ci = 0; ci < nck; ++ci) {
+              const int f = (j * PAIR + ci) * BK;
+              if (!A_RES) tma_load_2d(st + ci * A_CHUNK, tmA, &fullR[sr], f, row0);
+              tma_load_2d(st + STAGE_B_OFF + ci * B_CHUNK, tmB, &fullR[sr], f, col0);
+            }
           }
-          mbar_arrive_expect_tx(&fullS[ss], B_CHUNK);
-          tma_load_2d(smS + static_cast<size_t>(ss) * B_CHUNK, tmB, &fullS[ss], c * BK, col0);
+          __syncwarp();
+          if (++sr == p.nr) { sr = 0; pr ^= 1u; }
         }
-        __syncwarp();
-        if (!A_RES) { if (++sa == p.na) { sa = 0; pa ^= 1u; } }
-        if (++ss == p.ns) { ss = 0; ps ^= 1u; }
       }
-      mbar_wait(&emptyH[h], ph ^ 1u);
-      for (int ci = 0; ci < slice_nc; ++ci) {
-        const int c = slice_c0 + ci;
-        if (!A_RES) mbar_wait(&emptyA[sa], pa ^ 1u);
-        if (elect_one()) {
-          if (!A_RES) {
-            mbar_arrive_expect_tx(&fullA[sa], A_CHUNK);
-            tma_load_2d(smA + static_cast<size_t>(sa) * A_CHUNK, tmA, &fullA[sa], c * BK, row0);
+      if (tau >= 1) {
+        const int col0 = (tile_begin + tau - 1) * KT;
+        for (int j = 0; j < slice_np; ++j) {
+          const int nck = min(PAIR, slice_nc - j * PAIR);
+          mbar_wait(&emptyR[sr], pr ^ 1u);
+          if (elect_one()) {
+            uint8_t* st = smR + static_cast<size_t>(sr) * STAGE;
+            mbar_arrive_expect_tx(&fullR[sr], static_cast<uint32_t>(nck) * B_CHUNK);
+            for (int ci = 0; ci < nck; ++ci)
+              tma_load_2d(st + STAGE_B_OFF + ci * B_CHUNK, tmB, &fullR[sr], (slice_c0 + j * PAIR + ci) * BK, col0);
           }
-          uint64_t* fb = &fullH[h * HOLD_CHUNKS + ci];
-          mbar_arrive_expect_tx(fb, B_CHUNK);
-          tma_load_2d(smH + static_cast<size_t>(h) * HOLD_BYTES + static_cast<size_t>(ci) * B_CHUNK,
-                      tmB, fb, c * BK, col0);
+          __syncwarp();
+          if (++sr == p.nr) { sr = 0; pr ^= 1u; }
         }
-        __syncwarp();
-        if (!A_RES) { if (++sa == p.na) { sa = 0; pa ^= 1u; } }
       }
     }
   } else if (warp == 1) {
     // ---------------- MMA issuer (warp-uniform loop, one elected lane issues) ----------------
     const uint32_t fmt = p.idesc1_fmt;
     const uint32_t idesc1 = make_idesc(fmt, fmt, 0, 0, BM, KT);
-    const uint32_t idesc2 = make_idesc(p.g_fmt, fmt, 0, /*B MN-major*/ 1, BM, slice_w);
-    const uint32_t smA_addr = smem_u32(smA), smH_addr = smem_u32(smH), smS_addr = smem_u32(smS);
+    const uint32_t smA_addr = smem_u32(smA), smR_addr = smem_u32(smR);
     if (A_RES) {
       mbar_wait(a_full, 0);
       tc_fence_after();
     }
-    int sa = 0, ss = 0;
-    uint32_t pa = 0, ps = 0;
-
-    auto issue_mma2 = [&](int u) {
-      const int gb = u & 1;
-      mbar_wait(&g_ready[gb], static_cast<uint32_t>(u >> 1) & 1u);
-      tc_fence_after();
-      const int h = u % NH;
-      if (elect_one()) {
-        const uint64_t bd = make_smem_desc(smH_addr + static_cast<uint32_t>(h) * HOLD_BYTES, B_CHUNK, 1024);
+    int sr = 0;
+    uint32_t pr = 0;
+    for (int tau = 0; tau <= ntiles; ++tau) {
+      if (tau < ntiles) {
+        const uint32_t d_S = tmem_base + TMEM_S + (tau & 1) * KT;
+        for (int j = 0; j < npairs; ++j) {
+          const int nck = min(PAIR, p.kchunks - j * PAIR);
+          mbar_wait(&fullR[sr], pr);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t st = smR_addr + static_cast<uint32_t>(sr) * STAGE;
+            const uint64_t ad0 = make_smem_desc(A_RES ? smA_addr + static_cast<uint32_t>(j * PAIR) * A_CHUNK : st, 16, 1024);
+            const uint64_t bd0 = make_smem_desc(st + STAGE_B_OFF, 16, 1024);
+            for (int ci = 0; ci < nck; ++ci) {
+              const uint64_t ad = ad0 + static_cast<uint64_t>(ci * (A_CHUNK >> 4));
+              const uint64_t bd = bd0 + static_cast<uint64_t>(ci * (B_CHUNK >> 4));
 #pragma unroll
-        for (int kk = 0; kk < KT / 16; ++kk)  // 16 K-rows = 16 x 128 B = 2048 B (>> 4 = 128) per step
-          mma_ts(tmem_base, tmem_base + TMEM_G + gb * (KT / 2) + kk * 8, bd + 128 * kk, idesc2,
-                 (u > 0 || kk > 0) ? 1u : 0u);
-        tc_commit(&emptyH[h]);
-      }
-      __syncwarp();
-    };
-
-    for (int t = 0; t < ntiles; ++t) {
-      const uint32_t d_S = tmem_base + TMEM_S + (t & 1) * KT;
-      const int h = t % NH;
-      const uint32_t ph = static_cast<uint32_t>(t / NH) & 1u;
-      uint32_t acc = 0;
-      for (int c = 0; c < p.kchunks; ++c) {
-        if (c >= slice_c0 && c < slice_c0 + slice_nc) continue;
-        if (!A_RES) mbar_wait(&fullA[sa], pa);
-        mbar_wait(&fullS[ss], ps);
-        tc_fence_after();
-        if (elect_one()) {
-          const uint64_t ad = make_smem_desc(smA_addr + static_cast<uint32_t>(A_RES ? c : sa) * A_CHUNK, 16, 1024);
-          const uint64_t bd = make_smem_desc(smS_addr + static_cast<uint32_t>(ss) * B_CHUNK, 16, 1024);
-#pragma unroll
-          for (int k = 0; k < BK / 16; ++k) mma_ss(d_S, ad + 2 * k, bd + 2 * k, idesc1, (acc | k) != 0 ? 1u : 0u);
-          tc_commit(&emptyS[ss]);
-          if (!A_RES) tc_commit(&emptyA[sa]);
+              for (int k = 0; k < BK / 16; ++k)
+                mma_ss(d_S, ad + 2 * k, bd + 2 * k, idesc1, (j | ci | k) != 0 ? 1u : 0u);
+            }
+            tc_commit(&emptyR[sr]);
+            if (j == npairs - 1) tc_commit(&s_full[tau & 1]);
+          }
+          __syncwarp();
+          if (++sr == p.nr) { sr = 0; pr ^= 1u; }
         }
-        __syncwarp();
-        acc = 1;
-        if (++ss == p.ns) { ss = 0; ps ^= 1u; }
-        if (!A_RES) { if (++sa == p.na) { sa = 0; pa ^= 1u; } }
       }
-      for (int ci = 0; ci < slice_nc; ++ci) {
-        const int c = slice_c0 + ci;
-        if (!A_RES) mbar_wait(&fullA[sa], pa);
-        mbar_wait(&fullH[h * HOLD_CHUNKS + ci], ph);
+      if (tau >= 1) {
+        const int u = tau - 1;
+        const int gb = u & 1;
+        mbar_wait(&g_ready[gb], static_cast<uint32_t>(u >> 1) & 1u);
         tc_fence_after();
-        if (elect_one()) {
-          const uint64_t ad = make_smem_desc(smA_addr + static_cast<uint32_t>(A_RES ? c : sa) * A_CHUNK, 16, 1024);
-          const uint64_t bd = make_smem_desc(
-              smH_addr + static_cast<uint32_t>(h) * HOLD_BYTES + static_cast<uint32_t>(ci) * B_CHUNK, 16, 1024);
+        const uint32_t g_tmem = tmem_base + TMEM_S + gb * KT;
+        for (int j = 0; j < slice_np; ++j) {
+          const int nck = min(PAIR, slice_nc - j * PAIR);
+          mbar_wait(&fullR[sr], pr);
+          tc_fence_after();
+          if (elect_one()) {
+            // B_j[:, 64-feature blocks] as an MN-major operand: 128-byte lines = 64 features of one
+            // row, lines step K (rows), 8-row groups 1024 B apart, feature blocks one chunk apart
+            const uint32_t idesc2 = make_idesc(p.g_fmt, fmt, 0, 1, BM, nck * BK);
+            const uint64_t bd = make_smem_desc(smR_addr + static_cast<uint32_t>(sr) * STAGE + STAGE_B_OFF, B_CHUNK, 1024);
+            const uint32_t d_dA = tmem_base + static_cast<uint32_t>(j * PAIR * BK);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) mma_ss(d_S, ad + 2 * k, bd + 2 * k, idesc1, (acc | k) != 0 ? 1u : 0u);
-          if (!A_RES) tc_commit(&emptyA[sa]);
-          if (ci == slice_nc - 1) tc_commit(&s_full[t & 1]);
+            for (int kk = 0; kk < KT / 16; ++kk)  // 16 rows x 128 B = 2048 B (>> 4 = 128) per K step
+              mma_ts(d_dA, g_tmem + kk * 8, bd + 128 * kk, idesc2, (u > 0 || kk > 0) ? 1u : 0u);
+            tc_commit(&emptyR[sr]);
+            if (tau == ntiles && j == slice_np - 1) tc_commit(da_full);
+          }
+          __syncwarp();
+          if (++sr == p.nr) { sr = 0; pr ^= 1u; }
         }
-        __syncwarp();
-        acc = 1;
-        if (!A_RES) { if (++sa == p.na) { sa = 0; pa ^= 1u; } }
       }
-      if (t > 0) issue_mma2(t - 1);
     }
-    issue_mma2(ntiles - 1);
-    if (elect_one()) tc_commit(da_full);
-    __syncwarp();
   } else if (warp >= 4) {
-    // ---------------- softmax-gradient warps: thread = (row, 32-column half) ----------------
+    // ---------------- softmax-gradient warps: thread = (row, 64-column half of the tile) ---------
     const int wq = warp & 3;
     const int half = (warp - 4) >> 2;
     const uint32_t lane_base = static_cast<uint32_t>(wq * 32) << 16;
@@ -300,44 +289,62 @@ clip_bwd_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
 
     for (int t = 0; t < ntiles; ++t) {
       const int sb = t & 1;
-      mbar_wait(&s_full[sb], static_cast<uint32_t>(t >> 1) & 1u);
-      tc_fence_after();
-      const int cb = (tile_begin + t) * KT + half * 32;
-      const bool has_label = (warp_label_lo < cb + 32) && (warp_label_lo + 31 >= cb);
-      uint32_t r[32];
-      tmem_ld32(tmem_base + lane_base + TMEM_S + sb * KT + half * 32, r);
+      const int cb0 = (tile_begin + t) * KT + half * 64;
+      uint32_t g16[32];
+      // the column log-sum-exps do not depend on S: the first batch is fetched before the wait
       float lc2[32];
-      if (cb + 32 <= p.ncols) {
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float4 f = __ldg(reinterpret_cast<const float4*>(lse_col + cb) + q);
-          lc2[4 * q + 0] = f.x; lc2[4 * q + 1] = f.y; lc2[4 * q + 2] = f.z; lc2[4 * q + 3] = f.w;
-        }
-      } else {
+      for (int sub = 0; sub < 2; ++sub) {
+        const int cb = cb0 + sub * 32;
+        if (cb + 32 <= p.ncols) {
 #pragma unroll
-        for (int k = 0; k < 32; ++k) lc2[k] = __ldg(lse_col + min(cb + k, p.ncols - 1));
-      }
-      tmem_wait_ld();
-      uint32_t g16[16];
-#pragma unroll
-      for (int k = 0; k < 32; k += 2) {
-        float g[2];
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const float cosv = __uint_as_float(r[k + e]);
-          const float lcv = lc2[k + e] - kGShiftLog2;
-          g[e] = fast_exp2(fmaf(cosv, c, -lr2)) + fast_exp2(fmaf(cosv, c, -lcv));
-          if (has_label && cb + k + e == label) g[e] -= 8192.0f;  // 2 * 2^12
-        }
-        if (g_bf16) {
-          const __nv_bfloat162 hh = __floats2bfloat162_rn(g[0], g[1]);
-          g16[k >> 1] = *reinterpret_cast<const uint32_t*>(&hh);
+          for (int q = 0; q < 8; ++q) {
+            const float4 f = __ldg(reinterpret_cast<const float4*>(lse_col + cb) + q);
+            lc2[4 * q + 0] = f.x; lc2[4 * q + 1] = f.y; lc2[4 * q + 2] = f.z; lc2[4 * q + 3] = f.w;
+          }
         } else {
-          const __half2 hh = __floats2half2_rn(g[0], g[1]);
-          g16[k >> 1] = *reinterpret_cast<const uint32_t*>(&hh);
+#pragma unroll
+          for (int k = 0; k < 32; ++k) lc2[k] = __ldg(lse_col + max(min(cb + k, p.ncols - 1), 0));
+        }
+        if (sub == 0) {
+          mbar_wait(&s_full[sb], static_cast<uint32_t>(t >> 1) & 1u);
+          tc_fence_after();
+        }
+        const bool has_label = (warp_label_lo < cb + 32) && (warp_label_lo + 31 >= cb);
+        uint32_t r[32];
+        tmem_ld32(tmem_base + lane_base + TMEM_S + sb * KT + half * 64 + sub * 32, r);
+        tmem_wait_ld();
+#pragma unroll
+        for (int k = 0; k < 32; k += 2) {
+          float g[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const float cosv = __uint_as_float(r[k + e]);
+            const float lcv = lc2[k + e] - kGShiftLog2;
+            g[e] = fast_exp2(fmaf(cosv, c, -lr2)) + fast_exp2(fmaf(cosv, c, -lcv));
+            if (has_label && cb + k + e == label) g[e] -= 8192.0f;  // 2 * 2^12
+          }
+          if (g_bf16) {
+            const __nv_bfloat162 hh = __floats2bfloat162_rn(g[0], g[1]);
+            g16[sub * 16 + (k >> 1)] = *reinterpret_cast<const uint32_t*>(&hh);
+          } else {
+            const __half2 hh = __floats2half2_rn(g[0], g[1]);
+            g16[sub * 16 + (k >> 1)] = *reinterpret_cast<const uint32_t*>(&hh);
+          }
         }
       }
-      tmem_st16(tmem_base + lane_base + TMEM_G + sb * (KT / 2) + half * 16, g16);
+      // G (32 columns per half) overwrites S columns [0,64) of this buffer; the half-1 thread of a
+      // row writes columns [32,64), which the half-0 thread of the same row has just read as S:
+      // the two warps of a lane group meet before any of them stores.
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + wq) : "memory");
+      {
+        uint32_t lo[16], hi[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { lo[i] = g16[i]; hi[i] = g16[16 + i]; }
+        const uint32_t g_addr = tmem_base + lane_base + TMEM_S + sb * KT + half * 32;
+        tmem_st16(g_addr, lo);
+        tmem_st16(g_addr + 16, hi);
+      }
       tmem_wait_st();
       tc_fence_before();
       __syncwarp();
@@ -355,20 +362,21 @@ clip_bwd_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
       tmem_wait_ld();
       if (valid) {
         const int f0 = pass * SLICE + ch * 32;
-        if (p.accumulate) {
+        if (f0 + 32 <= p.D) {
 #pragma unroll
-          for (int k = 0; k < 32; ++k)
-            if (f0 + k < p.D) atomicAdd(out + ch * 32 + k, __uint_as_float(r[k]) * coef);
-        } else if (f0 + 32 <= p.D) {
-#pragma unroll
-          for (int k = 0; k < 32; k += 4)
-            *reinterpret_cast<float4*>(out + ch * 32 + k) =
-                make_float4(__uint_as_float(r[k]) * coef, __uint_as_float(r[k + 1]) * coef,
-                            __uint_as_float(r[k + 2]) * coef, __uint_as_float(r[k + 3]) * coef);
+          for (int k = 0; k < 32; k += 4) {
+            const float a0 = __uint_as_float(r[k]) * coef, a1 = __uint_as_float(r[k + 1]) * coef;
+            const float a2 = __uint_as_float(r[k + 2]) * coef, a3 = __uint_as_float(r[k + 3]) * coef;
+            if (p.accumulate) red_add_v4(out + ch * 32 + k, a0, a1, a2, a3);
+            else *reinterpret_cast<float4*>(out + ch * 32 + k) = make_float4(a0, a1, a2, a3);
+          }
         } else {
 #pragma unroll
           for (int k = 0; k < 32; ++k)
-            if (f0 + k < p.D) out[ch * 32 + k] = __uint_as_float(r[k]) * coef;
+            if (f0 + k < p.D) {
+              if (p.accumulate) atomicAdd(out + ch * 32 + k, __uint_as_float(r[k]) * coef);
+              else out[ch * 32 + k] = __uint_as_float(r[k]) * coef;
+            }
         }
       }
     }
@@ -459,7 +467,7 @@ extern "C" int nans_clip_loss_bwd(const void* I_loc, const void* T_loc, int64_t 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
 
   const int kchunks = static_cast<int>(ceil_div(D, BK));
-  const int npass = static_cast<int>(ceil_div(kchunks, HOLD_CHUNKS));
+  const int npass = static_cast<int>(ceil_div(kchunks, SLICE / BK));
   const BwdPlan plan = plan_bwd(kchunks);
   const int nsplit = choose_bwd_nsplit(grad_row_count, N, npass);
 
@@ -501,8 +509,7 @@ extern "C" int nans_clip_loss_bwd(const void* I_loc, const void* T_loc, int64_t 
   p.npass = npass;
   p.nsplit = nsplit;
   p.ntiles = static_cast<int>(ceil_div(N, KT));
-  p.na = plan.na;
-  p.ns = plan.ns;
+  p.nr = plan.nr;
   p.idesc1_fmt = static_cast<uint32_t>(idesc_fmt(feat_dtype));
   // tcgen05.mma kind::f16 wants A and B in the same 16-bit format (a mixed f16 x bf16 descriptor
   // faults as an illegal instruction on sm_100a), so G is written in the features' format.
