@@ -4,7 +4,10 @@
 // rows A (image or text features) and every 128-column tile B_j of the gathered other modality:
 //   MMA1 : S_j = A * B_j^T                      (recomputed logits / s, fp32 in TMEM; SS, N = 128)
 //   warps: G_j = 2^12 * ( exp(s S - lse_row) + exp(s S - lse_col[j]) - 2 delta_label )  -> 16 bit,
-//          written back into TMEM over S_j (tcgen05.st), never to shared or global memory
+//          written back into TMEM over S_j (tcgen05.st), never to shared or global memory.
+//          One MUFU per element instead of two: exp(sS-lr) + exp(sS-lc) = exp(sS-lr) * (1 + a_i b_j),
+//          a_i = 2^(lr_i - mu), b_j = 2^(mu - lc_j); b_j is produced once per tile by warp 3.
+//          (Used when all lse lie within 2^+-50 of mu; otherwise the two-exp form runs.)
 //   MMA2 : dA[:, slice] += G_j * B_j[:, slice]  (A operand from TMEM; B_j streamed a second time
 //          from L2 and read as an MN-major operand: rows of B_j are the K dimension)
 // The fp32 dA accumulator for 128 rows x D does not fit TMEM next to S (D = 512 alone is all 512
@@ -37,14 +40,15 @@ constexpr int SLICE = 256;
 constexpr int A_CHUNK = BM * BK * 2;        // 16 KB
 constexpr int B_CHUNK = KT * BK * 2;        // 16 KB
 constexpr int PAIR = 2;                     // chunks per ring stage
-constexpr int SLICE_PAIRS = SLICE / BK / PAIR;  // 2
 constexpr int MAX_NR = 6;
 constexpr int SM_WARPS = 8;  // softmax-gradient warps: 4 lane groups x 2 column halves
 constexpr int NUM_THREADS = 128 + SM_WARPS * 32;
 constexpr int TMEM_COLS = 512;
 constexpr int TMEM_S = 256;  // two 128-column S buffers; G aliases the first 64 columns of each
-constexpr int BAR_BYTES = 256;
+constexpr int BAR_BYTES = 1536;  // mbarriers + TMEM pointer (256 B) + two 128-float column-factor buffers
+constexpr int CF_OFF = 256;
 constexpr size_t SMEM_CAP = 227 * 1024;
+constexpr float kFactorRange = 100.0f;  // max spread of base-2 lse for the one-exp formulation
 constexpr float kGShiftLog2 = 12.0f;  // G is carried as fp16 scaled by 2^12 (|G| <= 2 -> 8192)
 
 struct BwdPlan {
@@ -88,6 +92,7 @@ struct BwdParams {
   const float* lse_col[2];  // per strip: base-2 lse of all columns
   float* out[2];            // per strip: fp32 [row_end-row_begin, D]
   int accumulate;           // 1: red.add into out (column splits), 0: plain stores
+  const int* lse_minmax;    // [2] order-preserving int encodings of min / max of all lse values
 };
 
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
@@ -114,7 +119,10 @@ clip_bwd_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
   uint64_t* s_full = a_full + 1;   // [2]
   uint64_t* g_ready = s_full + 2;  // [2]
   uint64_t* da_full = g_ready + 2;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(da_full + 1);
+  uint64_t* b_full = da_full + 1;   // [2] column factors of a tile are in shared memory
+  uint64_t* b_empty = b_full + 2;   // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(b_empty + 2);
+  float* cfbuf = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + CF_OFF);  // [2][128]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -148,6 +156,7 @@ clip_bwd_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
       mbar_init(a_full, 1);
       for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&g_ready[i], SM_WARPS); }
       mbar_init(da_full, 1);
+      for (int i = 0; i < 2; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], SM_WARPS); }
       fence_barrier_init();
     }
   } else if (warp == 2) {
@@ -158,6 +167,18 @@ clip_bwd_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+
+  // one-exp formulation if every lse lies within +-kFactorRange/2 of mu (uniform over the grid)
+  float lse_mu;
+  bool factored;
+  {
+    int lo = __ldg(p.lse_minmax), hi = __ldg(p.lse_minmax + 1);
+    lo = lo >= 0 ? lo : lo ^ 0x7fffffff;
+    hi = hi >= 0 ? hi : hi ^ 0x7fffffff;
+    const float fmin = __int_as_float(lo), fmax = __int_as_float(hi);
+    factored = (fmax - fmin) < kFactorRange;
+    lse_mu = 0.5f * (fmax + fmin);
+  }
 
   // Both the producer and the MMA issuer walk the same schedule:
   //   step tau = 0 .. ntiles :  [tau < ntiles] MMA1 stages of tile tau ; [tau >= 1] MMA2 stages of tile tau-1
@@ -271,6 +292,27 @@ clip_bwd_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         }
       }
     }
+  } else if (warp == 3) {
+    // ---------------- column-factor warp: per tile, b_j = 2^(mu - lc_j) (or lc_j - 12) -> smem ----
+    const float* lse_col = p.lse_col[strip];
+    for (int t = 0; t < ntiles; ++t) {
+      const int bb = t & 1;
+      mbar_wait(&b_empty[bb], (static_cast<uint32_t>(t >> 1) & 1u) ^ 1u);
+      const int cb = (tile_begin + t) * KT + lane * 4;
+      float v[4];
+      if (cb + 4 <= p.ncols) {
+        const float4 f = __ldg(reinterpret_cast<const float4*>(lse_col + cb));
+        v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = __ldg(lse_col + max(min(cb + k, p.ncols - 1), 0));
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) v[k] = factored ? fast_exp2(lse_mu - v[k]) : v[k] - kGShiftLog2;
+      *reinterpret_cast<float4*>(cfbuf + bb * KT + lane * 4) = make_float4(v[0], v[1], v[2], v[3]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&b_full[bb]);  // mbarrier arrive has release semantics (cta scope)
+    }
   } else if (warp >= 4) {
     // ---------------- softmax-gradient warps: thread = (row, 64-column half of the tile) ---------
     const int wq = warp & 3;
@@ -282,7 +324,8 @@ clip_bwd_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
     const float c = s * kLog2e;
     // 2^12 * exp(s cos - lse) = 2^(cos * c - (lse2 - 12)), lse2 = base-2 lse from the forward
     const float lr2 = valid ? __ldg(p.lse_row[strip] + row) - kGShiftLog2 : INFINITY;
-    const float* lse_col = p.lse_col[strip];
+    // a_i = 2^(lr_i - mu); rows past the end get 0 (their e1 is 0 as well)
+    const float a_i = valid ? fast_exp2(__ldg(p.lse_row[strip] + row) - lse_mu) : 0.f;
     const int label = row + p.label_shift;
     const int warp_label_lo = label - lane;
     const bool g_bf16 = p.g_fmt != 0;
@@ -291,28 +334,22 @@ clip_bwd_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
       const int sb = t & 1;
       const int cb0 = (tile_begin + t) * KT + half * 64;
       uint32_t g16[32];
-      // the column log-sum-exps do not depend on S: the first batch is fetched before the wait
-      float lc2[32];
+      mbar_wait(&b_full[sb], static_cast<uint32_t>(t >> 1) & 1u);
+      mbar_wait(&s_full[sb], static_cast<uint32_t>(t >> 1) & 1u);
+      tc_fence_after();
+      const float* cf = cfbuf + sb * KT + half * 64;
 #pragma unroll
       for (int sub = 0; sub < 2; ++sub) {
         const int cb = cb0 + sub * 32;
-        if (cb + 32 <= p.ncols) {
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const float4 f = __ldg(reinterpret_cast<const float4*>(lse_col + cb) + q);
-            lc2[4 * q + 0] = f.x; lc2[4 * q + 1] = f.y; lc2[4 * q + 2] = f.z; lc2[4 * q + 3] = f.w;
-          }
-        } else {
-#pragma unroll
-          for (int k = 0; k < 32; ++k) lc2[k] = __ldg(lse_col + max(min(cb + k, p.ncols - 1), 0));
-        }
-        if (sub == 0) {
-          mbar_wait(&s_full[sb], static_cast<uint32_t>(t >> 1) & 1u);
-          tc_fence_after();
-        }
         const bool has_label = (warp_label_lo < cb + 32) && (warp_label_lo + 31 >= cb);
         uint32_t r[32];
         tmem_ld32(tmem_base + lane_base + TMEM_S + sb * KT + half * 64 + sub * 32, r);
+        float lc2[32];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 f = *reinterpret_cast<const float4*>(cf + sub * 32 + 4 * q);  // broadcast
+          lc2[4 * q + 0] = f.x; lc2[4 * q + 1] = f.y; lc2[4 * q + 2] = f.z; lc2[4 * q + 3] = f.w;
+        }
         tmem_wait_ld();
 #pragma unroll
         for (int k = 0; k < 32; k += 2) {
@@ -320,8 +357,9 @@ clip_bwd_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
             const float cosv = __uint_as_float(r[k + e]);
-            const float lcv = lc2[k + e] - kGShiftLog2;
-            g[e] = fast_exp2(fmaf(cosv, c, -lr2)) + fast_exp2(fmaf(cosv, c, -lcv));
+            const float e1 = fast_exp2(fmaf(cosv, c, -lr2));
+            if (factored) g[e] = e1 * fmaf(a_i, lc2[k + e], 1.0f);
+            else g[e] = e1 + fast_exp2(fmaf(cosv, c, -lc2[k + e]));
             if (has_label && cb + k + e == label) g[e] -= 8192.0f;  // 2 * 2^12
           }
           if (g_bf16) {
@@ -333,6 +371,8 @@ clip_bwd_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
           }
         }
       }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&b_empty[sb]);
       // G (32 columns per half) overwrites S columns [0,64) of this buffer; the half-1 thread of a
       // row writes columns [32,64), which the half-0 thread of the same row has just read as S:
       // the two warps of a lane group meet before any of them stores.
@@ -390,6 +430,30 @@ clip_bwd_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
   }
 }
 
+// min / max over both lse arrays, as order-preserving ints (slots pre-set by a memset)
+__global__ void __launch_bounds__(256) lse_minmax_kernel(const float* __restrict__ a,
+                                                         const float* __restrict__ b, int n,
+                                                         int* __restrict__ out) {
+  float lo = INFINITY, hi = -INFINITY;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 2 * n; i += gridDim.x * blockDim.x) {
+    const float v = i < n ? a[i] : b[i - n];
+    lo = fminf(lo, v);
+    hi = fmaxf(hi, v);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    int il = __float_as_int(lo), ih = __float_as_int(hi);
+    il = il >= 0 ? il : il ^ 0x7fffffff;
+    ih = ih >= 0 ? ih : ih ^ 0x7fffffff;
+    atomicMin(out, il);
+    atomicMax(out + 1, ih);
+  }
+}
+
 // fp32 -> 16-bit cast of the gradient when the caller wants fp16 / bf16 outputs
 __global__ void cast_out_kernel(const float* __restrict__ in, void* __restrict__ out, int out_dtype,
                                 long long n) {
@@ -432,8 +496,8 @@ using namespace nans;
 
 extern "C" size_t nans_clip_loss_bwd_workspace_bytes(int64_t grad_row_count, int64_t N, int64_t D) {
   (void)N;
-  if (grad_row_count <= 0 || D <= 0) return 256;
-  return 2 * align_up(static_cast<size_t>(grad_row_count) * D * 4, 256) + 256;
+  if (grad_row_count <= 0 || D <= 0) return 512;
+  return 2 * align_up(static_cast<size_t>(grad_row_count) * D * 4, 256) + 512;
 }
 
 extern "C" int nans_clip_loss_bwd(const void* I_loc, const void* T_loc, int64_t ld_loc,
@@ -472,6 +536,20 @@ extern "C" int nans_clip_loss_bwd(const void* I_loc, const void* T_loc, int64_t 
   const int nsplit = choose_bwd_nsplit(grad_row_count, N, npass);
 
   const size_t out_bytes = static_cast<size_t>(grad_row_count) * D * 4;
+  // workspace: [0,256) lse min/max slots, then (16-bit outputs only) the two fp32 gradient buffers
+  if (ws == nullptr || ws_bytes < 512) {
+    set_error("loss_bwd: workspace %zu < 512 bytes", ws_bytes);
+    return NANS_ERR_WORKSPACE;
+  }
+  NANS_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 15) == 0, "loss_bwd: workspace must be 16-byte aligned");
+  int* minmax = static_cast<int*>(ws);
+  NANS_CUDA_OK(cudaMemsetAsync(minmax, 0x7f, 4, st));      // +3.39e38 as an ordered int
+  NANS_CUDA_OK(cudaMemsetAsync(minmax + 1, 0x80, 4, st));  // a very negative ordered int
+  {
+    const int blocks = static_cast<int>(ceil_div(2 * N, 256 * 8) < 1 ? 1 : (ceil_div(2 * N, 256 * 8) > 256 ? 256 : ceil_div(2 * N, 256 * 8)));
+    lse_minmax_kernel<<<blocks, 256, 0, st>>>(lse_img_all, lse_txt_all, static_cast<int>(N), minmax);
+    NANS_CUDA_OK(cudaGetLastError());
+  }
   float* out32[2];
   if (out_dtype == NANS_F32) {
     NANS_REQUIRE((reinterpret_cast<uintptr_t>(dI_loc) & 15) == 0 && (reinterpret_cast<uintptr_t>(dT_loc) & 15) == 0,
@@ -480,13 +558,12 @@ extern "C" int nans_clip_loss_bwd(const void* I_loc, const void* T_loc, int64_t 
     out32[1] = static_cast<float*>(dT_loc);
   } else {
     const size_t need = nans_clip_loss_bwd_workspace_bytes(grad_row_count, N, D);
-    if (ws == nullptr || ws_bytes < need) {
+    if (ws_bytes < need) {
       set_error("loss_bwd: workspace %zu < %zu bytes", ws_bytes, need);
       return NANS_ERR_WORKSPACE;
     }
-    NANS_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 15) == 0, "loss_bwd: workspace must be 16-byte aligned");
-    out32[0] = static_cast<float*>(ws);
-    out32[1] = reinterpret_cast<float*>(static_cast<uint8_t*>(ws) + align_up(out_bytes, 256));
+    out32[0] = reinterpret_cast<float*>(static_cast<uint8_t*>(ws) + 256);
+    out32[1] = reinterpret_cast<float*>(static_cast<uint8_t*>(ws) + 256 + align_up(out_bytes, 256));
   }
   if (nsplit > 1) {
     NANS_CUDA_OK(cudaMemsetAsync(out32[0], 0, out_bytes, st));
@@ -529,6 +606,7 @@ extern "C" int nans_clip_loss_bwd(const void* I_loc, const void* T_loc, int64_t 
   p.out[0] = out32[0];
   p.out[1] = out32[1];
   p.accumulate = nsplit > 1 ? 1 : 0;
+  p.lse_minmax = minmax;
 
   auto kern = plan.a_resident ? clip_bwd_kernel<true> : clip_bwd_kernel<false>;
   NANS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,

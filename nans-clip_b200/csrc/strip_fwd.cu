@@ -60,12 +60,12 @@ struct LseEpi {
     bi = -1;
   }
 
-  __device__ __forceinline__ void tile(uint32_t taddr, int tile_idx, int ch_begin, int ch_end) {
+  __device__ __forceinline__ void tile(uint32_t taddr, int tile_idx) {
     const int col0 = tile_idx * BN;
     const bool tail = col0 + BN > ncols;
     const bool has_label = (warp_label_lo < col0 + BN) && (warp_label_lo + 31 >= col0);
 #pragma unroll 1
-    for (int ch = ch_begin; ch < ch_end; ++ch) {
+    for (int ch = 0; ch < BN / 32; ++ch) {
       const int cb = col0 + ch * 32;
       if (cb >= ncols) break;  // whole chunk past the last column: the running max must only
                                // ever come from real columns (an all-masked max would make
@@ -147,8 +147,8 @@ clip_fwd_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
 
   uint8_t* scratch = run<A_RES>(a, epi);
 
-  // The two column halves of a row live in two threads (warps 4-7 and 8-11): merge through
-  // shared memory (the pipeline buffers are dead after run()).
+  // The even and odd tiles of a row were drained by two threads (warps 4-7 and 8-11): merge
+  // through shared memory (the pipeline buffers are dead after run()).
   float* xm = reinterpret_cast<float*>(scratch);  // [6][128]
   const int r = (warp & 3) * 32 + lane;
   float L = (epi.l[0] + epi.l[1]) + (epi.l[2] + epi.l[3]);
@@ -171,10 +171,9 @@ clip_fwd_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
     const float s1 = fast_exp2(epi.m - M), s2 = fast_exp2(m2 - M);
     L = L * s1 + xm[1 * 128 + r] * s2;
     Wt = Wt * s1 + xm[2 * 128 + r] * s2;
-    // the label column lies in exactly one half: whichever thread saw it holds cos there
-    const int half_cols = BN / 2;
-    const int lab_in_tile = epi.label - (epi.label / BN) * BN;
-    const float diag = (lab_in_tile < half_cols) ? epi.diag : xm[3 * 128 + r];
+    // the label column lies in exactly one tile: the set that owns that tile holds cos there
+    const int lab_set = has_diag ? ((epi.label / BN - a.tile_begin) & 1) : 0;
+    const float diag = lab_set == 0 ? epi.diag : xm[3 * 128 + r];
     float bv = epi.bv;
     int bi = epi.bi;
     if (WITH_ACC) {

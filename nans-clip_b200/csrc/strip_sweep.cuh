@@ -8,7 +8,8 @@
 //   warp 0    : TMA producer   (A block once if it fits in smem, else per K-chunk; B per K-chunk)
 //   warp 1    : tcgen05.mma issuer (one lane)
 //   warp 2    : TMEM allocator (512 columns = two 128x256 fp32 accumulators, double-buffered)
-//   warps 4-11: epilogue, thread = (row = TMEM lane, column half), tcgen05.ld 32 columns at a time
+//   warps 4-11: epilogue in two sets of 4 warps that alternate tiles; thread = row (TMEM lane),
+//               tcgen05.ld 32 columns at a time
 //
 // Shared memory (128-byte swizzle, K-major, 64 elements per line):
 //   A resident: kchunks x 16 KB  +  stages x 32 KB (B)      when that fits (D <= 640)
@@ -68,9 +69,10 @@ struct SweepArgs {
   uint32_t idesc;  // M=128, N=256, K-major A and B, fp32 accumulate
 };
 
-// Epi must provide:  __device__ void tile(uint32_t taddr, int tile_idx, int chunk_begin, int chunk_end)
-//   taddr = TMEM address of this thread's warp lane group at column 0 of the accumulator buffer;
-//   the thread handles the 32-column chunks [chunk_begin, chunk_end) of the tile.
+// Epi must provide:  __device__ void tile(uint32_t taddr, int tile_idx)
+//   taddr = TMEM address of this thread's warp lane group at column 0 of the accumulator buffer.
+// A row is served by two threads (one per epilogue set): set p sees the tiles tile_begin + p,
+// tile_begin + p + 2, ...; the caller merges the two partial results.
 // Returns the 1 KB-aligned base of the dynamic shared memory, free for reuse after the call
 // (all TMA loads and MMAs of this CTA have completed and every thread has passed a barrier).
 template <bool A_RES, class Epi>
@@ -102,7 +104,7 @@ __device__ __forceinline__ uint8_t* run(const SweepArgs& a, Epi& epi) {
       mbar_init(a_full, 1);
       for (int i = 0; i < 2; ++i) {
         mbar_init(&tfull[i], 1);
-        mbar_init(&tempty[i], EPI_WARPS);
+        mbar_init(&tempty[i], EPI_WARPS / 2);
       }
       fence_barrier_init();
     }
@@ -180,21 +182,20 @@ __device__ __forceinline__ uint8_t* run(const SweepArgs& a, Epi& epi) {
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
   } else if (warp >= 4) {
-    // ---------------- epilogue: 8 warps, lane group = warp % 4, column half = (warp - 4) / 4 ----
+    // ---------------- epilogue: 2 sets of 4 warps; set p owns the tiles t with (t & 1) == p ------
+    // (= TMEM accumulator buffer p), so each set has two MMA tile times per tile and the other
+    // set's tile is drained concurrently.  lane group = warp % 4.
     const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
-    const int half = (warp - 4) >> 2;
-    constexpr int CH = BN / 32 / 2;
-    int acc = 0;
+    const int set = (warp - 4) >> 2;
     uint32_t acc_phase = 0;
-    for (int t = 0; t < ntiles; ++t) {
-      mbar_wait(&tfull[acc], acc_phase);
+    for (int t = set; t < ntiles; t += 2) {
+      mbar_wait(&tfull[set], acc_phase);
       tc_fence_after();
-      epi.tile(tmem_base + lane_base + static_cast<uint32_t>(acc * BN), a.tile_begin + t, half * CH,
-               half * CH + CH);
+      epi.tile(tmem_base + lane_base + static_cast<uint32_t>(set * BN), a.tile_begin + t);
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[acc]);
-      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      if (lane == 0) mbar_arrive(&tempty[set]);
+      acc_phase ^= 1u;
     }
   }
 

@@ -55,11 +55,11 @@ struct TopkEpi {
     }
   }
 
-  __device__ __forceinline__ void tile(uint32_t taddr, int tile_idx, int ch_begin, int ch_end) {
+  __device__ __forceinline__ void tile(uint32_t taddr, int tile_idx) {
     const int col0 = tile_idx * BN;
     const bool tail = col0 + BN > ncols;
 #pragma unroll 1
-    for (int ch = ch_begin; ch < ch_end; ++ch) {
+    for (int ch = 0; ch < BN / 32; ++ch) {
       const int cb = col0 + ch * 32;
       if (cb >= ncols) break;
       uint32_t r[32];
@@ -98,7 +98,7 @@ struct TopkParams {
   int Q, G, kchunks, stages;
   uint32_t idesc;
   int nqb, nsplit, ntiles;
-  float* cand_s;  // [nsplit * 2][Q][KC]  (one list per gallery split and column half)
+  float* cand_s;  // [nsplit * 2][Q][KC]  (one list per gallery split and tile parity)
   int* cand_i;
 };
 
@@ -129,7 +129,7 @@ topk_sweep_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   run<A_RES>(a, epi);
 
   if (warp >= 4 && row < p.Q) {
-    const int half = (warp - 4) >> 2;  // each row has one list per column half
+    const int half = (warp - 4) >> 2;  // each row has one list per epilogue set (even / odd tiles)
     const long long base = (static_cast<long long>(split * 2 + half) * p.Q + row) * KC;
 #pragma unroll
     for (int i = 0; i < KC; i += 4) {
@@ -288,10 +288,12 @@ int choose_topk_nsplit(int64_t Q, int64_t G) {
   const int sms = sm_count();
   int best = 1;
   double best_cost = 1e300;
-  const int64_t max_ns = ntiles < 16 ? ntiles : 16;  // 16 splits x 2 halves x 32 candidates = FIN_MAXC
+  // Every split starts two cold candidate lists per query (their first ~512 * log columns all take
+  // the insertion path), so a split is charged a warm-up worth about 12 tiles of MMA time.
+  const int64_t max_ns = ntiles / 16 < 1 ? 1 : (ntiles / 16 > 16 ? 16 : ntiles / 16);
   for (int64_t ns = 1; ns <= max_ns; ++ns) {
     const double waves = static_cast<double>(ceil_div(base * ns, sms));
-    const double cost = waves * (static_cast<double>(ceil_div(ntiles, ns)) + 0.75);
+    const double cost = waves * (static_cast<double>(ceil_div(ntiles, ns)) + 12.0);
     if (cost < best_cost - 1e-9) {
       best_cost = cost;
       best = static_cast<int>(ns);

@@ -164,7 +164,7 @@ def bwd(I_loc, T_loc, T_all, I_all, *, label_begin: int, s_dev: torch.Tensor,
             s_dev.data_ptr(), lse_all[0].data_ptr(), lse_all[1].data_ptr(), grad_out.data_ptr(),
             float(grad_mult), row_begin, row_count, dI.data_ptr(), dT.data_ptr(),
             dtype_code(out_dtype), ws.data_ptr(), ws.numel(), _stream()))
-    _count(1 if out_dtype == torch.float32 else 3)
+    _count(2 if out_dtype == torch.float32 else 4)  # lse min/max + backward (+ 2 casts)
     return dI, dT
 
 

@@ -161,6 +161,21 @@ def test_loss_bf16_operands(dev, n, d, s):
     assert abs(float(ds) - float(want["ds"])) <= TOL * abs(float(want["ds"]))
 
 
+def test_wide_lse_spread_takes_the_two_exp_path(dev):
+    """Half the pairs identical (lse2 ~ s*log2e), half random (lse2 ~ 0.2*s*log2e) at s = 100: the
+    base-2 log-sum-exps spread over more than 100, so the backward must not factor exp(S-lr)+exp(S-lc)."""
+    from oracle import clip_loss as OL
+    n, d, s = 512, 512, 100.0
+    I, T = synth(n, d, 9, 0.0)
+    T[: n // 2] = I[: n // 2]
+    want = OL.global_loss_and_grads(I, T, s, torch.float64)
+    spread = (want["lse_img"].max() - want["lse_img"].min()) / math.log(2.0)
+    assert float(spread) > 100.0
+    loss, acc, dI, dT, ds = run_loss(dev, I, T, s)
+    assert abs(float(loss) - float(want["loss"])) <= TOL * abs(float(want["loss"])) + 1e-6 * s
+    assert grad_ok(dI, want["dI"], n, s) and grad_ok(dT, want["dT"], n, s)
+
+
 def test_known_answers_on_device(dev):
     # identical rows -> ln N; orthonormal I = T -> ln(1 + (N-1) e^-s)
     n = 500
