@@ -80,13 +80,30 @@ struct TopkEpi {
       const float m = fmaxf(fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])),
                             fmaxf(fmaxf(mx[4], mx[5]), fmaxf(mx[6], mx[7])));
       if (__any_sync(0xffffffffu, m > ls[KC - 1])) {
-        // rare path (entered by the whole warp): ascending column order so that equal scores keep
-        // the lower index first; a column is skipped with one vote unless some row wants it
+        // rare path, entered by the whole warp and kept small (a 32x unrolled insertion thrashed
+        // the instruction cache): each lane collects a bit mask of its qualifying columns, then all
+        // lanes insert their own next candidate in lockstep, in ascending column order so that
+        // equal scores keep the lower index first.
+        const float thr = ls[KC - 1];
+        uint32_t mask = 0;
 #pragma unroll
-        for (int k = 0; k < 32; ++k) {
-          const bool q = v[k] > ls[KC - 1];
-          if (__any_sync(0xffffffffu, q)) {
-            if (q) insert(v[k], cb + k);
+        for (int k = 0; k < 32; ++k) mask |= (v[k] > thr) ? (1u << k) : 0u;
+        while (__any_sync(0xffffffffu, mask != 0)) {
+          if (mask != 0) {
+            const int k = __ffs(mask) - 1;
+            mask &= mask - 1;
+            // x = v[k] through a 5-level select tree (register arrays cannot be indexed)
+            float t16[16], t8[8], t4[4], t2[2];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) t16[i] = (k & 1) ? v[2 * i + 1] : v[2 * i];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) t8[i] = (k & 2) ? t16[2 * i + 1] : t16[2 * i];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) t4[i] = (k & 4) ? t8[2 * i + 1] : t8[2 * i];
+#pragma unroll
+            for (int i = 0; i < 2; ++i) t2[i] = (k & 8) ? t4[2 * i + 1] : t4[2 * i];
+            const float x = (k & 16) ? t2[1] : t2[0];
+            if (x > ls[KC - 1]) insert(x, cb + k);
           }
         }
       }
