@@ -298,11 +298,10 @@ def bench_loss(args):
         kb = max(3, min(args.steps, 10))
         bwd_ms = timed_steps(bwd_only, kb, 2, flush, None, dev) / kb
         fwd_ms = timed_steps(fwd_only, kb, 2, flush, None, dev) / kb
-    bwd_flops = 4.0 * n_loc * N_GLOBAL * D * 2  # two strips, (S excluded) dA: 2*rows*N*D each ... see DESIGN.md
-    # algorithmic backward work per rank: 4 * n_loc * N * D (dI and dT), forward: 2 * n_loc * N * D
+    # algorithmic work per rank: backward 4 * n_loc * N * D (dI and dT; the logit
+    # recompute is not counted), forward 2 * n_loc * N * D
     bwd_alg = 4.0 * n_loc * N_GLOBAL * D
     fwd_alg = 2.0 * n_loc * N_GLOBAL * D
-    del bwd_flops
     traffic = None
     tf = ROOT / "profiles" / "traffic.json"
     if tf.exists():
