@@ -101,6 +101,49 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
                : "memory");
 }
 
+
+// G for 32 columns of one row: g = 2^12 (p_row + p_col) (- 2^13 at the label), packed to 16 bit.
+// Everything that is uniform over the tile is a template parameter: with run-time branches inside
+// the element loop the compiler predicated both exp formulations, both conversions and the label
+// test into every element (~13 issue slots per element instead of ~5).
+template <bool FACTORED, bool BF16, bool LABEL>
+__device__ __forceinline__ void softmax_grad32(const uint32_t (&r)[32], const float* __restrict__ cf,
+                                               float c, float lr2, float a_i, int label_rel,
+                                               uint32_t* __restrict__ g16) {
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const float4 f = *reinterpret_cast<const float4*>(cf + 4 * q);  // smem broadcast
+    const float cfv[4] = {f.x, f.y, f.z, f.w};
+    float g[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float cosv = __uint_as_float(r[4 * q + e]);
+      const float e1 = fast_exp2(fmaf(cosv, c, -lr2));
+      if (FACTORED) g[e] = e1 * fmaf(a_i, cfv[e], 1.0f);
+      else g[e] = e1 + fast_exp2(fmaf(cosv, c, -cfv[e]));
+      if (LABEL) g[e] = (4 * q + e == label_rel) ? g[e] - 8192.0f : g[e];  // 2 * 2^12
+    }
+#pragma unroll
+    for (int e = 0; e < 4; e += 2) {
+      if (BF16) {
+        const __nv_bfloat162 hh = __floats2bfloat162_rn(g[e], g[e + 1]);
+        g16[2 * q + (e >> 1)] = *reinterpret_cast<const uint32_t*>(&hh);
+      } else {
+        const __half2 hh = __floats2half2_rn(g[e], g[e + 1]);
+        g16[2 * q + (e >> 1)] = *reinterpret_cast<const uint32_t*>(&hh);
+      }
+    }
+  }
+}
+
+template <bool FACTORED, bool BF16>
+__device__ __forceinline__ void softmax_grad32_dispatch(bool has_label, const uint32_t (&r)[32],
+                                                        const float* __restrict__ cf, float c, float lr2,
+                                                        float a_i, int label_rel, uint32_t* __restrict__ g16) {
+  if (has_label) softmax_grad32<FACTORED, BF16, true>(r, cf, c, lr2, a_i, label_rel, g16);
+  else softmax_grad32<FACTORED, BF16, false>(r, cf, c, lr2, a_i, label_rel, g16);
+}
+
 template <bool A_RES>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 clip_bwd_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmB0,
@@ -357,31 +400,19 @@ clip_bwd_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         const bool has_label = (warp_label_lo < cb + 32) && (warp_label_lo + 31 >= cb);
         uint32_t r[32];
         tmem_ld32(tmem_base + lane_base + TMEM_S + sb * KT + half * 64 + sub * 32, r);
-        float lc2[32];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float4 f = *reinterpret_cast<const float4*>(cf + sub * 32 + 4 * q);  // broadcast
-          lc2[4 * q + 0] = f.x; lc2[4 * q + 1] = f.y; lc2[4 * q + 2] = f.z; lc2[4 * q + 3] = f.w;
-        }
         tmem_wait_ld();
+        const float* cfs = cf + sub * 32;
+        const int label_rel = label - cb;  // in [0,32) only for the thread whose label is here
+        uint32_t* go = g16 + sub * 16;
+        if (p.debug & 1) {
 #pragma unroll
-        for (int k = 0; k < 32; k += 2) {
-          float g[2];
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const float cosv = __uint_as_float(r[k + e]);
-            const float e1 = (p.debug & 1) ? cosv : fast_exp2(fmaf(cosv, c, -lr2));
-            if (factored) g[e] = e1 * fmaf(a_i, lc2[k + e], 1.0f);
-            else g[e] = e1 + fast_exp2(fmaf(cosv, c, -lc2[k + e]));
-            if (has_label && cb + k + e == label) g[e] -= 8192.0f;  // 2 * 2^12
-          }
-          if (g_bf16) {
-            const __nv_bfloat162 hh = __floats2bfloat162_rn(g[0], g[1]);
-            g16[sub * 16 + (k >> 1)] = *reinterpret_cast<const uint32_t*>(&hh);
-          } else {
-            const __half2 hh = __floats2half2_rn(g[0], g[1]);
-            g16[sub * 16 + (k >> 1)] = *reinterpret_cast<const uint32_t*>(&hh);
-          }
+          for (int k = 0; k < 16; ++k) go[k] = r[2 * k];
+        } else if (factored) {
+          if (g_bf16) softmax_grad32_dispatch<true, true>(has_label, r, cfs, c, lr2, a_i, label_rel, go);
+          else softmax_grad32_dispatch<true, false>(has_label, r, cfs, c, lr2, a_i, label_rel, go);
+        } else {
+          if (g_bf16) softmax_grad32_dispatch<false, true>(has_label, r, cfs, c, lr2, a_i, label_rel, go);
+          else softmax_grad32_dispatch<false, false>(has_label, r, cfs, c, lr2, a_i, label_rel, go);
         }
       }
       __syncwarp();
@@ -601,7 +632,7 @@ clip_bwd_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_cons
           if (++sr == p.nr) { sr = 0; pr ^= 1u; }
         }
       }
-      if (tau >= 1) {
+      if (tau >= 1 && !(p.debug & 2)) {
         const int col0 = (tile_begin + tau - 1) * KT;
         for (int j = 0; j < slice_np; ++j) {
           mbar_wait(&emptyR[sr], pr ^ 1u);
@@ -659,6 +690,10 @@ clip_bwd_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_cons
         mbar_wait(&g_ready[gb], static_cast<uint32_t>(u >> 1) & 1u);
         tc_fence_after();
         const uint32_t g_tmem = tmem_base + TMEM_S + gb * KT;
+        if (p.debug & 2) {
+          if (tau == ntiles) { if (elect_one()) tc_commit_pair(da_full, 3); __syncwarp(); }
+          continue;
+        }
         for (int j = 0; j < slice_np; ++j) {
           mbar_wait(&fullR[sr], pr);
           tc_fence_after();
@@ -720,37 +755,33 @@ clip_bwd_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_cons
       mbar_wait(&s_full[sb], static_cast<uint32_t>(t >> 1) & 1u);
       tc_fence_after();
       const float* cf = cfbuf + sb * KT + half * 64;
+      if (p.debug & 4) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&b_empty[sb]);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(&g_ready[sb], 0);
+        continue;
+      }
 #pragma unroll
       for (int sub = 0; sub < 2; ++sub) {
         const int cb = cb0 + sub * 32;
         const bool has_label = (warp_label_lo < cb + 32) && (warp_label_lo + 31 >= cb);
         uint32_t r[32];
         tmem_ld32(tmem_base + lane_base + TMEM_S + sb * KT + half * 64 + sub * 32, r);
-        float lc2[32];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float4 f = *reinterpret_cast<const float4*>(cf + sub * 32 + 4 * q);
-          lc2[4 * q + 0] = f.x; lc2[4 * q + 1] = f.y; lc2[4 * q + 2] = f.z; lc2[4 * q + 3] = f.w;
-        }
         tmem_wait_ld();
+        const float* cfs = cf + sub * 32;
+        const int label_rel = label - cb;  // in [0,32) only for the thread whose label is here
+        uint32_t* go = g16 + sub * 16;
+        if (p.debug & 1) {
 #pragma unroll
-        for (int k = 0; k < 32; k += 2) {
-          float g[2];
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const float cosv = __uint_as_float(r[k + e]);
-            const float e1 = fast_exp2(fmaf(cosv, c, -lr2));
-            if (factored) g[e] = e1 * fmaf(a_i, lc2[k + e], 1.0f);
-            else g[e] = e1 + fast_exp2(fmaf(cosv, c, -lc2[k + e]));
-            if (has_label && cb + k + e == label) g[e] -= 8192.0f;
-          }
-          if (g_bf16) {
-            const __nv_bfloat162 hh = __floats2bfloat162_rn(g[0], g[1]);
-            g16[sub * 16 + (k >> 1)] = *reinterpret_cast<const uint32_t*>(&hh);
-          } else {
-            const __half2 hh = __floats2half2_rn(g[0], g[1]);
-            g16[sub * 16 + (k >> 1)] = *reinterpret_cast<const uint32_t*>(&hh);
-          }
+          for (int k = 0; k < 16; ++k) go[k] = r[2 * k];
+        } else if (factored) {
+          if (g_bf16) softmax_grad32_dispatch<true, true>(has_label, r, cfs, c, lr2, a_i, label_rel, go);
+          else softmax_grad32_dispatch<true, false>(has_label, r, cfs, c, lr2, a_i, label_rel, go);
+        } else {
+          if (g_bf16) softmax_grad32_dispatch<false, true>(has_label, r, cfs, c, lr2, a_i, label_rel, go);
+          else softmax_grad32_dispatch<false, false>(has_label, r, cfs, c, lr2, a_i, label_rel, go);
         }
       }
       __syncwarp();
