@@ -12,6 +12,8 @@
 // clip_fwd_finalize_kernel merges the slots into lse, loss / d(scale) sums and hit counts.
 //
 // Roofline: tensor cores.  Algorithmic flops per unit row block = 2 * 128 * ncols * D per strip.
+#include <stdlib.h>
+
 #include "strip_sweep.cuh"
 
 namespace nans {
@@ -118,12 +120,13 @@ struct LseEpi {
   }
 };
 
-template <bool A_RES, bool WITH_ACC>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+// CP: CTA-pair mode (cluster of 2, cta_group::2 MMAs); a unit is then a 256-row block.
+template <bool A_RES, bool WITH_ACC, bool CP>
+__global__ void __cluster_dims__(CP ? 2 : 1, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 clip_fwd_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmB0,
                 const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
                 const FwdParams p) {
-  const int unit = blockIdx.x;
+  const int unit = CP ? (blockIdx.x >> 1) : blockIdx.x;
   const int split = unit % p.nsplit;
   const int rb = (unit / p.nsplit) % p.nrb;
   const int strip = unit / (p.nsplit * p.nrb);
@@ -131,7 +134,7 @@ clip_fwd_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
   SweepArgs a;
   a.tmA = strip == 0 ? &tmA0 : &tmA1;
   a.tmB = strip == 0 ? &tmB0 : &tmB1;
-  a.row0 = rb * BM;
+  a.row0 = CP ? rb * 2 * BM + static_cast<int>(blockIdx.x & 1) * BM : rb * BM;
   a.tile_begin = static_cast<int>(static_cast<long long>(split) * p.ntiles / p.nsplit);
   a.tile_end = static_cast<int>(static_cast<long long>(split + 1) * p.ntiles / p.nsplit);
   a.kchunks = p.kchunks;
@@ -145,7 +148,7 @@ clip_fwd_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
   LseEpi<WITH_ACC> epi;
   epi.init(__ldg(p.s_dev) * kLog2e, p.ncols, row + p.label_shift, lane);
 
-  uint8_t* scratch = run<A_RES>(a, epi);
+  uint8_t* scratch = run<A_RES, CP>(a, epi);
 
   // The even and odd tiles of a row were drained by two threads (warps 4-7 and 8-11): merge
   // through shared memory (the pipeline buffers are dead after run()).
@@ -324,10 +327,16 @@ FwdWs carve_fwd_ws(void* ws, int64_t n_loc, int64_t total_slots) {
   return w;
 }
 
+bool fwd_pair_mode() {
+  const char* e = getenv("NANS_FWD_1CTA");
+  return !(e && e[0] == '1');
+}
+
 int choose_nsplit(int64_t n_loc, int64_t ncols) {
-  const int64_t base = 2 * ceil_div(n_loc, BM);
+  const bool pair = fwd_pair_mode();
+  const int64_t base = 2 * ceil_div(n_loc, pair ? 2 * BM : BM);
   const int64_t ntiles = ceil_div(ncols, BN);
-  const int sms = sm_count();
+  const int sms = pair ? sm_count() / 2 : sm_count();
   int best = 1;
   double best_cost = 1e300;
   const int64_t max_ns = ntiles < 32 ? ntiles : 32;
@@ -385,22 +394,24 @@ extern "C" int nans_clip_loss_fwd_phase(const void* I_loc, const void* T_loc, in
   }
   FwdWs w = carve_fwd_ws(ws, n_loc, slot_begin + nsplit);
 
+  const bool pair = fwd_pair_mode();
   const int kchunks = static_cast<int>(ceil_div(D, BK));
-  const SmemPlan plan = plan_smem(kchunks);
+  const SmemPlan plan = plan_smem(kchunks, pair);
 
   CUtensorMap tmA0, tmB0, tmA1, tmB1;
+  const uint32_t bbox = pair ? BN / 2 : BN;  // in pair mode a CTA loads 128 of a tile's 256 rows
   if ((rc = make_tmap_16b(&tmA0, I_loc, feat_dtype, n_loc, D, ld_loc, BM)) != NANS_OK) return rc;
-  if ((rc = make_tmap_16b(&tmB0, T_cols, feat_dtype, ncols, D, ld_cols, BN)) != NANS_OK) return rc;
+  if ((rc = make_tmap_16b(&tmB0, T_cols, feat_dtype, ncols, D, ld_cols, bbox)) != NANS_OK) return rc;
   if ((rc = make_tmap_16b(&tmA1, T_loc, feat_dtype, n_loc, D, ld_loc, BM)) != NANS_OK) return rc;
-  if ((rc = make_tmap_16b(&tmB1, I_cols, feat_dtype, ncols, D, ld_cols, BN)) != NANS_OK) return rc;
+  if ((rc = make_tmap_16b(&tmB1, I_cols, feat_dtype, ncols, D, ld_cols, bbox)) != NANS_OK) return rc;
 
   FwdParams p;
   p.n_loc = static_cast<int>(n_loc);
   p.ncols = static_cast<int>(ncols);
   p.kchunks = kchunks;
   p.stages = plan.stages;
-  p.idesc = make_idesc(idesc_fmt(feat_dtype), idesc_fmt(feat_dtype), 0, 0, BM, BN);
-  p.nrb = static_cast<int>(ceil_div(n_loc, BM));
+  p.idesc = make_idesc(idesc_fmt(feat_dtype), idesc_fmt(feat_dtype), 0, 0, pair ? 2 * BM : BM, BN);
+  p.nrb = static_cast<int>(ceil_div(n_loc, pair ? 2 * BM : BM));
   p.nsplit = nsplit;
   p.ntiles = static_cast<int>(ceil_div(ncols, BN));
   p.label_shift = static_cast<int>(label_begin - col_global_begin);
@@ -416,11 +427,17 @@ extern "C" int nans_clip_loss_fwd_phase(const void* I_loc, const void* T_loc, in
   p.slot_stride = w.slot_stride;
 
   const bool with_acc = (flags & NANS_LOSS_WITH_ACC) != 0;
-  auto kern = plan.a_resident ? (with_acc ? clip_fwd_kernel<true, true> : clip_fwd_kernel<true, false>)
-                              : (with_acc ? clip_fwd_kernel<false, true> : clip_fwd_kernel<false, false>);
+  void (*kern)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const FwdParams);
+  if (pair) {
+    kern = plan.a_resident ? (with_acc ? clip_fwd_kernel<true, true, true> : clip_fwd_kernel<true, false, true>)
+                           : (with_acc ? clip_fwd_kernel<false, true, true> : clip_fwd_kernel<false, false, true>);
+  } else {
+    kern = plan.a_resident ? (with_acc ? clip_fwd_kernel<true, true, false> : clip_fwd_kernel<true, false, false>)
+                           : (with_acc ? clip_fwd_kernel<false, true, false> : clip_fwd_kernel<false, false, false>);
+  }
   NANS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     static_cast<int>(plan.bytes)));
-  const unsigned grid = static_cast<unsigned>(2 * p.nrb * p.nsplit);
+  const unsigned grid = static_cast<unsigned>((pair ? 2 : 1) * 2 * p.nrb * p.nsplit);
   kern<<<grid, NUM_THREADS, plan.bytes, static_cast<cudaStream_t>(stream)>>>(tmA0, tmB0, tmA1, tmB1, p);
   NANS_CUDA_OK(cudaGetLastError());
   return NANS_OK;

@@ -38,20 +38,22 @@ struct SmemPlan {
   size_t bytes;  // dynamic shared memory to request (includes 1 KB alignment slack)
 };
 
-inline SmemPlan plan_smem(int kchunks) {
+// pair = true: CTA-pair mode, a CTA stages half of every B stage (16 KB)
+inline SmemPlan plan_smem(int kchunks, bool pair) {
   SmemPlan p;
+  const size_t bst = pair ? B_STAGE / 2 : B_STAGE;
   const size_t cap = SMEM_CAP - 1024 - BAR_BYTES;
   const size_t a_res = static_cast<size_t>(kchunks) * A_CHUNK;
-  if (a_res + 2 * B_STAGE <= cap) {
+  if (a_res + 2 * bst <= cap) {
     p.a_resident = true;
-    p.stages = static_cast<int>((cap - a_res) / B_STAGE);
+    p.stages = static_cast<int>((cap - a_res) / bst);
     if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
-    p.bytes = a_res + static_cast<size_t>(p.stages) * B_STAGE + BAR_BYTES + 1024;
+    p.bytes = a_res + static_cast<size_t>(p.stages) * bst + BAR_BYTES + 1024;
   } else {
     p.a_resident = false;
-    p.stages = static_cast<int>(cap / (A_CHUNK + B_STAGE));
+    p.stages = static_cast<int>(cap / (A_CHUNK + bst));
     if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
-    p.bytes = static_cast<size_t>(p.stages) * (A_CHUNK + B_STAGE) + BAR_BYTES + 1024;
+    p.bytes = static_cast<size_t>(p.stages) * (A_CHUNK + bst) + BAR_BYTES + 1024;
   }
   return p;
 }
@@ -66,23 +68,33 @@ struct SweepArgs {
   int tile_end;
   int kchunks;     // ceil(D / 64)
   int stages;
-  uint32_t idesc;  // M=128, N=256, K-major A and B, fp32 accumulate
+  uint32_t idesc;  // M=128 (256 in pair mode), N=256, K-major A and B, fp32 accumulate
 };
 
 // Epi must provide:  __device__ void tile(uint32_t taddr, int tile_idx)
 //   taddr = TMEM address of this thread's warp lane group at column 0 of the accumulator buffer.
 // A row is served by two threads (one per epilogue set): set p sees the tiles tile_begin + p,
 // tile_begin + p + 2, ...; the caller merges the two partial results.
+//
+// CP = true: CTA-pair mode (cta_group::2).  The two CTAs of a cluster own 256 consecutive rows
+// (SweepArgs::row0 is the CTA's own first row) and share every tcgen05.mma (M = 256, N = 256): each
+// CTA stages only its half of every B stage (128 of the 256 tile rows), which halves the shared-
+// memory traffic per MMA — the single-CTA kernel moves 4 KB (A) + 8 KB (B) of reads and 8 KB of TMA
+// writes per 128-clk MMA against 128 B/clk of shared memory (84 % tensor pipe measured).  Only the
+// leader (cluster rank 0) issues MMAs; loads of both CTAs credit the leader's barriers, the leader's
+// commits are multicast, and the partner's epilogue warps release accumulators remotely.
+//
 // Returns the 1 KB-aligned base of the dynamic shared memory, free for reuse after the call
 // (all TMA loads and MMAs of this CTA have completed and every thread has passed a barrier).
-template <bool A_RES, class Epi>
+template <bool A_RES, bool CP, class Epi>
 __device__ __forceinline__ uint8_t* run(const SweepArgs& a, Epi& epi) {
+  constexpr int BST = CP ? B_STAGE / 2 : B_STAGE;  // this CTA's bytes of a B stage
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* smA = smem;
   uint8_t* smB = smem + static_cast<size_t>(A_RES ? a.kchunks : a.stages) * A_CHUNK;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smB + static_cast<size_t>(a.stages) * B_STAGE);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smB + static_cast<size_t>(a.stages) * BST);
   uint64_t* full = bars;
   uint64_t* empty = bars + MAX_STAGES;
   uint64_t* a_full = bars + 2 * MAX_STAGES;
@@ -92,6 +104,9 @@ __device__ __forceinline__ uint8_t* run(const SweepArgs& a, Epi& epi) {
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t rank = CP ? cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
+  constexpr uint32_t NCTA = CP ? 2u : 1u;
 
   if (warp == 0) {
     if (elect_one()) {
@@ -104,16 +119,22 @@ __device__ __forceinline__ uint8_t* run(const SweepArgs& a, Epi& epi) {
       mbar_init(a_full, 1);
       for (int i = 0; i < 2; ++i) {
         mbar_init(&tfull[i], 1);
-        mbar_init(&tempty[i], EPI_WARPS / 2);
+        mbar_init(&tempty[i], NCTA * (EPI_WARPS / 2));
       }
       fence_barrier_init();
     }
   } else if (warp == 2) {
-    tmem_alloc(tmem_ptr, TMEM_COLS);
-    tmem_relinquish();
+    if (CP) {
+      tmem_alloc_pair(tmem_ptr, TMEM_COLS);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(tmem_ptr, TMEM_COLS);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if (CP) cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
@@ -123,31 +144,38 @@ __device__ __forceinline__ uint8_t* run(const SweepArgs& a, Epi& epi) {
     // ---------------- TMA producer (whole warp in the loop, one elected lane issues) ----------
     if (A_RES) {
       if (elect_one()) {
-        mbar_arrive_expect_tx(a_full, static_cast<uint32_t>(a.kchunks) * A_CHUNK);
-        for (int c = 0; c < a.kchunks; ++c)
-          tma_load_2d(smA + static_cast<size_t>(c) * A_CHUNK, a.tmA, a_full, c * BK, a.row0);
+        if (leader) mbar_arrive_expect_tx(a_full, NCTA * static_cast<uint32_t>(a.kchunks) * A_CHUNK);
+        for (int c = 0; c < a.kchunks; ++c) {
+          if (CP) tma_load_2d_pair(smA + static_cast<size_t>(c) * A_CHUNK, a.tmA, a_full, c * BK, a.row0);
+          else tma_load_2d(smA + static_cast<size_t>(c) * A_CHUNK, a.tmA, a_full, c * BK, a.row0);
+        }
       }
       __syncwarp();
     }
     int stage = 0;
     uint32_t phase = 0;
     for (int t = 0; t < ntiles; ++t) {
-      const int col0 = (a.tile_begin + t) * BN;
+      const int col0 = (a.tile_begin + t) * BN + (CP ? static_cast<int>(rank) * (BN / 2) : 0);
       for (int c = 0; c < a.kchunks; ++c) {
         mbar_wait(&empty[stage], phase ^ 1u);
         if (elect_one()) {
-          mbar_arrive_expect_tx(&full[stage], A_RES ? B_STAGE : (A_CHUNK + B_STAGE));
-          if (!A_RES)
-            tma_load_2d(smA + static_cast<size_t>(stage) * A_CHUNK, a.tmA, &full[stage], c * BK,
-                        a.row0);
-          tma_load_2d(smB + static_cast<size_t>(stage) * B_STAGE, a.tmB, &full[stage], c * BK, col0);
+          if (leader) mbar_arrive_expect_tx(&full[stage], NCTA * (A_RES ? BST : (A_CHUNK + BST)));
+          if (CP) {
+            if (!A_RES)
+              tma_load_2d_pair(smA + static_cast<size_t>(stage) * A_CHUNK, a.tmA, &full[stage], c * BK, a.row0);
+            tma_load_2d_pair(smB + static_cast<size_t>(stage) * BST, a.tmB, &full[stage], c * BK, col0);
+          } else {
+            if (!A_RES)
+              tma_load_2d(smA + static_cast<size_t>(stage) * A_CHUNK, a.tmA, &full[stage], c * BK, a.row0);
+            tma_load_2d(smB + static_cast<size_t>(stage) * BST, a.tmB, &full[stage], c * BK, col0);
+          }
         }
         __syncwarp();
         if (++stage == a.stages) { stage = 0; phase ^= 1u; }
       }
     }
-  } else if (warp == 1) {
-    // ---------------- MMA issuer ----------------
+  } else if (warp == 1 && leader) {
+    // ---------------- MMA issuer (leader CTA only in pair mode) ----------------
     if (A_RES) {
       mbar_wait(a_full, 0);
       tc_fence_after();
@@ -167,14 +195,21 @@ __device__ __forceinline__ uint8_t* run(const SweepArgs& a, Epi& epi) {
         tc_fence_after();
         if (elect_one()) {
           const uint32_t a_addr = smA_addr + static_cast<uint32_t>(A_RES ? c : stage) * A_CHUNK;
-          const uint32_t b_addr = smB_addr + static_cast<uint32_t>(stage) * B_STAGE;
+          const uint32_t b_addr = smB_addr + static_cast<uint32_t>(stage) * BST;
           const uint64_t ad = make_smem_desc(a_addr, 16, 1024);
           const uint64_t bd = make_smem_desc(b_addr, 16, 1024);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k)  // +32 bytes (>> 4 = 2) per K step inside the swizzle atom
-            mma_ss(d_tmem, ad + 2 * k, bd + 2 * k, a.idesc, (c | k) != 0 ? 1u : 0u);
-          tc_commit(&empty[stage]);  // frees the smem stage once these MMAs have read it
-          if (c == a.kchunks - 1) tc_commit(&tfull[acc]);  // accumulator complete -> epilogue
+          for (int k = 0; k < BK / 16; ++k) {  // +32 bytes (>> 4 = 2) per K step inside the swizzle atom
+            if (CP) mma_ss_pair(d_tmem, ad + 2 * k, bd + 2 * k, a.idesc, (c | k) != 0 ? 1u : 0u);
+            else mma_ss(d_tmem, ad + 2 * k, bd + 2 * k, a.idesc, (c | k) != 0 ? 1u : 0u);
+          }
+          if (CP) {
+            tc_commit_pair(&empty[stage], 3);
+            if (c == a.kchunks - 1) tc_commit_pair(&tfull[acc], 3);
+          } else {
+            tc_commit(&empty[stage]);  // frees the smem stage once these MMAs have read it
+            if (c == a.kchunks - 1) tc_commit(&tfull[acc]);  // accumulator complete -> epilogue
+          }
         }
         __syncwarp();
         if (++stage == a.stages) { stage = 0; phase ^= 1u; }
@@ -194,16 +229,21 @@ __device__ __forceinline__ uint8_t* run(const SweepArgs& a, Epi& epi) {
       epi.tile(tmem_base + lane_base + static_cast<uint32_t>(set * BN), a.tile_begin + t);
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[set]);
+      if (lane == 0) {
+        if (CP) mbar_arrive_cluster(&tempty[set], 0);
+        else mbar_arrive(&tempty[set]);
+      }
       acc_phase ^= 1u;
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  if (CP) cluster_sync_all();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    if (CP) tmem_dealloc_pair(tmem_base, TMEM_COLS);
+    else tmem_dealloc(tmem_base, TMEM_COLS);
   }
   return smem;
 }

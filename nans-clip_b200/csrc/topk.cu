@@ -15,6 +15,7 @@
 //
 // Roofline: tensor cores, 2*Q*G*D flops; the candidate lists are O(Q * k_cand) bytes.
 #include <limits.h>
+#include <stdlib.h>
 
 #include "strip_sweep.cuh"
 
@@ -119,18 +120,18 @@ struct TopkParams {
   int* cand_i;
 };
 
-template <bool A_RES, int KC>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+template <bool A_RES, int KC, bool CP>
+__global__ void __cluster_dims__(CP ? 2 : 1, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 topk_sweep_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmG,
                   const TopkParams p) {
-  const int unit = blockIdx.x;
+  const int unit = CP ? (blockIdx.x >> 1) : blockIdx.x;
   const int split = unit % p.nsplit;
   const int qb = unit / p.nsplit;
 
   SweepArgs a;
   a.tmA = &tmQ;
   a.tmB = &tmG;
-  a.row0 = qb * BM;
+  a.row0 = CP ? qb * 2 * BM + static_cast<int>(blockIdx.x & 1) * BM : qb * BM;
   a.tile_begin = static_cast<int>(static_cast<long long>(split) * p.ntiles / p.nsplit);
   a.tile_end = static_cast<int>(static_cast<long long>(split + 1) * p.ntiles / p.nsplit);
   a.kchunks = p.kchunks;
@@ -143,7 +144,7 @@ topk_sweep_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 
   TopkEpi<KC> epi;
   epi.init(p.G);
-  run<A_RES>(a, epi);
+  run<A_RES, CP>(a, epi);
 
   if (warp >= 4 && row < p.Q) {
     const int half = (warp - 4) >> 2;  // each row has one list per epilogue set (even / odd tiles)
@@ -299,10 +300,16 @@ __global__ void __launch_bounds__(FIN_WARPS * 32) topk_merge_kernel(const MergeP
   }
 }
 
+bool topk_pair_mode() {
+  const char* e = getenv("NANS_TOPK_1CTA");
+  return !(e && e[0] == '1');
+}
+
 int choose_topk_nsplit(int64_t Q, int64_t G) {
-  const int64_t base = ceil_div(Q, BM);
+  const bool pair = topk_pair_mode();
+  const int64_t base = ceil_div(Q, pair ? 2 * BM : BM);
   const int64_t ntiles = ceil_div(G, BN);
-  const int sms = sm_count();
+  const int sms = pair ? sm_count() / 2 : sm_count();
   int best = 1;
   double best_cost = 1e300;
   // Every split starts two cold candidate lists per query (their first ~512 * log columns all take
@@ -368,19 +375,20 @@ extern "C" int nans_topk_ip(const void* Q16, const void* G16, int feat_dtype, co
 
   const int nsplit = choose_topk_nsplit(Q, G);
   const int kchunks = static_cast<int>(ceil_div(D, BK));
-  const SmemPlan plan = plan_smem(kchunks);
+  const bool pair = topk_pair_mode();
+  const SmemPlan plan = plan_smem(kchunks, pair);
 
   CUtensorMap tmQ, tmG;
   if ((rc = make_tmap_16b(&tmQ, Q16, feat_dtype, Q, D, D, BM)) != NANS_OK) return rc;
-  if ((rc = make_tmap_16b(&tmG, G16, feat_dtype, G, D, D, BN)) != NANS_OK) return rc;
+  if ((rc = make_tmap_16b(&tmG, G16, feat_dtype, G, D, D, pair ? BN / 2 : BN)) != NANS_OK) return rc;
 
   TopkParams p;
   p.Q = static_cast<int>(Q);
   p.G = static_cast<int>(G);
   p.kchunks = kchunks;
   p.stages = plan.stages;
-  p.idesc = make_idesc(idesc_fmt(feat_dtype), idesc_fmt(feat_dtype), 0, 0, BM, BN);
-  p.nqb = static_cast<int>(ceil_div(Q, BM));
+  p.idesc = make_idesc(idesc_fmt(feat_dtype), idesc_fmt(feat_dtype), 0, 0, pair ? 2 * BM : BM, BN);
+  p.nqb = static_cast<int>(ceil_div(Q, pair ? 2 * BM : BM));
   p.nsplit = nsplit;
   p.ntiles = static_cast<int>(ceil_div(G, BN));
   p.cand_s = static_cast<float*>(ws);
@@ -388,11 +396,16 @@ extern "C" int nans_topk_ip(const void* Q16, const void* G16, int feat_dtype, co
                                     align_up(static_cast<size_t>(nsplit) * 2 * Q * k_cand * 4, 256));
 
   void (*kern)(const CUtensorMap, const CUtensorMap, const TopkParams);
-  if (k_cand == 16) kern = plan.a_resident ? topk_sweep_kernel<true, 16> : topk_sweep_kernel<false, 16>;
-  else kern = plan.a_resident ? topk_sweep_kernel<true, 32> : topk_sweep_kernel<false, 32>;
+  if (pair) {
+    if (k_cand == 16) kern = plan.a_resident ? topk_sweep_kernel<true, 16, true> : topk_sweep_kernel<false, 16, true>;
+    else kern = plan.a_resident ? topk_sweep_kernel<true, 32, true> : topk_sweep_kernel<false, 32, true>;
+  } else {
+    if (k_cand == 16) kern = plan.a_resident ? topk_sweep_kernel<true, 16, false> : topk_sweep_kernel<false, 16, false>;
+    else kern = plan.a_resident ? topk_sweep_kernel<true, 32, false> : topk_sweep_kernel<false, 32, false>;
+  }
   NANS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     static_cast<int>(plan.bytes)));
-  const unsigned grid = static_cast<unsigned>(p.nqb * p.nsplit);
+  const unsigned grid = static_cast<unsigned>((pair ? 2 : 1) * p.nqb * p.nsplit);
   kern<<<grid, NUM_THREADS, plan.bytes, st>>>(tmQ, tmG, p);
   NANS_CUDA_OK(cudaGetLastError());
 
