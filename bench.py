@@ -279,7 +279,7 @@ def bench_loss(args):
                         with_acc=False, ws=ws, slot_begin=0)
 
         fwd_only()
-        lse, _sc = K.fwd_finalize(n_loc, slots, rank * n_loc, s_dev, False, ws)
+        lse, _sc, _ = K.fwd_finalize(n_loc, slots, rank * n_loc, s_dev, False, ws)
         if W > 1:
             lse_g = torch.empty((W * 2, n_loc), dtype=torch.float32, device=dev)
             dist.all_gather_into_tensor(lse_g, lse.contiguous())

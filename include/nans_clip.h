@@ -90,6 +90,11 @@ int nans_l2norm_bwd(const void* x, int x_dtype, int64_t ld_x, const float* inv_n
  * [slot_begin, slot_begin + nans_clip_loss_fwd_phase_slots(...)); nans_clip_loss_fwd_finalize
  * merges `total_slots` slots.
  *
+ * Columns [skip_col_begin, skip_col_begin + skip_col_count) of the operands are NOT swept by this
+ * phase (e.g. the local block inside the gathered buffer, already covered by the local phase);
+ * both values must be multiples of 256.  Size the slots with
+ * nans_clip_loss_fwd_phase_slots(n_loc, ncols - skip_col_count, D).
+ *
  *   I_loc, T_loc   [n_loc, D] 16-bit (feat_dtype), leading dims ld_loc
  *   T_cols, I_cols [ncols, D] 16-bit, leading dim ld_cols
  *   s_dev          device pointer to the fp32 logit scale s = exp(logit_scale)
@@ -100,7 +105,8 @@ size_t nans_clip_loss_fwd_workspace_bytes(int64_t n_loc, int64_t total_slots);
 int nans_clip_loss_fwd_phase(const void* I_loc, const void* T_loc, int64_t ld_loc,
                              const void* T_cols, const void* I_cols, int64_t ld_cols,
                              int feat_dtype, int64_t n_loc, int64_t ncols, int64_t D,
-                             int64_t col_global_begin, int64_t label_begin, const float* s_dev,
+                             int64_t col_global_begin, int64_t label_begin,
+                             int64_t skip_col_begin, int64_t skip_col_count, const float* s_dev,
                              int flags, void* ws, size_t ws_bytes, int64_t slot_begin,
                              void* stream);
 

@@ -38,6 +38,7 @@ _SIGNATURES = {
     "nans_clip_loss_fwd_workspace_bytes": (c_size_t, [c_int64, c_int64]),
     "nans_clip_loss_fwd_phase": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64,
                                          c_int, c_int64, c_int64, c_int64, c_int64, c_int64,
+                                         c_int64, c_int64,
                                          c_void_p, c_int, c_void_p, c_size_t, c_int64, c_void_p]),
     "nans_clip_loss_fwd_finalize": (c_int, [c_int64, c_int64, c_int64, c_void_p, c_int, c_void_p,
                                             c_size_t, c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -840,12 +840,14 @@ clip_bwd_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_cons
   }
 }
 
-// min / max over both lse arrays, as order-preserving ints (slots pre-set by a memset)
-__global__ void __launch_bounds__(256) lse_minmax_kernel(const float* __restrict__ a,
-                                                         const float* __restrict__ b, int n,
-                                                         int* __restrict__ out) {
+// min / max over both lse arrays, written as order-preserving ints.  One block (2N floats is at
+// most a few hundred KB): a single launch, no memset, no atomics.
+__global__ void __launch_bounds__(1024) lse_minmax_kernel(const float* __restrict__ a,
+                                                          const float* __restrict__ b, int n,
+                                                          int* __restrict__ out) {
+  __shared__ float slo[32], shi[32];
   float lo = INFINITY, hi = -INFINITY;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 2 * n; i += gridDim.x * blockDim.x) {
+  for (int i = threadIdx.x; i < 2 * n; i += blockDim.x) {
     const float v = i < n ? a[i] : b[i - n];
     lo = fminf(lo, v);
     hi = fmaxf(hi, v);
@@ -856,11 +858,23 @@ __global__ void __launch_bounds__(256) lse_minmax_kernel(const float* __restrict
     hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
   }
   if ((threadIdx.x & 31) == 0) {
-    int il = __float_as_int(lo), ih = __float_as_int(hi);
-    il = il >= 0 ? il : il ^ 0x7fffffff;
-    ih = ih >= 0 ? ih : ih ^ 0x7fffffff;
-    atomicMin(out, il);
-    atomicMax(out + 1, ih);
+    slo[threadIdx.x >> 5] = lo;
+    shi[threadIdx.x >> 5] = hi;
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    lo = slo[threadIdx.x];
+    hi = shi[threadIdx.x];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+      hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if (threadIdx.x == 0) {
+      int il = __float_as_int(lo), ih = __float_as_int(hi);
+      out[0] = il >= 0 ? il : il ^ 0x7fffffff;
+      out[1] = ih >= 0 ? ih : ih ^ 0x7fffffff;
+    }
   }
 }
 
@@ -960,13 +974,8 @@ extern "C" int nans_clip_loss_bwd(const void* I_loc, const void* T_loc, int64_t 
   }
   NANS_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 15) == 0, "loss_bwd: workspace must be 16-byte aligned");
   int* minmax = static_cast<int*>(ws);
-  NANS_CUDA_OK(cudaMemsetAsync(minmax, 0x7f, 4, st));      // +3.39e38 as an ordered int
-  NANS_CUDA_OK(cudaMemsetAsync(minmax + 1, 0x80, 4, st));  // a very negative ordered int
-  {
-    const int blocks = static_cast<int>(ceil_div(2 * N, 256 * 8) < 1 ? 1 : (ceil_div(2 * N, 256 * 8) > 256 ? 256 : ceil_div(2 * N, 256 * 8)));
-    lse_minmax_kernel<<<blocks, 256, 0, st>>>(lse_img_all, lse_txt_all, static_cast<int>(N), minmax);
-    NANS_CUDA_OK(cudaGetLastError());
-  }
+  lse_minmax_kernel<<<1, 1024, 0, st>>>(lse_img_all, lse_txt_all, static_cast<int>(N), minmax);
+  NANS_CUDA_OK(cudaGetLastError());
   float* out32[2];
   if (out_dtype == NANS_F32) {
     NANS_REQUIRE((reinterpret_cast<uintptr_t>(dI_loc) & 15) == 0 && (reinterpret_cast<uintptr_t>(dT_loc) & 15) == 0,

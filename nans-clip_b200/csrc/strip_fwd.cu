@@ -29,6 +29,7 @@ struct FwdParams {
   int nrb, nsplit, ntiles;
   int label_shift;  // label column of row r in phase coordinates = r + label_shift
   int col_global_begin;  // global column of phase column 0
+  int skip_begin, skip_count;  // tiles of the column operand this phase does not sweep
   const float* s_dev;
   float* part_m;
   float* part_l;
@@ -137,6 +138,8 @@ clip_fwd_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
   a.row0 = CP ? rb * 2 * BM + static_cast<int>(blockIdx.x & 1) * BM : rb * BM;
   a.tile_begin = static_cast<int>(static_cast<long long>(split) * p.ntiles / p.nsplit);
   a.tile_end = static_cast<int>(static_cast<long long>(split + 1) * p.ntiles / p.nsplit);
+  a.skip_begin = p.skip_begin;
+  a.skip_count = p.skip_count;
   a.kchunks = p.kchunks;
   a.stages = p.stages;
   a.idesc = p.idesc;
@@ -156,9 +159,12 @@ clip_fwd_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
   const int r = (warp & 3) * 32 + lane;
   float L = (epi.l[0] + epi.l[1]) + (epi.l[2] + epi.l[3]);
   float Wt = (epi.w[0] + epi.w[1]) + (epi.w[2] + epi.w[3]);
-  const int cbeg = a.tile_begin * BN;
-  const int cend = min(a.tile_end * BN, p.ncols);
-  const bool has_diag = epi.label >= cbeg && epi.label < cend;
+  // does this unit sweep the tile that holds the row's label?  (swept index = tile index minus the
+  // skipped tiles before it; tiles inside the skipped range belong to another phase)
+  const int lab_tile = epi.label >= 0 && epi.label < p.ncols ? epi.label / BN : -1;
+  const bool lab_skipped = lab_tile >= a.skip_begin && lab_tile < a.skip_begin + a.skip_count;
+  const int lab_swept = lab_tile < a.skip_begin ? lab_tile : lab_tile - a.skip_count;
+  const bool has_diag = lab_tile >= 0 && !lab_skipped && lab_swept >= a.tile_begin && lab_swept < a.tile_end;
   if (warp >= 8) {
     xm[0 * 128 + r] = epi.m;
     xm[1 * 128 + r] = L;
@@ -175,7 +181,7 @@ clip_fwd_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
     L = L * s1 + xm[1 * 128 + r] * s2;
     Wt = Wt * s1 + xm[2 * 128 + r] * s2;
     // the label column lies in exactly one tile: the set that owns that tile holds cos there
-    const int lab_set = has_diag ? ((epi.label / BN - a.tile_begin) & 1) : 0;
+    const int lab_set = has_diag ? ((lab_swept - a.tile_begin) & 1) : 0;
     const float diag = lab_set == 0 ? epi.diag : xm[3 * 128 + r];
     float bv = epi.bv;
     int bi = epi.bi;
@@ -371,6 +377,7 @@ extern "C" int nans_clip_loss_fwd_phase(const void* I_loc, const void* T_loc, in
                                         const void* T_cols, const void* I_cols, int64_t ld_cols,
                                         int feat_dtype, int64_t n_loc, int64_t ncols, int64_t D,
                                         int64_t col_global_begin, int64_t label_begin,
+                                        int64_t skip_col_begin, int64_t skip_col_count,
                                         const float* s_dev, int flags, void* ws, size_t ws_bytes,
                                         int64_t slot_begin, void* stream) {
   int rc = check_device();
@@ -384,8 +391,12 @@ extern "C" int nans_clip_loss_fwd_phase(const void* I_loc, const void* T_loc, in
   NANS_REQUIRE(I_loc && T_loc && T_cols && I_cols && s_dev && ws, "loss_fwd: null pointer");
   NANS_REQUIRE(ld_loc >= D && ld_cols >= D, "loss_fwd: leading dimension smaller than D");
   NANS_REQUIRE(slot_begin >= 0, "loss_fwd: negative slot");
+  NANS_REQUIRE(skip_col_begin >= 0 && skip_col_count >= 0 && skip_col_begin % BN == 0 &&
+                   skip_col_count % BN == 0 && skip_col_begin + skip_col_count <= ncols,
+               "loss_fwd: the skipped column range must be made of whole 256-column tiles inside the operand");
+  if (skip_col_count == ncols) return NANS_OK;
 
-  const int nsplit = choose_nsplit(n_loc, ncols);
+  const int nsplit = choose_nsplit(n_loc, ncols - skip_col_count);
   // the caller sized the workspace for total_slots >= slot_begin + nsplit
   const size_t need = carve_fwd_ws(nullptr, n_loc, slot_begin + nsplit).bytes;
   if (ws_bytes < need) {
@@ -413,7 +424,9 @@ extern "C" int nans_clip_loss_fwd_phase(const void* I_loc, const void* T_loc, in
   p.idesc = make_idesc(idesc_fmt(feat_dtype), idesc_fmt(feat_dtype), 0, 0, pair ? 2 * BM : BM, BN);
   p.nrb = static_cast<int>(ceil_div(n_loc, pair ? 2 * BM : BM));
   p.nsplit = nsplit;
-  p.ntiles = static_cast<int>(ceil_div(ncols, BN));
+  p.ntiles = static_cast<int>(ceil_div(ncols, BN) - skip_col_count / BN);
+  p.skip_begin = skip_col_count > 0 ? static_cast<int>(skip_col_begin / BN) : (1 << 30);
+  p.skip_count = static_cast<int>(skip_col_count / BN);
   p.label_shift = static_cast<int>(label_begin - col_global_begin);
   p.col_global_begin = static_cast<int>(col_global_begin);
   p.s_dev = s_dev;
@@ -490,7 +503,7 @@ extern "C" int nans_clip_loss_fwd(const void* I_loc, const void* T_loc, int64_t 
                                   size_t ws_bytes, void* stream) {
   NANS_REQUIRE(n_loc > 0 && N > 0, "loss_fwd: empty batch");
   int rc = nans_clip_loss_fwd_phase(I_loc, T_loc, ld_loc, T_all, I_all, ld_all, feat_dtype, n_loc, N,
-                                    D, 0, label_begin, s_dev, flags, ws, ws_bytes, 0, stream);
+                                    D, 0, label_begin, 0, 0, s_dev, flags, ws, ws_bytes, 0, stream);
   if (rc != NANS_OK) return rc;
   const int64_t slots = nans_clip_loss_fwd_phase_slots(n_loc, N, D);
   return nans_clip_loss_fwd_finalize(n_loc, slots, label_begin, s_dev, flags, ws, ws_bytes,

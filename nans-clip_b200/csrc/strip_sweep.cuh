@@ -64,8 +64,10 @@ struct SweepArgs {
   const CUtensorMap* tmA;
   const CUtensorMap* tmB;
   int row0;        // first row of this CTA's block in A
-  int tile_begin;  // column tiles [tile_begin, tile_end) of B
+  int tile_begin;  // column tiles [tile_begin, tile_end) of B, counted WITHOUT the skipped tiles
   int tile_end;
+  int skip_begin;  // tiles [skip_begin, skip_begin + skip_count) of B are not swept (another phase
+  int skip_count;  // covered them): swept index t maps to tile t + (t >= skip_begin ? skip_count : 0)
   int kchunks;     // ceil(D / 64)
   int stages;
   uint32_t idesc;  // M=128 (256 in pair mode), N=256, K-major A and B, fp32 accumulate
@@ -155,7 +157,8 @@ __device__ __forceinline__ uint8_t* run(const SweepArgs& a, Epi& epi) {
     int stage = 0;
     uint32_t phase = 0;
     for (int t = 0; t < ntiles; ++t) {
-      const int col0 = (a.tile_begin + t) * BN + (CP ? static_cast<int>(rank) * (BN / 2) : 0);
+      const int tix = a.tile_begin + t;
+      const int col0 = (tix + (tix >= a.skip_begin ? a.skip_count : 0)) * BN + (CP ? static_cast<int>(rank) * (BN / 2) : 0);
       for (int c = 0; c < a.kchunks; ++c) {
         mbar_wait(&empty[stage], phase ^ 1u);
         if (elect_one()) {
@@ -226,7 +229,8 @@ __device__ __forceinline__ uint8_t* run(const SweepArgs& a, Epi& epi) {
     for (int t = set; t < ntiles; t += 2) {
       mbar_wait(&tfull[set], acc_phase);
       tc_fence_after();
-      epi.tile(tmem_base + lane_base + static_cast<uint32_t>(set * BN), a.tile_begin + t);
+      const int tix = a.tile_begin + t;
+      epi.tile(tmem_base + lane_base + static_cast<uint32_t>(set * BN), tix + (tix >= a.skip_begin ? a.skip_count : 0));
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {

@@ -134,6 +134,8 @@ topk_sweep_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   a.row0 = CP ? qb * 2 * BM + static_cast<int>(blockIdx.x & 1) * BM : qb * BM;
   a.tile_begin = static_cast<int>(static_cast<long long>(split) * p.ntiles / p.nsplit);
   a.tile_end = static_cast<int>(static_cast<long long>(split + 1) * p.ntiles / p.nsplit);
+  a.skip_begin = 1 << 30;
+  a.skip_count = 0;
   a.kchunks = p.kchunks;
   a.stages = p.stages;
   a.idesc = p.idesc;

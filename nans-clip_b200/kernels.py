@@ -103,7 +103,10 @@ def fwd_workspace(n_loc: int, total_slots: int, device) -> torch.Tensor:
 
 
 def fwd_phase(I_loc, T_loc, T_cols, I_cols, *, col_global_begin: int, label_begin: int,
-              s_dev: torch.Tensor, with_acc: bool, ws: torch.Tensor, slot_begin: int) -> None:
+              s_dev: torch.Tensor, with_acc: bool, ws: torch.Tensor, slot_begin: int,
+              skip_begin: int = 0, skip_count: int = 0) -> None:
+    """One phase of the forward column sweep; columns [skip_begin, skip_begin + skip_count) of the
+    operands (multiples of 256) are left to another phase."""
     _require_cuda(I_loc, T_loc, T_cols, I_cols, s_dev, ws)
     n_loc, D = I_loc.shape
     ncols = T_cols.shape[0]
@@ -113,7 +116,7 @@ def fwd_phase(I_loc, T_loc, T_cols, I_cols, *, col_global_begin: int, label_begi
         check(_lib.load().nans_clip_loss_fwd_phase(
             I_loc.data_ptr(), T_loc.data_ptr(), I_loc.stride(0), T_cols.data_ptr(),
             I_cols.data_ptr(), T_cols.stride(0), dtype_code(I_loc.dtype), n_loc, ncols, D,
-            col_global_begin, label_begin, s_dev.data_ptr(),
+            col_global_begin, label_begin, skip_begin, skip_count, s_dev.data_ptr(),
             NANS_LOSS_WITH_ACC if with_acc else 0, ws.data_ptr(), ws.numel(), slot_begin,
             _stream()))
     _count(1)
@@ -121,17 +124,21 @@ def fwd_phase(I_loc, T_loc, T_cols, I_cols, *, col_global_begin: int, label_begi
 
 def fwd_finalize(n_loc: int, total_slots: int, label_begin: int, s_dev: torch.Tensor,
                  with_acc: bool, ws: torch.Tensor):
-    """Returns (lse [2, n_loc] (row 0 image->text, row 1 text->image), scalars [8])."""
-    pad = (n_loc + 3) // 4 * 4  # keeps row 1 16-byte aligned (the backward loads float4)
-    lse = torch.empty((2, pad), dtype=torch.float32, device=ws.device)[:, :n_loc]
-    scalars = torch.empty((8,), dtype=torch.float32, device=ws.device)
+    """Returns (lse2 [2, n_loc] (row 0 image->text, row 1 text->image; base-2 log-sum-exp),
+    scalars [8], packed) — `packed` is the single contiguous buffer [2 * pad + 8] both views live
+    in (pad = n_loc rounded up to 4, keeping row 1 16-byte aligned), so that a multi-rank caller
+    can exchange lse and the partial scalars with ONE all-gather."""
+    pad = (n_loc + 3) // 4 * 4
+    packed = torch.empty((2 * pad + 8,), dtype=torch.float32, device=ws.device)
+    lse = packed[:2 * pad].view(2, pad)[:, :n_loc]
+    scalars = packed[2 * pad:]
     with torch.cuda.device(ws.device):
         check(_lib.load().nans_clip_loss_fwd_finalize(
             n_loc, total_slots, label_begin, s_dev.data_ptr(),
             NANS_LOSS_WITH_ACC if with_acc else 0, ws.data_ptr(), ws.numel(),
             lse[0].data_ptr(), lse[1].data_ptr(), scalars.data_ptr(), _stream()))
     _count(1)
-    return lse, scalars
+    return lse, scalars, packed
 
 
 # --------------------------------------------------------------------------------------------

@@ -45,6 +45,19 @@ def _world(group) -> tuple[int, int]:
     return dist.get_world_size(group), dist.get_rank(group)
 
 
+_COEFS: dict = {}
+
+
+def _scalar_coefs(N: int, dev) -> torch.Tensor:
+    key = (N, str(dev))
+    t = _COEFS.get(key)
+    if t is None:
+        i2n = 1.0 / (2.0 * N)
+        t = torch.tensor([i2n, i2n, i2n, i2n, 1.0 / N, 1.0 / N, 0.0, 0.0], dtype=torch.float32, device=dev)
+        _COEFS[key] = t
+    return t
+
+
 def _as_operand(x: torch.Tensor, dt: torch.dtype) -> torch.Tensor:
     """[n, D] contiguous 16-bit operand; a no-op when x already is one."""
     if x.dtype == dt and x.is_contiguous():
@@ -74,9 +87,10 @@ class _ClipLossFn(torch.autograd.Function):
         label_begin = rank * n_loc
 
         # ---- phases of the column sweep -----------------------------------------------------
+        # a phase = (T columns, I columns, global index of column 0, skipped range (begin, count))
         if W == 1:
             I_all, T_all = I16, T16
-            phases = [(T16, I16, 0)]
+            phases = [(T16, I16, 0, (0, 0))]
             works = []
         else:
             I_all = torch.empty((N, D), dtype=cfg.feat_dtype, device=dev)
@@ -84,41 +98,48 @@ class _ClipLossFn(torch.autograd.Function):
             works = [dist.all_gather_into_tensor(I_all, I16, group=cfg.group, async_op=True),
                      dist.all_gather_into_tensor(T_all, T16, group=cfg.group, async_op=True)]
             lo, hi = rank * n_loc, (rank + 1) * n_loc
-            phases = [(T16, I16, lo)]                       # local block: needs no remote data
-            if lo > 0:
-                phases.append((T_all[:lo], I_all[:lo], 0))
-            if hi < N:
-                phases.append((T_all[hi:], I_all[hi:], hi))
-        slots = [K.fwd_phase_slots(n_loc, tc.shape[0], D) for tc, _, _ in phases]
+            phases = [(T16, I16, lo, (0, 0))]               # local block: needs no remote data
+            if n_loc % 256 == 0:
+                # everything else in ONE launch over the gathered buffers, skipping the local tiles
+                phases.append((T_all, I_all, 0, (lo, n_loc)))
+            else:
+                if lo > 0:
+                    phases.append((T_all[:lo], I_all[:lo], 0, (0, 0)))
+                if hi < N:
+                    phases.append((T_all[hi:], I_all[hi:], hi, (0, 0)))
+        slots = [K.fwd_phase_slots(n_loc, tc.shape[0] - sk[1], D) for tc, _, _, sk in phases]
         ws = K.fwd_workspace(n_loc, sum(slots), dev)
         slot = 0
-        for i, (tc, ic, col0) in enumerate(phases):
+        for i, (tc, ic, col0, sk) in enumerate(phases):
             if i == 1 or (i == 0 and works and not cfg.overlap_gather):
                 for w in works:
                     w.wait()
                 works = []
             K.fwd_phase(I16, T16, tc, ic, col_global_begin=col0, label_begin=label_begin,
-                        s_dev=s_dev, with_acc=cfg.report_acc, ws=ws, slot_begin=slot)
+                        s_dev=s_dev, with_acc=cfg.report_acc, ws=ws, slot_begin=slot,
+                        skip_begin=sk[0], skip_count=sk[1])
             slot += slots[i]
         for w in works:
             w.wait()
-        lse, scalars = K.fwd_finalize(n_loc, slot, label_begin, s_dev, cfg.report_acc, ws)
+        lse, scalars, packed = K.fwd_finalize(n_loc, slot, label_begin, s_dev, cfg.report_acc, ws)
 
-        # ---- the two small exchanges --------------------------------------------------------
+        # ---- one small exchange: per-row lse (for the backward) and the 8 partial scalars -------
         if W > 1:
-            lse_g = torch.empty((W * 2, n_loc), dtype=torch.float32, device=dev)
-            h = dist.all_gather_into_tensor(lse_g, lse.contiguous(), group=cfg.group, async_op=True)
-            dist.all_reduce(scalars, op=dist.ReduceOp.SUM, group=cfg.group)
-            h.wait()
-            lse_all = lse_g.view(W, 2, n_loc).permute(1, 0, 2).reshape(2, N)
+            L = packed.numel()
+            pad = (L - 8) // 2
+            gathered = torch.empty((W, L), dtype=torch.float32, device=dev)
+            dist.all_gather_into_tensor(gathered.view(-1), packed, group=cfg.group)
+            lse_all = gathered[:, :2 * pad].view(W, 2, pad)[:, :, :n_loc].permute(1, 0, 2).reshape(2, N)
+            scalars = gathered[:, 2 * pad:].sum(dim=0)   # == all_reduce(SUM) of the partial sums
         else:
             lse_all = lse
 
-        inv2n = 1.0 / (2.0 * N)
-        loss = (scalars[0] + scalars[1]) * inv2n
-        dscale = (scalars[2] + scalars[3]) * inv2n
-        acc_i2t = scalars[4] / N
-        acc_t2i = scalars[5] / N
+        # loss = (sum_i + sum_j) / 2N (train.py:112-115); d loss / d s likewise; acc = hits / N
+        red = scalars * _scalar_coefs(N, dev)
+        loss = red[0] + red[1]
+        dscale = red[2] + red[3]
+        acc_i2t = red[4]
+        acc_t2i = red[5]
 
         ctx.save_for_backward(I16, T16, I_all, T_all, s_dev, lse_all, dscale)
         ctx.cfg = cfg

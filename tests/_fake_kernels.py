@@ -36,7 +36,10 @@ def fwd_workspace(n_loc, total_slots, device):
     return t
 
 
-def fwd_phase(I_loc, T_loc, T_cols, I_cols, *, col_global_begin, label_begin, s_dev, with_acc, ws, slot_begin):
+def fwd_phase(I_loc, T_loc, T_cols, I_cols, *, col_global_begin, label_begin, s_dev, with_acc, ws, slot_begin,
+              skip_begin=0, skip_count=0):
+    if skip_count:
+        raise NotImplementedError("the CPU stand-in only sees tile-unaligned (3-phase) cases")
     st = STATE[ws.data_ptr()]
     s = float(s_dev)
     n_loc, ncols = I_loc.shape[0], T_cols.shape[0]
@@ -81,7 +84,7 @@ def fwd_finalize(n_loc, total_slots, label_begin, s_dev, with_acc, ws):
         sc[2 + strip] = ((Wt / L).double() - d.double()).sum()
         if with_acc:
             sc[4 + strip] = (arg == torch.arange(n_loc) + label_begin).sum()
-    return lse, sc
+    return lse, sc, torch.cat([lse.reshape(-1), sc])
 
 
 def bwd(I_loc, T_loc, T_all, I_all, *, label_begin, s_dev, lse_all, grad_out, grad_mult, row_begin,

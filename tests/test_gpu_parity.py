@@ -217,7 +217,7 @@ def test_rank_strip_kernels_vs_oracle(dev, W, rank, gwg):
         K.fwd_phase(I16[lo:hi], T16[lo:hi], tc, ic, col_global_begin=c0, label_begin=lo, s_dev=s_dev,
                     with_acc=True, ws=ws, slot_begin=sb)
         sb += ns
-    lse, sc = K.fwd_finalize(n_loc, sb, lo, s_dev, True, ws)
+    lse, sc, _ = K.fwd_finalize(n_loc, sb, lo, s_dev, True, ws)
     torch.cuda.synchronize()
     LN2 = math.log(2.0)  # the kernels carry log-sum-exp in base 2
     assert torch.allclose(lse[0].cpu() * LN2, glob["lse_img"][lo:hi], rtol=1e-5, atol=1e-4)
@@ -227,6 +227,36 @@ def test_rank_strip_kernels_vs_oracle(dev, W, rank, gwg):
                    grad_out=torch.ones(1, device=dev), grad_mult=float(W) if gwg else 1.0, row_begin=0,
                    row_count=n_loc, out_dtype=torch.float32)
     assert relerr(dI.cpu(), want_dI) < TOL and relerr(dT.cpu(), want_dT) < TOL
+
+
+@pytest.mark.parametrize("W,rank", [(4, 0), (4, 2), (3, 2)])
+def test_rank_strip_with_skipped_local_tiles(dev, W, rank):
+    """Tile-aligned local block (n_loc % 256 == 0): loss.py sweeps the gathered buffer in ONE phase
+    that skips the local tiles (they were covered by the local phase)."""
+    from nans_clip_b200 import kernels as K
+    from oracle import clip_loss as OL
+    n_loc, d, s = 256, 128, 25.0
+    I, T = synth(W * n_loc, d, 77 + W, 0.5)
+    glob = OL.global_loss_and_grads(I, T, s)
+    I16, T16 = I.half().to(dev), T.half().to(dev)
+    lo, hi = rank * n_loc, (rank + 1) * n_loc
+    s_dev = torch.tensor([s], device=dev)
+    n_other = W * n_loc - n_loc
+    slots = [K.fwd_phase_slots(n_loc, n_loc, d), K.fwd_phase_slots(n_loc, n_other, d)]
+    ws = K.fwd_workspace(n_loc, sum(slots), dev)
+    K.fwd_phase(I16[lo:hi], T16[lo:hi], T16[lo:hi], I16[lo:hi], col_global_begin=lo, label_begin=lo, s_dev=s_dev,
+                with_acc=True, ws=ws, slot_begin=0)
+    K.fwd_phase(I16[lo:hi], T16[lo:hi], T16, I16, col_global_begin=0, label_begin=lo, s_dev=s_dev,
+                with_acc=True, ws=ws, slot_begin=slots[0], skip_begin=lo, skip_count=n_loc)
+    lse, sc, _ = K.fwd_finalize(n_loc, sum(slots), lo, s_dev, True, ws)
+    LN2 = math.log(2.0)
+    assert torch.allclose(lse[0].cpu() * LN2, glob["lse_img"][lo:hi], rtol=1e-5, atol=1e-4)
+    assert torch.allclose(lse[1].cpu() * LN2, glob["lse_txt"][lo:hi], rtol=1e-5, atol=1e-4)
+    logits = s * I.double() @ T.double().t()
+    want_hits = float((logits[lo:hi].argmax(-1) == torch.arange(lo, hi)).sum())
+    assert abs(float(sc[4]) - want_hits) <= 1.0
+    want0 = float((torch.logsumexp(logits[lo:hi], 1) - logits[lo:hi].diagonal(lo)).sum())
+    assert abs(float(sc[0]) - want0) <= 1e-3 * abs(want0) + 1e-3
 
 
 def test_accumulate_path_rows(dev, golden_dir):
@@ -304,7 +334,7 @@ def test_full_size_properties(dev):
     slots = K.fwd_phase_slots(n, n, d)
     ws = K.fwd_workspace(n, slots, dev)
     K.fwd_phase(I16, T16, T16, I16, col_global_begin=0, label_begin=0, s_dev=s_dev, with_acc=False, ws=ws, slot_begin=0)
-    lse, sc = K.fwd_finalize(n, slots, 0, s_dev, False, ws)
+    lse, sc, _ = K.fwd_finalize(n, slots, 0, s_dev, False, ws)
     rows = torch.arange(0, n, 128, device=dev)  # 256 rows spread over all row blocks
     S = s0 * I[rows] @ T.t()
     lse = lse * math.log(2.0)  # kernels carry base-2 lse

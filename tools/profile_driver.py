@@ -19,7 +19,7 @@ for it in range(3):
     slots = K.fwd_phase_slots(n, n, d)
     ws = K.fwd_workspace(n, slots, dev)
     K.fwd_phase(I16, T16, T16, I16, col_global_begin=0, label_begin=0, s_dev=s_dev, with_acc=False, ws=ws, slot_begin=0)
-    lse, sc = K.fwd_finalize(n, slots, 0, s_dev, False, ws)
+    lse, sc, _ = K.fwd_finalize(n, slots, 0, s_dev, False, ws)
     if which in ("all", "bwd"):
         K.bwd(I16, T16, T16, I16, label_begin=0, s_dev=s_dev, lse_all=lse, grad_out=torch.ones(1, device=dev),
               grad_mult=1.0, row_begin=0, row_count=n, out_dtype=torch.float32)
