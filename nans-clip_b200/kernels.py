@@ -197,7 +197,7 @@ def topk_ip(Q16, G16, Q32, G32, k: int, k_cand: int, gallery_index_offset: int =
                                _ptr(G32), Qn, Gn, D, k, k_cand, gallery_index_offset,
                                scores.data_ptr(), index.data_ptr(), ws.data_ptr(), ws.numel(),
                                _stream()))
-    _count(2 if Gn else 1)
+    _count(0 if not Qn else (1 if not Gn else (3 if Gn >= 3 * 16384 else 2)))  # [pre-pass +] sweep + finalize
     return scores, index
 
 
