@@ -4,14 +4,22 @@
 // query, the k gallery rows with the largest inner product in (score desc, gallery index asc)
 // order — what Python's stable sorted(score_tuples, key=score, reverse=True)[:k] yields.
 //
-// Pass 1 (topk_sweep_kernel): unit = (128-query block, gallery split).  The query block stays in
-//   shared memory; 256-row gallery tiles stream through tcgen05.mma into TMEM (strip_sweep.cuh).
-//   The epilogue thread of a query keeps a sorted k_cand-entry (score, index) list in registers;
-//   a score is compared against the list's current minimum and only the rare winners take the
-//   insertion path.  Lists go to the workspace, one per (split, query).
-// Pass 2 (topk_finalize_kernel): one warp per query merges the splits' lists, keeps the best
-//   k_cand by 16-bit score, recomputes those scores exactly in fp32 from the fp32 copies, and
-//   emits the top k in the reference order.  (16-bit scores alone flip near-ties)
+// All sweeps use the strip_sweep.cuh skeleton (256 queries per CTA pair resident in shared memory,
+// 256-row gallery tiles through tcgen05.mma into TMEM, two epilogue warp sets alternating tiles).
+//
+// Floor pass (topk_floor_kernel, galleries >= 48K rows): over the first 16K gallery rows each
+//   epilogue thread keeps only the k_cand largest 32-column CHUNK MAXIMA of its query (values only,
+//   branch-free insert).  The k_cand-th largest of them over both threads of a query is a lower
+//   bound ("floor") of the query's k_cand-th best score in the shard.  MMA-bound.
+// Main pass (topk_sweep_kernel): unit = (query block, gallery split).  The epilogue thread keeps a
+//   sorted k_cand-entry (score, index) list in registers that only admits scores >= floor; per
+//   32-column chunk one max tree + one compare + one warp vote; on the rare path each lane builds
+//   a bit mask of its qualifying columns and the lanes insert in lockstep.  Lists go to the
+//   workspace, one per (split, tile parity, query).  Without a floor a cold list spends its first
+//   ~16K columns almost entirely on the insertion path (22 % tensor pipe measured).
+// Finalize (topk_finalize_kernel): one warp per query k-way-merges the sorted lists, keeps the best
+//   k_cand by 16-bit score, recomputes those scores exactly in fp32 from the fp32 copies, and emits
+//   the top k in the reference order.  (16-bit scores alone flip near-ties)
 //
 // Roofline: tensor cores, 2*Q*G*D flops; the candidate lists are O(Q * k_cand) bytes.
 #include <limits.h>
