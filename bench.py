@@ -98,7 +98,7 @@ class ClockSampler:
                         self.reasons.add(k)
             except Exception:
                 pass
-            time.sleep(0.02)
+            time.sleep(0.002)
 
     def start(self):
         if self.nv is not None:
@@ -253,8 +253,35 @@ def bench_loss(args):
         step()
     torch.cuda.synchronize()
     launches_per_step = (K.LAUNCHES - l0) // max(args.warmup, 1)
+    run_step = step
+    graphed = False
+    if args.graph and dist is None:  # NCCL collectives inside a captured step hung at 2 GPUs: 1 GPU only
+        # capture one whole step (casts, gathers, fused forward, exchange, fused backward) in a CUDA
+        # graph and replay it: same kernels and collectives, no per-launch host latency
+        try:
+            g = torch.cuda.CUDAGraph()
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    step()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            if dist is not None:
+                dist.barrier()
+            with torch.cuda.graph(g):
+                step()
+            torch.cuda.synchronize()
+            run_step = g.replay
+            graphed = True
+            for _ in range(2):
+                run_step()
+            torch.cuda.synchronize()
+        except Exception as exc:  # fall back to eager launches, say so in the line
+            print(f"[bench] CUDA graph capture failed, timing eager launches: {exc!r}", file=sys.stderr)
+            run_step = step
     sampler.start()
-    total_ms = timed_steps(step, args.steps, 0, flush, dist, dev)
+    total_ms = timed_steps(run_step, args.steps, 0, flush, dist, dev)
     clocks = sampler.stop()
     ms = total_ms / args.steps
     e2e_ms = timed_steps(step_e2e, args.steps, min(args.warmup, 3), flush, dist, dev) / args.steps
@@ -324,6 +351,7 @@ def bench_loss(args):
                        "global_batch": N_GLOBAL, "D": D, "operand_dtype": "fp16 (fp32 accumulate)",
                        "logit_scale": LOGIT_SCALE, "parallelism": f"dp{W}",
                        "l2": "flushed (256 MB write) before every timed step",
+                       "launch": "cuda-graph replay of one captured step" if graphed else "eager",
                        "step_algorithmic_tflop": step_alg / 1e12},
             "algorithmic_tflops": step_alg / (ms / 1e3) / 1e12 ,
             "frac_of_bf16_peak_algorithmic": step_alg / (ms / 1e3) / 1e12 / (W * peaks["bf16_tflops_sustained"]),
@@ -435,6 +463,7 @@ def main():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--workload", choices=["loss", "retrieval"], default="loss")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--graph", action="store_true", help="1 GPU only: time a CUDA-graph replay of the step (value only)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -490,6 +490,25 @@ def test_topk_full_gallery_properties(dev):
 
 
 # --------------------------------------------------------------------------------------------
+# single-CTA fallbacks (NANS_*_1CTA=1): the CTA-pair kernels are the default everywhere above
+# --------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,d,s", [(300, 512, 14.2857), (1111, 768, 50.0), (513, 64, 5.0)])
+def test_single_cta_fallback_kernels(dev, monkeypatch, n, d, s):
+    from nans_clip_b200 import kernels as K
+    from oracle import clip_loss as OL
+    for var in ("NANS_FWD_1CTA", "NANS_BWD_1CTA", "NANS_TOPK_1CTA"):
+        monkeypatch.setenv(var, "1")
+    I, T = synth(n, d, 3 * n + d, 0.5)
+    want = OL.global_loss_and_grads(I, T, s, torch.float64)
+    loss, acc, dI, dT, ds = run_loss(dev, I, T, s)
+    assert abs(float(loss) - float(want["loss"])) <= TOL * abs(float(want["loss"])) + 1e-6 * s
+    assert grad_ok(dI, want["dI"], n, s) and grad_ok(dT, want["dT"], n, s)
+    assert abs(float(ds) - float(want["ds"])) <= TOL * abs(float(want["ds"])) + 1e-6
+    sc, idx = K.topk_ip(I.half().to(dev), T.half().to(dev), I.to(dev), T.to(dev), 10, 16, 0)
+    check_topk(idx.cpu(), sc.cpu(), T, I, 10)
+
+
+# --------------------------------------------------------------------------------------------
 # error behaviour
 # --------------------------------------------------------------------------------------------
 def test_errors_are_loud(dev):
