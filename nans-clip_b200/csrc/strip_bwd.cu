@@ -840,6 +840,349 @@ clip_bwd_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_cons
   }
 }
 
+// ================================================================================================
+// Narrow CTA-pair version (D <= 512): the pair owns 128 rows, 64 per CTA (cta_group::2, M = 128).
+// With 64 rows per CTA the fp32 dA for ALL D <= 512 features takes 256 TMEM columns (the M = 128
+// pair layout puts the two N halves of an accumulator on lanes 0-63 / 64-127), which leaves room for
+// four 64-column S buffers: the logits are recomputed ONCE per tile instead of once per 256-feature
+// slice, and the softmax warps get two tile periods of slack (MMA2 lags MMA1 by two tiles).
+//   TMEM : [0,128) dA features 0-255 | [128,256) dA features 256-511 | [256,512) S buffers 0-3
+//          S / dA rows 0-63 of the CTA sit on lanes 0-63 (first N half) and 64-127 (second N half).
+//   SMEM : A (64 rows, resident) | 3 G buffers (64 rows x 128 K, 16-bit, K-major swizzled: G goes
+//          through shared memory because the TMEM-A form of a pair MMA wants a duplicated layout)
+//          | ring of 32 KB stages: MMA1 = 4 chunks of [64 tile rows x 64 features] of this CTA's
+//          half of the tile; MMA2 = this CTA's 128 features of a 256-feature block, [128 rows x 64] x 2.
+constexpr int NP_ROWS = 64;
+constexpr int NP_ACH = NP_ROWS * BK * 2;      // 8 KB  : one 64-feature chunk of this CTA's A rows
+constexpr int NP_BH = (KT / 2) * BK * 2;      // 8 KB  : this CTA's 64 rows of a tile, one chunk
+constexpr int NP_STAGE = 32 * 1024;
+constexpr int NP_GBUF = NP_ROWS * KT * 2;     // 16 KB
+constexpr int NP_NG = 3;
+constexpr int NP_NS = 4;                      // S buffers
+constexpr int NP_LAG = 2;                     // MMA2 of tile t is issued after MMA1 of tile t + 2
+constexpr int NP_MAXR = 4;
+
+struct NpPlan {
+  int nr;
+  size_t bytes;
+};
+NpPlan plan_np(int kchunks) {
+  NpPlan p;
+  const size_t cap = SMEM_CAP - 1024 - BAR_BYTES;
+  const size_t fixed = static_cast<size_t>(kchunks) * NP_ACH + static_cast<size_t>(NP_NG) * NP_GBUF;
+  p.nr = static_cast<int>((cap - fixed) / NP_STAGE);
+  if (p.nr > NP_MAXR) p.nr = NP_MAXR;
+  p.bytes = fixed + static_cast<size_t>(p.nr) * NP_STAGE + BAR_BYTES + 1024;
+  return p;
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+clip_bwd_np_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmBk0,
+                   const __grid_constant__ CUtensorMap tmBm0, const __grid_constant__ CUtensorMap tmA1,
+                   const __grid_constant__ CUtensorMap tmBk1, const __grid_constant__ CUtensorMap tmBm1,
+                   const BwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* smA = smem;
+  uint8_t* smG = smA + static_cast<size_t>(p.kchunks) * NP_ACH;
+  uint8_t* smR = smG + static_cast<size_t>(NP_NG) * NP_GBUF;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smR + static_cast<size_t>(p.nr) * NP_STAGE);
+  uint64_t* fullR = bars;                 // leader only
+  uint64_t* emptyR = fullR + NP_MAXR;
+  uint64_t* a_full = emptyR + NP_MAXR;    // leader only
+  uint64_t* s_full = a_full + 1;          // [NP_NS]
+  uint64_t* g_ready = s_full + NP_NS;     // [NP_NS] leader only, 16 arrivals
+  uint64_t* g_empty = g_ready + NP_NS;    // [NP_NG]
+  uint64_t* da_full = g_empty + NP_NG;
+  uint64_t* b_full = da_full + 1;         // [2]
+  uint64_t* b_empty = b_full + 2;         // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(b_empty + 2);
+  float* cfbuf = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + CF_OFF);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  int unit = blockIdx.x >> 1;
+  const int split = unit % p.nsplit;
+  unit /= p.nsplit;
+  const int rb = unit % p.nrb;
+  const int strip = unit / p.nrb;
+
+  const CUtensorMap* tmA = strip == 0 ? &tmA0 : &tmA1;     // box [64 rows, 64 features]
+  const CUtensorMap* tmBk = strip == 0 ? &tmBk0 : &tmBk1;  // box [64 rows, 64 features]
+  const CUtensorMap* tmBm = strip == 0 ? &tmBm0 : &tmBm1;  // box [128 rows, 64 features]
+  const int row0 = p.row_begin + rb * 2 * NP_ROWS + static_cast<int>(rank) * NP_ROWS;
+  const int tile_begin = static_cast<int>(static_cast<long long>(split) * p.ntiles / p.nsplit);
+  const int tile_end = static_cast<int>(static_cast<long long>(split + 1) * p.ntiles / p.nsplit);
+  const int ntiles = tile_end - tile_begin;
+  const int n1 = (p.kchunks + 3) / 4;  // MMA1 stages per tile (4 chunks each)
+  const int nfb = (p.kchunks + 3) / 4; // 256-feature blocks of dA = MMA2 stages per tile
+
+  if (warp == 0) {
+    if (elect_one()) {
+      tma_prefetch_desc(tmA);
+      tma_prefetch_desc(tmBk);
+      tma_prefetch_desc(tmBm);
+      for (int i = 0; i < NP_MAXR; ++i) { mbar_init(&fullR[i], 1); mbar_init(&emptyR[i], 1); }
+      mbar_init(a_full, 1);
+      for (int i = 0; i < NP_NS; ++i) { mbar_init(&s_full[i], 1); mbar_init(&g_ready[i], 2 * SM_WARPS); }
+      for (int i = 0; i < NP_NG; ++i) mbar_init(&g_empty[i], 1);
+      mbar_init(da_full, 1);
+      for (int i = 0; i < 2; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], SM_WARPS); }
+      fence_barrier_init();
+    }
+  } else if (warp == 2) {
+    tmem_alloc_pair(tmem_ptr, TMEM_COLS);
+    tmem_relinquish_pair();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  float lse_mu;
+  bool factored;
+  {
+    int lo = __ldg(p.lse_minmax), hi = __ldg(p.lse_minmax + 1);
+    lo = lo >= 0 ? lo : lo ^ 0x7fffffff;
+    hi = hi >= 0 ? hi : hi ^ 0x7fffffff;
+    const float fmin = __int_as_float(lo), fmax = __int_as_float(hi);
+    factored = (fmax - fmin) < kFactorRange;
+    lse_mu = 0.5f * (fmax + fmin);
+  }
+
+  // schedule shared by producer and issuer: step tau: [tau < ntiles] MMA1(tau); [tau >= LAG] MMA2(tau - LAG)
+  if (warp == 0) {
+    if (elect_one()) {
+      if (leader) mbar_arrive_expect_tx(a_full, 2u * static_cast<uint32_t>(p.kchunks) * NP_ACH);
+      for (int c = 0; c < p.kchunks; ++c)
+        tma_load_2d_pair(smA + static_cast<size_t>(c) * NP_ACH, tmA, a_full, c * BK, row0);
+    }
+    __syncwarp();
+    int sr = 0;
+    uint32_t pr = 0;
+    for (int tau = 0; tau < ntiles + NP_LAG; ++tau) {
+      if (tau < ntiles) {
+        const int col0 = (tile_begin + tau) * KT + static_cast<int>(rank) * (KT / 2);
+        for (int j = 0; j < n1; ++j) {
+          const int nck = min(4, p.kchunks - 4 * j);
+          mbar_wait(&emptyR[sr], pr ^ 1u);
+          if (elect_one()) {
+            uint8_t* st = smR + static_cast<size_t>(sr) * NP_STAGE;
+            if (leader) mbar_arrive_expect_tx(&fullR[sr], 2u * static_cast<uint32_t>(nck) * NP_BH);
+            for (int ci = 0; ci < nck; ++ci)
+              tma_load_2d_pair(st + ci * NP_BH, tmBk, &fullR[sr], (4 * j + ci) * BK, col0);
+          }
+          __syncwarp();
+          if (++sr == p.nr) { sr = 0; pr ^= 1u; }
+        }
+      }
+      if (tau >= NP_LAG) {
+        const int col0 = (tile_begin + tau - NP_LAG) * KT;
+        for (int fb = 0; fb < nfb; ++fb) {
+          mbar_wait(&emptyR[sr], pr ^ 1u);
+          if (elect_one()) {
+            uint8_t* st = smR + static_cast<size_t>(sr) * NP_STAGE;
+            if (leader) mbar_arrive_expect_tx(&fullR[sr], 2u * 2u * B_CHUNK);
+            // this CTA's 128 of the block's 256 features: chunks 4 fb + 2 rank, + 1 (zero fill past D)
+            for (int ci = 0; ci < 2; ++ci)
+              tma_load_2d_pair(st + ci * B_CHUNK, tmBm, &fullR[sr], (4 * fb + 2 * static_cast<int>(rank) + ci) * BK, col0);
+          }
+          __syncwarp();
+          if (++sr == p.nr) { sr = 0; pr ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1 && leader) {
+    const uint32_t fmt = p.idesc1_fmt;
+    const uint32_t idesc1 = make_idesc(fmt, fmt, 0, 0, 2 * NP_ROWS, KT);
+    const uint32_t idesc2 = make_idesc(p.g_fmt, fmt, 0, 1, 2 * NP_ROWS, SLICE);
+    const uint32_t smA_addr = smem_u32(smA), smR_addr = smem_u32(smR), smG_addr = smem_u32(smG);
+    mbar_wait(a_full, 0);
+    tc_fence_after();
+    int sr = 0;
+    uint32_t pr = 0;
+    for (int tau = 0; tau < ntiles + NP_LAG; ++tau) {
+      if (tau < ntiles) {
+        const uint32_t d_S = tmem_base + TMEM_S + static_cast<uint32_t>((tau % NP_NS) * (KT / 2));
+        for (int j = 0; j < n1; ++j) {
+          const int nck = min(4, p.kchunks - 4 * j);
+          mbar_wait(&fullR[sr], pr);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint64_t ad0 = make_smem_desc(smA_addr + static_cast<uint32_t>(4 * j) * NP_ACH, 16, 1024);
+            const uint64_t bd0 = make_smem_desc(smR_addr + static_cast<uint32_t>(sr) * NP_STAGE, 16, 1024);
+            for (int ci = 0; ci < nck; ++ci) {
+              const uint64_t ad = ad0 + static_cast<uint64_t>(ci * (NP_ACH >> 4));
+              const uint64_t bd = bd0 + static_cast<uint64_t>(ci * (NP_BH >> 4));
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k)
+                mma_ss_pair(d_S, ad + 2 * k, bd + 2 * k, idesc1, (j | ci | k) != 0 ? 1u : 0u);
+            }
+            tc_commit_pair(&emptyR[sr], 3);
+            if (j == n1 - 1) tc_commit_pair(&s_full[tau % NP_NS], 3);
+          }
+          __syncwarp();
+          if (++sr == p.nr) { sr = 0; pr ^= 1u; }
+        }
+      }
+      if (tau >= NP_LAG) {
+        const int u = tau - NP_LAG;
+        mbar_wait(&g_ready[u % NP_NS], static_cast<uint32_t>(u / NP_NS) & 1u);
+        tc_fence_after();
+        const uint32_t g_addr = smG_addr + static_cast<uint32_t>(u % NP_NG) * NP_GBUF;
+        for (int fb = 0; fb < nfb; ++fb) {
+          mbar_wait(&fullR[sr], pr);
+          tc_fence_after();
+          if (elect_one()) {
+            // A = G from shared memory (K-major, 64 rows per CTA, two 64-wide K chunks of 8 KB)
+            const uint64_t gd0 = make_smem_desc(g_addr, 16, 1024);
+            // B = the tile rows as K, 2 x 64 features of this CTA as MN blocks 16 KB apart
+            const uint64_t bd = make_smem_desc(smR_addr + static_cast<uint32_t>(sr) * NP_STAGE, B_CHUNK, 1024);
+            const uint32_t d_dA = tmem_base + static_cast<uint32_t>(fb * (SLICE / 2));
+#pragma unroll
+            for (int kk = 0; kk < KT / 16; ++kk) {
+              const uint64_t gd = gd0 + static_cast<uint64_t>((kk >> 2) * (NP_ACH >> 4) + (kk & 3) * 2);
+              mma_ss_pair(d_dA, gd, bd + 128 * kk, idesc2, (u > 0 || kk > 0) ? 1u : 0u);
+            }
+            tc_commit_pair(&emptyR[sr], 3);
+            if (fb == nfb - 1) {
+              tc_commit_pair(&g_empty[u % NP_NG], 3);
+              if (u == ntiles - 1) tc_commit_pair(da_full, 3);
+            }
+          }
+          __syncwarp();
+          if (++sr == p.nr) { sr = 0; pr ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 3) {
+    const float* lse_col = p.lse_col[strip];
+    for (int t = 0; t < ntiles; ++t) {
+      const int bb = t & 1;
+      mbar_wait(&b_empty[bb], (static_cast<uint32_t>(t >> 1) & 1u) ^ 1u);
+      const int cb = (tile_begin + t) * KT + lane * 4;
+      float v[4];
+      if (cb + 4 <= p.ncols) {
+        const float4 f = __ldg(reinterpret_cast<const float4*>(lse_col + cb));
+        v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = __ldg(lse_col + max(min(cb + k, p.ncols - 1), 0));
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) v[k] = factored ? fast_exp2(lse_mu - v[k]) : v[k] - kGShiftLog2;
+      *reinterpret_cast<float4*>(cfbuf + bb * KT + lane * 4) = make_float4(v[0], v[1], v[2], v[3]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&b_full[bb]);
+    }
+  } else if (warp >= 4) {
+    // softmax-gradient warps.  Lane group q = warp % 4 sits on TMEM lanes 32q..32q+31:
+    //   row of the CTA = (q & 1) * 32 + lane,  tile columns (q >> 1) * 64 + [0,64) in TMEM columns [0,64);
+    // the two warps of a lane group split those 64 columns (h = 0 / 1 -> 32 columns each).
+    const int q = warp & 3;
+    const int h = (warp - 4) >> 2;
+    const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
+    const int rloc = (q & 1) * 32 + lane;
+    const int row = row0 + rloc;
+    const bool valid = row < p.row_end;
+    const int ctile = (q >> 1) * 64 + h * 32;  // first tile column of this thread
+    const float s = __ldg(p.s_dev);
+    const float c = s * kLog2e;
+    const float lr2 = valid ? __ldg(p.lse_row[strip] + row) - kGShiftLog2 : INFINITY;
+    const float a_i = valid ? fast_exp2(__ldg(p.lse_row[strip] + row) - lse_mu) : 0.f;
+    const int label = row + p.label_shift;
+    const int warp_label_lo = label - lane;
+    const bool g_bf16 = p.g_fmt != 0;
+
+    for (int t = 0; t < ntiles; ++t) {
+      const int sb = t % NP_NS;
+      const int bb = t & 1;
+      const int cb = (tile_begin + t) * KT + ctile;
+      mbar_wait(&b_full[bb], static_cast<uint32_t>(t >> 1) & 1u);
+      mbar_wait(&s_full[sb], static_cast<uint32_t>(t / NP_NS) & 1u);
+      tc_fence_after();
+      const bool has_label = (warp_label_lo < cb + 32) && (warp_label_lo + 31 >= cb);
+      uint32_t r[32];
+      tmem_ld32(tmem_base + lane_base + TMEM_S + sb * (KT / 2) + h * 32, r);
+      tmem_wait_ld();
+      const float* cfs = cfbuf + bb * KT + ctile;
+      const int label_rel = label - cb;
+      uint32_t go[16];
+      if (factored) {
+        if (g_bf16) softmax_grad32_dispatch<true, true>(has_label, r, cfs, c, lr2, a_i, label_rel, go);
+        else softmax_grad32_dispatch<true, false>(has_label, r, cfs, c, lr2, a_i, label_rel, go);
+      } else {
+        if (g_bf16) softmax_grad32_dispatch<false, true>(has_label, r, cfs, c, lr2, a_i, label_rel, go);
+        else softmax_grad32_dispatch<false, false>(has_label, r, cfs, c, lr2, a_i, label_rel, go);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&b_empty[bb]);
+      // G(t) -> shared memory buffer t % 3 once MMA2(t - 3) has drained it
+      const int gbi = t % NP_NG;
+      mbar_wait(&g_empty[gbi], (static_cast<uint32_t>(t / NP_NG) & 1u) ^ 1u);
+      {
+        // K index = tile column: chunk (q >> 1), 16-byte units 4h .. 4h+3 of row rloc, 128-B swizzle
+        uint8_t* grow = smG + static_cast<size_t>(gbi) * NP_GBUF + static_cast<size_t>(q >> 1) * NP_ACH +
+                        static_cast<size_t>(rloc) * 128;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int unit16 = (4 * h + j) ^ (rloc & 7);
+          *reinterpret_cast<uint4*>(grow + unit16 * 16) = make_uint4(go[4 * j], go[4 * j + 1], go[4 * j + 2], go[4 * j + 3]);
+        }
+      }
+      fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core's async proxy
+      tc_fence_before();         // the S reads above are ordered before the hand-over as well
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(&g_ready[sb], 0);
+    }
+
+    // ---- dA: lanes 0-63 hold features [0,128) of each 256-feature block, lanes 64-127 [128,256) ----
+    mbar_wait(da_full, 0);
+    tc_fence_after();
+    const float coef = __ldg(p.grad_out_dev) * s * p.coef_host;
+    float* out = p.out[strip] + static_cast<long long>(row - p.row_begin) * p.D;
+    for (int fb = 0; fb < nfb; ++fb) {
+      for (int ch = h; ch < 4; ch += 2) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + lane_base + fb * (SLICE / 2) + ch * 32, r);
+        tmem_wait_ld();
+        const int f0 = fb * SLICE + (q >> 1) * (SLICE / 2) + ch * 32;
+        if (valid && f0 < p.D) {
+          if (f0 + 32 <= p.D) {
+#pragma unroll
+            for (int k = 0; k < 32; k += 4) {
+              const float a0 = __uint_as_float(r[k]) * coef, a1 = __uint_as_float(r[k + 1]) * coef;
+              const float a2 = __uint_as_float(r[k + 2]) * coef, a3 = __uint_as_float(r[k + 3]) * coef;
+              if (p.accumulate) red_add_v4(out + f0 + k, a0, a1, a2, a3);
+              else *reinterpret_cast<float4*>(out + f0 + k) = make_float4(a0, a1, a2, a3);
+            }
+          } else {
+#pragma unroll
+            for (int k = 0; k < 32; ++k)
+              if (f0 + k < p.D) {
+                if (p.accumulate) atomicAdd(out + f0 + k, __uint_as_float(r[k]) * coef);
+                else out[f0 + k] = __uint_as_float(r[k]) * coef;
+              }
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, TMEM_COLS);
+  }
+}
+
 // min / max over both lse arrays, written as order-preserving ints.  One block (2N floats is at
 // most a few hundred KB): a single launch, no memset, no atomics.
 __global__ void __launch_bounds__(1024) lse_minmax_kernel(const float* __restrict__ a,
@@ -962,10 +1305,19 @@ extern "C" int nans_clip_loss_bwd(const void* I_loc, const void* T_loc, int64_t 
     const char* e = getenv("NANS_BWD_1CTA");
     if (e && e[0] == '1') use_pair = false;
   }
+  // narrow pairs (64 rows per CTA, no S recompute per feature slice) whenever D <= 512;
+  // NANS_BWD_NP=0 falls back to the 128-row pair kernel
+  bool use_np = use_pair && kchunks <= 8;
+  {
+    const char* e = getenv("NANS_BWD_NP");
+    if (e && e[0] == '0') use_np = false;
+  }
   const BwdPlan plan = plan_bwd(kchunks);
   const PairPlan pplan = plan_pair(kchunks);
-  const int nsplit = use_pair ? choose_bwd_nsplit(grad_row_count, N, npass, 2 * BM, sm_count() / 2)
-                              : choose_bwd_nsplit(grad_row_count, N, npass, BM, sm_count());
+  const NpPlan nplan = plan_np(kchunks);
+  const int nsplit = use_np     ? choose_bwd_nsplit(grad_row_count, N, 1, 2 * NP_ROWS, sm_count() / 2)
+                     : use_pair ? choose_bwd_nsplit(grad_row_count, N, npass, 2 * BM, sm_count() / 2)
+                                : choose_bwd_nsplit(grad_row_count, N, npass, BM, sm_count());
   const size_t out_bytes = static_cast<size_t>(grad_row_count) * D * 4;
   // workspace: [0,256) lse min/max slots, then (16-bit outputs only) the two fp32 gradient buffers
   if (ws == nullptr || ws_bytes < 512) {
@@ -1003,6 +1355,9 @@ extern "C" int nans_clip_loss_bwd(const void* I_loc, const void* T_loc, int64_t 
   if ((rc = make_tmap_16b(&tmB1, I_all, feat_dtype, N, D, ld_all, KT)) != NANS_OK) return rc;
   if ((rc = make_tmap_16b(&tmBk0, T_all, feat_dtype, N, D, ld_all, KT / 2)) != NANS_OK) return rc;
   if ((rc = make_tmap_16b(&tmBk1, I_all, feat_dtype, N, D, ld_all, KT / 2)) != NANS_OK) return rc;
+  CUtensorMap tmAn0, tmAn1;  // narrow pairs: 64-row A boxes
+  if ((rc = make_tmap_16b(&tmAn0, I_loc, feat_dtype, n_loc, D, ld_loc, NP_ROWS)) != NANS_OK) return rc;
+  if ((rc = make_tmap_16b(&tmAn1, T_loc, feat_dtype, n_loc, D, ld_loc, NP_ROWS)) != NANS_OK) return rc;
 
   BwdParams p;
   p.row_begin = static_cast<int>(grad_row_begin);
@@ -1010,11 +1365,11 @@ extern "C" int nans_clip_loss_bwd(const void* I_loc, const void* T_loc, int64_t 
   p.ncols = static_cast<int>(N);
   p.D = static_cast<int>(D);
   p.kchunks = kchunks;
-  p.nrb = static_cast<int>(ceil_div(grad_row_count, use_pair ? 2 * BM : BM));
+  p.nrb = static_cast<int>(ceil_div(grad_row_count, use_np ? 2 * NP_ROWS : (use_pair ? 2 * BM : BM)));
   p.npass = npass;
   p.nsplit = nsplit;
   p.ntiles = static_cast<int>(ceil_div(N, KT));
-  p.nr = use_pair ? pplan.nr : plan.nr;
+  p.nr = use_np ? nplan.nr : (use_pair ? pplan.nr : plan.nr);
   p.idesc1_fmt = static_cast<uint32_t>(idesc_fmt(feat_dtype));
   // tcgen05.mma kind::f16 wants A and B in the same 16-bit format (a mixed f16 x bf16 descriptor
   // faults as an illegal instruction on sm_100a), so G is written in the features' format.
@@ -1040,7 +1395,12 @@ extern "C" int nans_clip_loss_bwd(const void* I_loc, const void* T_loc, int64_t 
     p.debug = e ? atoi(e) : 0;
   }
 
-  if (use_pair) {
+  if (use_np) {
+    NANS_CUDA_OK(cudaFuncSetAttribute(clip_bwd_np_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(nplan.bytes)));
+    const unsigned grid = static_cast<unsigned>(2 * 2 * p.nrb * p.nsplit);
+    clip_bwd_np_kernel<<<grid, NUM_THREADS, nplan.bytes, st>>>(tmAn0, tmBk0, tmB0, tmAn1, tmBk1, tmB1, p);
+  } else if (use_pair) {
     auto kern = pplan.a_resident ? clip_bwd_pair_kernel<true> : clip_bwd_pair_kernel<false>;
     NANS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       static_cast<int>(pplan.bytes)));

@@ -508,6 +508,20 @@ def test_single_cta_fallback_kernels(dev, monkeypatch, n, d, s):
     check_topk(idx.cpu(), sc.cpu(), T, I, 10)
 
 
+@pytest.mark.parametrize("n,d,s,dt", [(300, 512, 14.2857, torch.float16), (1000, 256, 100.0, torch.float16),
+                                      (2050, 448, 30.0, torch.bfloat16), (513, 64, 5.0, torch.float16)])
+def test_wide_pair_backward_fallback(dev, monkeypatch, n, d, s, dt):
+    """NANS_BWD_NP=0: the 128-row CTA-pair backward (the D > 512 kernel) on D <= 512 shapes; the
+    default there is the 64-row pair kernel, covered by every other test."""
+    from oracle import clip_loss as OL
+    monkeypatch.setenv("NANS_BWD_NP", "0")
+    I, T = synth(n, d, 5 * n + d, 0.5)
+    want = OL.global_loss_and_grads(I, T, s, torch.float64)
+    loss, acc, dI, dT, ds = run_loss(dev, I, T, s, dt=dt)
+    tol = TOL if dt == torch.float16 else 3e-3
+    assert grad_ok(dI, want["dI"], n, s, tol) and grad_ok(dT, want["dT"], n, s, tol)
+
+
 # --------------------------------------------------------------------------------------------
 # error behaviour
 # --------------------------------------------------------------------------------------------
