@@ -844,23 +844,27 @@ clip_bwd_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_cons
 // Narrow CTA-pair version (D <= 512): the pair owns 128 rows, 64 per CTA (cta_group::2, M = 128).
 // With 64 rows per CTA the fp32 dA for ALL D <= 512 features takes 256 TMEM columns (the M = 128
 // pair layout puts the two N halves of an accumulator on lanes 0-63 / 64-127), which leaves room for
-// four 64-column S buffers: the logits are recomputed ONCE per tile instead of once per 256-feature
-// slice, and the softmax warps get two tile periods of slack (MMA2 lags MMA1 by two tiles).
-//   TMEM : [0,128) dA features 0-255 | [128,256) dA features 256-511 | [256,512) S buffers 0-3
+// two S buffers of a 256-column tile: the logits are recomputed ONCE per tile instead of once per
+// 256-feature slice.  The kernel is bound by the shared-memory data pipe (tensor-core operand reads
+// + the softmax warps' TMEM / shared traffic, ncu: 98 % with 128-column tiles), so MMA1 uses the
+// widest N (256: A is re-read once per 256 columns) and the softmax warps use ld/st.shared.
+//   TMEM : [0,128) dA features 0-255 | [128,256) dA features 256-511 | [256,512) S buffers 0-1
 //          S / dA rows 0-63 of the CTA sit on lanes 0-63 (first N half) and 64-127 (second N half).
-//   SMEM : A (64 rows, resident) | 3 G buffers (64 rows x 128 K, 16-bit, K-major swizzled: G goes
+//   SMEM : A (64 rows, resident) | 2 G buffers (64 rows x 256 K, 16-bit, K-major swizzled: G goes
 //          through shared memory because the TMEM-A form of a pair MMA wants a duplicated layout)
-//          | ring of 32 KB stages: MMA1 = 4 chunks of [64 tile rows x 64 features] of this CTA's
-//          half of the tile; MMA2 = this CTA's 128 features of a 256-feature block, [128 rows x 64] x 2.
+//          | ring of 32 KB stages: MMA1 = 2 chunks of [128 tile rows x 64 features] of this CTA's
+//          half of the tile; MMA2 = [128 tile rows x 64 features] x 2 of this CTA's 128 features of
+//          a 256-feature block.  MMA2 of tile t is issued after MMA1 of tile t + 1.
 constexpr int NP_ROWS = 64;
-constexpr int NP_ACH = NP_ROWS * BK * 2;      // 8 KB  : one 64-feature chunk of this CTA's A rows
-constexpr int NP_BH = (KT / 2) * BK * 2;      // 8 KB  : this CTA's 64 rows of a tile, one chunk
-constexpr int NP_STAGE = 32 * 1024;
-constexpr int NP_GBUF = NP_ROWS * KT * 2;     // 16 KB
-constexpr int NP_NG = 3;
-constexpr int NP_NS = 4;                      // S buffers
-constexpr int NP_LAG = 2;                     // MMA2 of tile t is issued after MMA1 of tile t + 2
+constexpr int NP_KT = 256;
+constexpr int NP_ACH = NP_ROWS * BK * 2;      // 8 KB  : one 64-feature chunk of this CTA's A rows / of G
+constexpr int NP_STAGE = 2 * B_CHUNK;         // 32 KB
+constexpr int NP_GBUF = NP_ROWS * NP_KT * 2;  // 32 KB
+constexpr int NP_NG = 2;
+constexpr int NP_NS = 2;                      // S buffers (128 TMEM columns each)
 constexpr int NP_MAXR = 4;
+constexpr int NP_BAR_BYTES = 2560;            // mbarriers + TMEM pointer (256 B) + two 256-float column-factor buffers
+constexpr int NP_CF_OFF = 256;
 
 struct NpPlan {
   int nr;
@@ -868,18 +872,69 @@ struct NpPlan {
 };
 NpPlan plan_np(int kchunks) {
   NpPlan p;
-  const size_t cap = SMEM_CAP - 1024 - BAR_BYTES;
-  const size_t fixed = static_cast<size_t>(kchunks) * NP_ACH + static_cast<size_t>(NP_NG) * NP_GBUF;
-  p.nr = static_cast<int>((cap - fixed) / NP_STAGE);
+  const size_t fixed = static_cast<size_t>(kchunks) * NP_ACH + static_cast<size_t>(NP_NG) * NP_GBUF + NP_BAR_BYTES;
+  // the 1 KB of alignment slack is dropped when it would cost a ring stage (D = 512): the kernel
+  // checks that its aligned carve-up fits and traps otherwise
+  size_t pad = 1024;
+  p.nr = static_cast<int>((SMEM_CAP - pad - fixed) / NP_STAGE);
+  if (p.nr < 3 && (SMEM_CAP - fixed) / NP_STAGE >= 3) {
+    p.nr = 3;
+    pad = SMEM_CAP - fixed - 3 * static_cast<size_t>(NP_STAGE);
+  }
   if (p.nr > NP_MAXR) p.nr = NP_MAXR;
-  p.bytes = fixed + static_cast<size_t>(p.nr) * NP_STAGE + BAR_BYTES + 1024;
+  p.bytes = fixed + static_cast<size_t>(p.nr) * NP_STAGE + pad;
   return p;
 }
 
+__device__ __forceinline__ float4 lds_v4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+// softmax_grad32 with the column factors read through ld.shared (one wavefront per broadcast load)
+template <bool FACTORED, bool BF16, bool LABEL>
+__device__ __forceinline__ void np_grad32(const uint32_t (&r)[32], uint32_t cf_addr, float c, float lr2,
+                                          float a_i, int label_rel, uint32_t* __restrict__ g16) {
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const float4 f = lds_v4(cf_addr + 16 * q);
+    const float cfv[4] = {f.x, f.y, f.z, f.w};
+    float g[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float cosv = __uint_as_float(r[4 * q + e]);
+      const float e1 = fast_exp2(fmaf(cosv, c, -lr2));
+      if (FACTORED) g[e] = e1 * fmaf(a_i, cfv[e], 1.0f);
+      else g[e] = e1 + fast_exp2(fmaf(cosv, c, -cfv[e]));
+      if (LABEL) g[e] = (4 * q + e == label_rel) ? g[e] - 8192.0f : g[e];  // 2 * 2^12
+    }
+#pragma unroll
+    for (int e = 0; e < 4; e += 2) {
+      if (BF16) {
+        const __nv_bfloat162 hh = __floats2bfloat162_rn(g[e], g[e + 1]);
+        g16[2 * q + (e >> 1)] = *reinterpret_cast<const uint32_t*>(&hh);
+      } else {
+        const __half2 hh = __floats2half2_rn(g[e], g[e + 1]);
+        g16[2 * q + (e >> 1)] = *reinterpret_cast<const uint32_t*>(&hh);
+      }
+    }
+  }
+}
+template <bool FACTORED, bool BF16>
+__device__ __forceinline__ void np_grad32_dispatch(bool has_label, const uint32_t (&r)[32], uint32_t cf_addr,
+                                                   float c, float lr2, float a_i, int label_rel,
+                                                   uint32_t* __restrict__ g16) {
+  if (has_label) np_grad32<FACTORED, BF16, true>(r, cf_addr, c, lr2, a_i, label_rel, g16);
+  else np_grad32<FACTORED, BF16, false>(r, cf_addr, c, lr2, a_i, label_rel, g16);
+}
+
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
-clip_bwd_np_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmBk0,
-                   const __grid_constant__ CUtensorMap tmBm0, const __grid_constant__ CUtensorMap tmA1,
-                   const __grid_constant__ CUtensorMap tmBk1, const __grid_constant__ CUtensorMap tmBm1,
+clip_bwd_np_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmBm0,
+                   const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmBm1,
                    const BwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(
@@ -888,6 +943,11 @@ clip_bwd_np_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
   uint8_t* smG = smA + static_cast<size_t>(p.kchunks) * NP_ACH;
   uint8_t* smR = smG + static_cast<size_t>(NP_NG) * NP_GBUF;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smR + static_cast<size_t>(p.nr) * NP_STAGE);
+  {
+    uint32_t dyn;
+    asm volatile("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn));
+    if (reinterpret_cast<uint8_t*>(bars) + NP_BAR_BYTES > smem_raw + dyn) __trap();  // carve-up does not fit
+  }
   uint64_t* fullR = bars;                 // leader only
   uint64_t* emptyR = fullR + NP_MAXR;
   uint64_t* a_full = emptyR + NP_MAXR;    // leader only
@@ -898,7 +958,7 @@ clip_bwd_np_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
   uint64_t* b_full = da_full + 1;         // [2]
   uint64_t* b_empty = b_full + 2;         // [2]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(b_empty + 2);
-  float* cfbuf = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + CF_OFF);
+  float* cfbuf = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + NP_CF_OFF);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -912,19 +972,17 @@ clip_bwd_np_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
   const int strip = unit / p.nrb;
 
   const CUtensorMap* tmA = strip == 0 ? &tmA0 : &tmA1;     // box [64 rows, 64 features]
-  const CUtensorMap* tmBk = strip == 0 ? &tmBk0 : &tmBk1;  // box [64 rows, 64 features]
   const CUtensorMap* tmBm = strip == 0 ? &tmBm0 : &tmBm1;  // box [128 rows, 64 features]
   const int row0 = p.row_begin + rb * 2 * NP_ROWS + static_cast<int>(rank) * NP_ROWS;
   const int tile_begin = static_cast<int>(static_cast<long long>(split) * p.ntiles / p.nsplit);
   const int tile_end = static_cast<int>(static_cast<long long>(split + 1) * p.ntiles / p.nsplit);
   const int ntiles = tile_end - tile_begin;
-  const int n1 = (p.kchunks + 3) / 4;  // MMA1 stages per tile (4 chunks each)
-  const int nfb = (p.kchunks + 3) / 4; // 256-feature blocks of dA = MMA2 stages per tile
+  const int n1 = (p.kchunks + 1) / 2;  // MMA1 stages per tile (2 chunks each)
+  const int nfb = (p.kchunks + 3) / 4; // 256-feature blocks of dA; MMA2 stages per tile = 2 nfb
 
   if (warp == 0) {
     if (elect_one()) {
       tma_prefetch_desc(tmA);
-      tma_prefetch_desc(tmBk);
       tma_prefetch_desc(tmBm);
       for (int i = 0; i < NP_MAXR; ++i) { mbar_init(&fullR[i], 1); mbar_init(&emptyR[i], 1); }
       mbar_init(a_full, 1);
@@ -955,7 +1013,7 @@ clip_bwd_np_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
     lse_mu = 0.5f * (fmax + fmin);
   }
 
-  // schedule shared by producer and issuer: step tau: [tau < ntiles] MMA1(tau); [tau >= LAG] MMA2(tau - LAG)
+  // schedule shared by producer and issuer: step tau: [tau < ntiles] MMA1(tau); [tau >= 1] MMA2(tau - 1)
   if (warp == 0) {
     if (elect_one()) {
       if (leader) mbar_arrive_expect_tx(a_full, 2u * static_cast<uint32_t>(p.kchunks) * NP_ACH);
@@ -965,60 +1023,63 @@ clip_bwd_np_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
     __syncwarp();
     int sr = 0;
     uint32_t pr = 0;
-    for (int tau = 0; tau < ntiles + NP_LAG; ++tau) {
+    for (int tau = 0; tau <= ntiles; ++tau) {
       if (tau < ntiles) {
-        const int col0 = (tile_begin + tau) * KT + static_cast<int>(rank) * (KT / 2);
+        const int col0 = (tile_begin + tau) * NP_KT + static_cast<int>(rank) * (NP_KT / 2);
         for (int j = 0; j < n1; ++j) {
-          const int nck = min(4, p.kchunks - 4 * j);
-          mbar_wait(&emptyR[sr], pr ^ 1u);
+          const int nck = min(2, p.kchunks - 2 * j);
+          mbar_wait_parked(&emptyR[sr], pr ^ 1u);
           if (elect_one()) {
             uint8_t* st = smR + static_cast<size_t>(sr) * NP_STAGE;
-            if (leader) mbar_arrive_expect_tx(&fullR[sr], 2u * static_cast<uint32_t>(nck) * NP_BH);
+            if (leader) mbar_arrive_expect_tx(&fullR[sr], 2u * static_cast<uint32_t>(nck) * B_CHUNK);
             for (int ci = 0; ci < nck; ++ci)
-              tma_load_2d_pair(st + ci * NP_BH, tmBk, &fullR[sr], (4 * j + ci) * BK, col0);
+              tma_load_2d_pair(st + ci * B_CHUNK, tmBm, &fullR[sr], (2 * j + ci) * BK, col0);
           }
           __syncwarp();
           if (++sr == p.nr) { sr = 0; pr ^= 1u; }
         }
       }
-      if (tau >= NP_LAG) {
-        const int col0 = (tile_begin + tau - NP_LAG) * KT;
-        for (int fb = 0; fb < nfb; ++fb) {
-          mbar_wait(&emptyR[sr], pr ^ 1u);
-          if (elect_one()) {
-            uint8_t* st = smR + static_cast<size_t>(sr) * NP_STAGE;
-            if (leader) mbar_arrive_expect_tx(&fullR[sr], 2u * 2u * B_CHUNK);
-            // this CTA's 128 of the block's 256 features: chunks 4 fb + 2 rank, + 1 (zero fill past D)
-            for (int ci = 0; ci < 2; ++ci)
-              tma_load_2d_pair(st + ci * B_CHUNK, tmBm, &fullR[sr], (4 * fb + 2 * static_cast<int>(rank) + ci) * BK, col0);
+      if (tau >= 1) {
+        const int col0 = (tile_begin + tau - 1) * NP_KT;
+        for (int kh = 0; kh < 2; ++kh) {
+          for (int fb = 0; fb < nfb; ++fb) {
+            mbar_wait_parked(&emptyR[sr], pr ^ 1u);
+            if (elect_one()) {
+              uint8_t* st = smR + static_cast<size_t>(sr) * NP_STAGE;
+              if (leader) mbar_arrive_expect_tx(&fullR[sr], 2u * 2u * B_CHUNK);
+              // this CTA's 128 of the block's 256 features: chunks 4 fb + 2 rank, + 1 (zero fill past D)
+              for (int ci = 0; ci < 2; ++ci)
+                tma_load_2d_pair(st + ci * B_CHUNK, tmBm, &fullR[sr],
+                                 (4 * fb + 2 * static_cast<int>(rank) + ci) * BK, col0 + kh * (NP_KT / 2));
+            }
+            __syncwarp();
+            if (++sr == p.nr) { sr = 0; pr ^= 1u; }
           }
-          __syncwarp();
-          if (++sr == p.nr) { sr = 0; pr ^= 1u; }
         }
       }
     }
   } else if (warp == 1 && leader) {
     const uint32_t fmt = p.idesc1_fmt;
-    const uint32_t idesc1 = make_idesc(fmt, fmt, 0, 0, 2 * NP_ROWS, KT);
+    const uint32_t idesc1 = make_idesc(fmt, fmt, 0, 0, 2 * NP_ROWS, NP_KT);
     const uint32_t idesc2 = make_idesc(p.g_fmt, fmt, 0, 1, 2 * NP_ROWS, SLICE);
     const uint32_t smA_addr = smem_u32(smA), smR_addr = smem_u32(smR), smG_addr = smem_u32(smG);
     mbar_wait(a_full, 0);
     tc_fence_after();
     int sr = 0;
     uint32_t pr = 0;
-    for (int tau = 0; tau < ntiles + NP_LAG; ++tau) {
+    for (int tau = 0; tau <= ntiles; ++tau) {
       if (tau < ntiles) {
-        const uint32_t d_S = tmem_base + TMEM_S + static_cast<uint32_t>((tau % NP_NS) * (KT / 2));
+        const uint32_t d_S = tmem_base + TMEM_S + static_cast<uint32_t>((tau % NP_NS) * (NP_KT / 2));
         for (int j = 0; j < n1; ++j) {
-          const int nck = min(4, p.kchunks - 4 * j);
+          const int nck = min(2, p.kchunks - 2 * j);
           mbar_wait(&fullR[sr], pr);
           tc_fence_after();
           if (elect_one()) {
-            const uint64_t ad0 = make_smem_desc(smA_addr + static_cast<uint32_t>(4 * j) * NP_ACH, 16, 1024);
+            const uint64_t ad0 = make_smem_desc(smA_addr + static_cast<uint32_t>(2 * j) * NP_ACH, 16, 1024);
             const uint64_t bd0 = make_smem_desc(smR_addr + static_cast<uint32_t>(sr) * NP_STAGE, 16, 1024);
             for (int ci = 0; ci < nck; ++ci) {
               const uint64_t ad = ad0 + static_cast<uint64_t>(ci * (NP_ACH >> 4));
-              const uint64_t bd = bd0 + static_cast<uint64_t>(ci * (NP_BH >> 4));
+              const uint64_t bd = bd0 + static_cast<uint64_t>(ci * (B_CHUNK >> 4));
 #pragma unroll
               for (int k = 0; k < BK / 16; ++k)
                 mma_ss_pair(d_S, ad + 2 * k, bd + 2 * k, idesc1, (j | ci | k) != 0 ? 1u : 0u);
@@ -1030,33 +1091,35 @@ clip_bwd_np_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
           if (++sr == p.nr) { sr = 0; pr ^= 1u; }
         }
       }
-      if (tau >= NP_LAG) {
-        const int u = tau - NP_LAG;
+      if (tau >= 1) {
+        const int u = tau - 1;
         mbar_wait(&g_ready[u % NP_NS], static_cast<uint32_t>(u / NP_NS) & 1u);
         tc_fence_after();
         const uint32_t g_addr = smG_addr + static_cast<uint32_t>(u % NP_NG) * NP_GBUF;
-        for (int fb = 0; fb < nfb; ++fb) {
-          mbar_wait(&fullR[sr], pr);
-          tc_fence_after();
-          if (elect_one()) {
-            // A = G from shared memory (K-major, 64 rows per CTA, two 64-wide K chunks of 8 KB)
-            const uint64_t gd0 = make_smem_desc(g_addr, 16, 1024);
-            // B = the tile rows as K, 2 x 64 features of this CTA as MN blocks 16 KB apart
-            const uint64_t bd = make_smem_desc(smR_addr + static_cast<uint32_t>(sr) * NP_STAGE, B_CHUNK, 1024);
-            const uint32_t d_dA = tmem_base + static_cast<uint32_t>(fb * (SLICE / 2));
+        for (int kh = 0; kh < 2; ++kh) {
+          for (int fb = 0; fb < nfb; ++fb) {
+            mbar_wait(&fullR[sr], pr);
+            tc_fence_after();
+            if (elect_one()) {
+              // A = G from shared memory (K-major, 64 rows per CTA, 64-wide K chunks of 8 KB)
+              const uint64_t gd0 = make_smem_desc(g_addr + static_cast<uint32_t>(2 * kh) * NP_ACH, 16, 1024);
+              // B = 128 tile rows as K, 2 x 64 features of this CTA as MN blocks 16 KB apart
+              const uint64_t bd = make_smem_desc(smR_addr + static_cast<uint32_t>(sr) * NP_STAGE, B_CHUNK, 1024);
+              const uint32_t d_dA = tmem_base + static_cast<uint32_t>(fb * (SLICE / 2));
 #pragma unroll
-            for (int kk = 0; kk < KT / 16; ++kk) {
-              const uint64_t gd = gd0 + static_cast<uint64_t>((kk >> 2) * (NP_ACH >> 4) + (kk & 3) * 2);
-              mma_ss_pair(d_dA, gd, bd + 128 * kk, idesc2, (u > 0 || kk > 0) ? 1u : 0u);
+              for (int kk = 0; kk < 8; ++kk) {
+                const uint64_t gd = gd0 + static_cast<uint64_t>((kk >> 2) * (NP_ACH >> 4) + (kk & 3) * 2);
+                mma_ss_pair(d_dA, gd, bd + 128 * kk, idesc2, (u > 0 || kh > 0 || kk > 0) ? 1u : 0u);
+              }
+              tc_commit_pair(&emptyR[sr], 3);
+              if (kh == 1 && fb == nfb - 1) {
+                tc_commit_pair(&g_empty[u % NP_NG], 3);
+                if (u == ntiles - 1) tc_commit_pair(da_full, 3);
+              }
             }
-            tc_commit_pair(&emptyR[sr], 3);
-            if (fb == nfb - 1) {
-              tc_commit_pair(&g_empty[u % NP_NG], 3);
-              if (u == ntiles - 1) tc_commit_pair(da_full, 3);
-            }
+            __syncwarp();
+            if (++sr == p.nr) { sr = 0; pr ^= 1u; }
           }
-          __syncwarp();
-          if (++sr == p.nr) { sr = 0; pr ^= 1u; }
         }
       }
     }
@@ -1064,33 +1127,37 @@ clip_bwd_np_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
     const float* lse_col = p.lse_col[strip];
     for (int t = 0; t < ntiles; ++t) {
       const int bb = t & 1;
-      mbar_wait(&b_empty[bb], (static_cast<uint32_t>(t >> 1) & 1u) ^ 1u);
-      const int cb = (tile_begin + t) * KT + lane * 4;
-      float v[4];
-      if (cb + 4 <= p.ncols) {
-        const float4 f = __ldg(reinterpret_cast<const float4*>(lse_col + cb));
-        v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
-      } else {
+      mbar_wait_parked(&b_empty[bb], (static_cast<uint32_t>(t >> 1) & 1u) ^ 1u);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) v[k] = __ldg(lse_col + max(min(cb + k, p.ncols - 1), 0));
+      for (int hh = 0; hh < 2; ++hh) {
+        const int cb = (tile_begin + t) * NP_KT + hh * 128 + lane * 4;
+        float v[4];
+        if (cb + 4 <= p.ncols) {
+          const float4 f = __ldg(reinterpret_cast<const float4*>(lse_col + cb));
+          v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
+        } else {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) v[k] = __ldg(lse_col + max(min(cb + k, p.ncols - 1), 0));
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = factored ? fast_exp2(lse_mu - v[k]) : v[k] - kGShiftLog2;
+        *reinterpret_cast<float4*>(cfbuf + bb * NP_KT + hh * 128 + lane * 4) = make_float4(v[0], v[1], v[2], v[3]);
       }
-#pragma unroll
-      for (int k = 0; k < 4; ++k) v[k] = factored ? fast_exp2(lse_mu - v[k]) : v[k] - kGShiftLog2;
-      *reinterpret_cast<float4*>(cfbuf + bb * KT + lane * 4) = make_float4(v[0], v[1], v[2], v[3]);
       __syncwarp();
       if (lane == 0) mbar_arrive(&b_full[bb]);
     }
   } else if (warp >= 4) {
     // softmax-gradient warps.  Lane group q = warp % 4 sits on TMEM lanes 32q..32q+31:
-    //   row of the CTA = (q & 1) * 32 + lane,  tile columns (q >> 1) * 64 + [0,64) in TMEM columns [0,64);
-    // the two warps of a lane group split those 64 columns (h = 0 / 1 -> 32 columns each).
+    //   row of the CTA = (q & 1) * 32 + lane,  tile columns (q >> 1) * 128 + [0,128) in TMEM columns [0,128);
+    // the two warps of a lane group split those 128 columns (h = 0 / 1 -> 64 columns each = one
+    // 64-wide K chunk of G: the thread writes one whole swizzled 128-byte row of that chunk).
     const int q = warp & 3;
     const int h = (warp - 4) >> 2;
     const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
     const int rloc = (q & 1) * 32 + lane;
     const int row = row0 + rloc;
     const bool valid = row < p.row_end;
-    const int ctile = (q >> 1) * 64 + h * 32;  // first tile column of this thread
+    const int ctile = (q >> 1) * 128 + h * 64;  // first tile column of this thread
     const float s = __ldg(p.s_dev);
     const float c = s * kLog2e;
     const float lr2 = valid ? __ldg(p.lse_row[strip] + row) - kGShiftLog2 : INFINITY;
@@ -1098,42 +1165,45 @@ clip_bwd_np_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
     const int label = row + p.label_shift;
     const int warp_label_lo = label - lane;
     const bool g_bf16 = p.g_fmt != 0;
+    const uint32_t cf_addr0 = smem_u32(cfbuf) + static_cast<uint32_t>(ctile) * 4;
+    const uint32_t g_row_addr = smem_u32(smG) + static_cast<uint32_t>((q >> 1) * 2 + h) * NP_ACH +
+                                static_cast<uint32_t>(rloc) * 128;
 
     for (int t = 0; t < ntiles; ++t) {
       const int sb = t % NP_NS;
       const int bb = t & 1;
-      const int cb = (tile_begin + t) * KT + ctile;
-      mbar_wait(&b_full[bb], static_cast<uint32_t>(t >> 1) & 1u);
-      mbar_wait(&s_full[sb], static_cast<uint32_t>(t / NP_NS) & 1u);
+      const int cb = (tile_begin + t) * NP_KT + ctile;
+      mbar_wait_parked(&b_full[bb], static_cast<uint32_t>(t >> 1) & 1u);
+      mbar_wait_parked(&s_full[sb], static_cast<uint32_t>(t / NP_NS) & 1u);
       tc_fence_after();
-      const bool has_label = (warp_label_lo < cb + 32) && (warp_label_lo + 31 >= cb);
-      uint32_t r[32];
-      tmem_ld32(tmem_base + lane_base + TMEM_S + sb * (KT / 2) + h * 32, r);
-      tmem_wait_ld();
-      const float* cfs = cfbuf + bb * KT + ctile;
-      const int label_rel = label - cb;
-      uint32_t go[16];
-      if (factored) {
-        if (g_bf16) softmax_grad32_dispatch<true, true>(has_label, r, cfs, c, lr2, a_i, label_rel, go);
-        else softmax_grad32_dispatch<true, false>(has_label, r, cfs, c, lr2, a_i, label_rel, go);
-      } else {
-        if (g_bf16) softmax_grad32_dispatch<false, true>(has_label, r, cfs, c, lr2, a_i, label_rel, go);
-        else softmax_grad32_dispatch<false, false>(has_label, r, cfs, c, lr2, a_i, label_rel, go);
+      uint32_t go[32];
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        const int cbh = cb + 32 * hf;
+        const bool has_label = (warp_label_lo < cbh + 32) && (warp_label_lo + 31 >= cbh);
+        uint32_t r[32];
+        tmem_ld32(tmem_base + lane_base + TMEM_S + sb * (NP_KT / 2) + h * 64 + hf * 32, r);
+        tmem_wait_ld();
+        const uint32_t cfa = cf_addr0 + static_cast<uint32_t>(bb * NP_KT + 32 * hf) * 4;
+        const int label_rel = label - cbh;
+        if (factored) {
+          if (g_bf16) np_grad32_dispatch<true, true>(has_label, r, cfa, c, lr2, a_i, label_rel, go + 16 * hf);
+          else np_grad32_dispatch<true, false>(has_label, r, cfa, c, lr2, a_i, label_rel, go + 16 * hf);
+        } else {
+          if (g_bf16) np_grad32_dispatch<false, true>(has_label, r, cfa, c, lr2, a_i, label_rel, go + 16 * hf);
+          else np_grad32_dispatch<false, false>(has_label, r, cfa, c, lr2, a_i, label_rel, go + 16 * hf);
+        }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&b_empty[bb]);
-      // G(t) -> shared memory buffer t % 3 once MMA2(t - 3) has drained it
+      // G(t) -> shared memory buffer t % 2 once MMA2(t - 2) has drained it
       const int gbi = t % NP_NG;
-      mbar_wait(&g_empty[gbi], (static_cast<uint32_t>(t / NP_NG) & 1u) ^ 1u);
+      mbar_wait_parked(&g_empty[gbi], (static_cast<uint32_t>(t / NP_NG) & 1u) ^ 1u);
       {
-        // K index = tile column: chunk (q >> 1), 16-byte units 4h .. 4h+3 of row rloc, 128-B swizzle
-        uint8_t* grow = smG + static_cast<size_t>(gbi) * NP_GBUF + static_cast<size_t>(q >> 1) * NP_ACH +
-                        static_cast<size_t>(rloc) * 128;
+        const uint32_t grow = g_row_addr + static_cast<uint32_t>(gbi) * NP_GBUF;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int unit16 = (4 * h + j) ^ (rloc & 7);
-          *reinterpret_cast<uint4*>(grow + unit16 * 16) = make_uint4(go[4 * j], go[4 * j + 1], go[4 * j + 2], go[4 * j + 3]);
-        }
+        for (int j = 0; j < 8; ++j)
+          sts_v4(grow + static_cast<uint32_t>((j ^ (rloc & 7)) * 16), go[4 * j], go[4 * j + 1], go[4 * j + 2], go[4 * j + 3]);
       }
       fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core's async proxy
       tc_fence_before();         // the S reads above are ordered before the hand-over as well
@@ -1142,7 +1212,7 @@ clip_bwd_np_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
     }
 
     // ---- dA: lanes 0-63 hold features [0,128) of each 256-feature block, lanes 64-127 [128,256) ----
-    mbar_wait(da_full, 0);
+    mbar_wait_parked(da_full, 0);
     tc_fence_after();
     const float coef = __ldg(p.grad_out_dev) * s * p.coef_host;
     float* out = p.out[strip] + static_cast<long long>(row - p.row_begin) * p.D;
@@ -1368,7 +1438,7 @@ extern "C" int nans_clip_loss_bwd(const void* I_loc, const void* T_loc, int64_t 
   p.nrb = static_cast<int>(ceil_div(grad_row_count, use_np ? 2 * NP_ROWS : (use_pair ? 2 * BM : BM)));
   p.npass = npass;
   p.nsplit = nsplit;
-  p.ntiles = static_cast<int>(ceil_div(N, KT));
+  p.ntiles = static_cast<int>(ceil_div(N, use_np ? NP_KT : KT));
   p.nr = use_np ? nplan.nr : (use_pair ? pplan.nr : plan.nr);
   p.idesc1_fmt = static_cast<uint32_t>(idesc_fmt(feat_dtype));
   // tcgen05.mma kind::f16 wants A and B in the same 16-bit format (a mixed f16 x bf16 descriptor
@@ -1399,7 +1469,7 @@ extern "C" int nans_clip_loss_bwd(const void* I_loc, const void* T_loc, int64_t 
     NANS_CUDA_OK(cudaFuncSetAttribute(clip_bwd_np_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       static_cast<int>(nplan.bytes)));
     const unsigned grid = static_cast<unsigned>(2 * 2 * p.nrb * p.nsplit);
-    clip_bwd_np_kernel<<<grid, NUM_THREADS, nplan.bytes, st>>>(tmAn0, tmBk0, tmB0, tmAn1, tmBk1, tmB1, p);
+    clip_bwd_np_kernel<<<grid, NUM_THREADS, nplan.bytes, st>>>(tmAn0, tmB0, tmAn1, tmB1, p);
   } else if (use_pair) {
     auto kern = pplan.a_resident ? clip_bwd_pair_kernel<true> : clip_bwd_pair_kernel<false>;
     NANS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
