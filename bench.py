@@ -333,7 +333,7 @@ def bench_loss(args):
     tf = ROOT / "profiles" / "traffic.json"
     if tf.exists():
         try:
-            traffic = json.loads(tf.read_text()).get("clip_bwd_kernel", {}).get(f"W{W}")
+            traffic = json.loads(tf.read_text()).get("clip_bwd_np_kernel", {}).get(f"W{W}")
         except Exception:
             traffic = None
 
@@ -359,10 +359,11 @@ def bench_loss(args):
                     "h2d_bytes_per_step": 2 * n_loc * D * 4, "d2h_bytes_per_step": 4},
             "gpu_launches": launches_per_step * args.steps,
             "gpu_launches_per_step": launches_per_step,
-            "roofline": {"kernel": "clip_bwd_kernel", "bound": "tensor", "achieved": bwd_alg / (bwd_ms / 1e3) / 1e12,
+            "roofline": {"kernel": "clip_bwd_np_kernel", "bound": "tensor", "achieved": bwd_alg / (bwd_ms / 1e3) / 1e12,
                          "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                          "frac": bwd_alg / (bwd_ms / 1e3) / 1e12 / peaks["bf16_tflops"], "traffic": traffic,
                          "launch_ms": bwd_ms, "algorithmic_flops_per_launch": bwd_alg,
+                         "hardware_tflops": 2 * bwd_alg / (bwd_ms / 1e3) / 1e12,
                          "peak_source": f"{peaks['source']} burst bf16 (kernel timed alone)"},
             "roofline_fwd": {"kernel": "clip_fwd_kernel", "bound": "tensor", "achieved": fwd_alg / (fwd_ms / 1e3) / 1e12,
                              "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
