@@ -44,6 +44,12 @@ extern "C" {
 
 /* flags for nans_clip_loss_fwd */
 #define NANS_LOSS_WITH_ACC 1 /* also count in-batch top-1 hits (train.py:117-121) */
+/* nans_clip_loss_fwd_phase only: sweep one of the two strips (image rows x text columns / text rows
+ * x image columns).  Lets the image strip start as soon as the gathered TEXT features have arrived
+ * while the image features are still in flight.  The two single-strip launches of a column range
+ * must use the SAME slot range (each fills its half of every slot). */
+#define NANS_LOSS_STRIP_IMG 2
+#define NANS_LOSS_STRIP_TXT 4
 
 /* ---- plumbing -------------------------------------------------------------------------- */
 
@@ -100,6 +106,8 @@ int nans_l2norm_bwd(const void* x, int x_dtype, int64_t ld_x, const float* inv_n
  *   s_dev          device pointer to the fp32 logit scale s = exp(logit_scale)
  */
 int64_t nans_clip_loss_fwd_phase_slots(int64_t n_loc, int64_t ncols, int64_t D);
+/* Same for a launch with `flags` (a single-strip launch splits its columns further). */
+int64_t nans_clip_loss_fwd_phase_slots_flags(int64_t n_loc, int64_t ncols, int64_t D, int flags);
 size_t nans_clip_loss_fwd_workspace_bytes(int64_t n_loc, int64_t total_slots);
 
 int nans_clip_loss_fwd_phase(const void* I_loc, const void* T_loc, int64_t ld_loc,
@@ -160,6 +168,28 @@ int nans_clip_loss_bwd(const void* I_loc, const void* T_loc, int64_t ld_loc, con
                        const float* grad_out_dev, float grad_mult, int64_t grad_row_begin,
                        int64_t grad_row_count, void* dI_loc, void* dT_loc, int out_dtype,
                        void* ws, size_t ws_bytes, void* stream);
+
+/* ---- (3b) label-smoothed variant ---------------------------------------------------------- */
+/*
+ * Replaces the fork's train_lora.py:95-110 (`contrastive_loss`: F.cross_entropy(logits, arange,
+ * label_smoothing=eps) in both directions).  The smoothed loss is the plain fused loss plus O(N D)
+ * terms (derivation in csrc/smooth.cu), so it needs two small HBM-bound kernels around (2) and (3):
+ *   nans_label_smooth_stats: stats[0..D) = sum_i I_i, stats[D..2D) = sum_i T_i,
+ *                            stats[2D] = sum_i I_i.T_i over this rank's rows (the function zeroes
+ *                            `stats` first; sum over ranks with an all-reduce).  I, T fp32, row pitch ld.
+ *       loss_eps = loss + eps*s/N * stats[2D] - eps*s/N^2 * (stats[0..D) . stats[D..2D))
+ *       dloss/ds likewise without the factor s.
+ *   nans_label_smooth_bwd: dI[r] += a*T[r] - (a*inv_n)*Tsum, dT[r] += a*I[r] - (a*inv_n)*Isum with
+ *                            a = grad_out * s * coef, coef = grad_mult * eps / N, inv_n = 1 / N;
+ *                            dI, dT fp32 [rows, D] contiguous (the outputs of nans_clip_loss_bwd),
+ *                            I_rows / T_rows the same rows of the fp32 features (pitch ld),
+ *                            stats the GLOBAL sums.
+ */
+int nans_label_smooth_stats(const float* I, const float* T, int64_t ld, int64_t rows, int64_t D,
+                            float* stats, void* stream);
+int nans_label_smooth_bwd(float* dI, float* dT, const float* I_rows, const float* T_rows, int64_t ld,
+                          int64_t rows, int64_t D, const float* stats, const float* s_dev,
+                          const float* grad_out_dev, float coef, float inv_n, void* stream);
 
 /* ---- (4) top-k inner-product retrieval ---------------------------------------------------- */
 /*

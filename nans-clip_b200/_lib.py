@@ -15,6 +15,8 @@ LIB_PATH = PKG / "lib" / "libnans_clip.so"
 
 NANS_F32, NANS_F16, NANS_BF16 = 0, 1, 2
 NANS_LOSS_WITH_ACC = 1
+NANS_LOSS_STRIP_IMG = 2
+NANS_LOSS_STRIP_TXT = 4
 
 ERR_NAMES = {-1: "NANS_ERR_ARG", -2: "NANS_ERR_DEVICE", -3: "NANS_ERR_CUDA", -4: "NANS_ERR_WORKSPACE"}
 
@@ -35,6 +37,7 @@ _SIGNATURES = {
     "nans_l2norm_bwd": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p, c_int64, c_int64,
                                 c_void_p, c_void_p]),
     "nans_clip_loss_fwd_phase_slots": (c_int64, [c_int64, c_int64, c_int64]),
+    "nans_clip_loss_fwd_phase_slots_flags": (c_int64, [c_int64, c_int64, c_int64, c_int]),
     "nans_clip_loss_fwd_workspace_bytes": (c_size_t, [c_int64, c_int64]),
     "nans_clip_loss_fwd_phase": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64,
                                          c_int, c_int64, c_int64, c_int64, c_int64, c_int64,
@@ -50,6 +53,9 @@ _SIGNATURES = {
                                    c_int64, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p,
                                    c_void_p, c_float, c_int64, c_int64, c_void_p, c_void_p, c_int,
                                    c_void_p, c_size_t, c_void_p]),
+    "nans_label_smooth_stats": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p]),
+    "nans_label_smooth_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64,
+                                      c_void_p, c_void_p, c_void_p, c_float, c_float, c_void_p]),
     "nans_topk_ip_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64, c_int]),
     "nans_topk_ip": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int64, c_int64,
                              c_int64, c_int, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_size_t,

@@ -1260,10 +1260,22 @@ __global__ void __launch_bounds__(1024) lse_minmax_kernel(const float* __restric
                                                           int* __restrict__ out) {
   __shared__ float slo[32], shi[32];
   float lo = INFINITY, hi = -INFINITY;
-  for (int i = threadIdx.x; i < 2 * n; i += blockDim.x) {
-    const float v = i < n ? a[i] : b[i - n];
-    lo = fminf(lo, v);
-    hi = fmaxf(hi, v);
+  // both arrays are 16-byte aligned (checked by the caller): independent float4 loads in flight
+  const int n4 = n >> 2;
+#pragma unroll
+  for (int arr = 0; arr < 2; ++arr) {
+    const float* __restrict__ src = arr == 0 ? a : b;
+    const float4* __restrict__ v4 = reinterpret_cast<const float4*>(src);
+#pragma unroll 8
+    for (int i = threadIdx.x; i < n4; i += 1024) {
+      const float4 v = __ldg(v4 + i);
+      lo = fminf(fminf(lo, fminf(v.x, v.y)), fminf(v.z, v.w));
+      hi = fmaxf(fmaxf(hi, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
+    }
+    for (int i = 4 * n4 + threadIdx.x; i < n; i += 1024) {
+      lo = fminf(lo, src[i]);
+      hi = fmaxf(hi, src[i]);
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {

@@ -27,6 +27,7 @@ struct FwdParams {
   int n_loc, ncols, kchunks, stages;
   uint32_t idesc;
   int nrb, nsplit, ntiles;
+  int strip0;       // first strip of this launch (1 for a text-rows-only launch)
   int label_shift;  // label column of row r in phase coordinates = r + label_shift
   int col_global_begin;  // global column of phase column 0
   int skip_begin, skip_count;  // tiles of the column operand this phase does not sweep
@@ -130,7 +131,7 @@ clip_fwd_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
   const int unit = CP ? (blockIdx.x >> 1) : blockIdx.x;
   const int split = unit % p.nsplit;
   const int rb = (unit / p.nsplit) % p.nrb;
-  const int strip = unit / (p.nsplit * p.nrb);
+  const int strip = unit / (p.nsplit * p.nrb) + p.strip0;
 
   SweepArgs a;
   a.tmA = strip == 0 ? &tmA0 : &tmA1;
@@ -338,9 +339,13 @@ bool fwd_pair_mode() {
   return !(e && e[0] == '1');
 }
 
-int choose_nsplit(int64_t n_loc, int64_t ncols) {
+int strips_of(int flags) {
+  return (flags & (NANS_LOSS_STRIP_IMG | NANS_LOSS_STRIP_TXT)) ? 1 : 2;
+}
+
+int choose_nsplit(int64_t n_loc, int64_t ncols, int nstrips) {
   const bool pair = fwd_pair_mode();
-  const int64_t base = 2 * ceil_div(n_loc, pair ? 2 * BM : BM);
+  const int64_t base = nstrips * ceil_div(n_loc, pair ? 2 * BM : BM);
   const int64_t ntiles = ceil_div(ncols, BN);
   const int sms = pair ? sm_count() / 2 : sm_count();
   int best = 1;
@@ -365,7 +370,13 @@ using namespace nans;
 extern "C" int64_t nans_clip_loss_fwd_phase_slots(int64_t n_loc, int64_t ncols, int64_t D) {
   (void)D;
   if (n_loc <= 0 || ncols <= 0) return 0;
-  return choose_nsplit(n_loc, ncols);
+  return choose_nsplit(n_loc, ncols, 2);
+}
+
+extern "C" int64_t nans_clip_loss_fwd_phase_slots_flags(int64_t n_loc, int64_t ncols, int64_t D, int flags) {
+  (void)D;
+  if (n_loc <= 0 || ncols <= 0) return 0;
+  return choose_nsplit(n_loc, ncols, strips_of(flags));
 }
 
 extern "C" size_t nans_clip_loss_fwd_workspace_bytes(int64_t n_loc, int64_t total_slots) {
@@ -395,8 +406,11 @@ extern "C" int nans_clip_loss_fwd_phase(const void* I_loc, const void* T_loc, in
                    skip_col_count % BN == 0 && skip_col_begin + skip_col_count <= ncols,
                "loss_fwd: the skipped column range must be made of whole 256-column tiles inside the operand");
   if (skip_col_count == ncols) return NANS_OK;
+  NANS_REQUIRE((flags & NANS_LOSS_STRIP_IMG) == 0 || (flags & NANS_LOSS_STRIP_TXT) == 0,
+               "loss_fwd: NANS_LOSS_STRIP_IMG and NANS_LOSS_STRIP_TXT are exclusive (pass neither for both)");
 
-  const int nsplit = choose_nsplit(n_loc, ncols - skip_col_count);
+  const int nstrips = strips_of(flags);
+  const int nsplit = choose_nsplit(n_loc, ncols - skip_col_count, nstrips);
   // the caller sized the workspace for total_slots >= slot_begin + nsplit
   const size_t need = carve_fwd_ws(nullptr, n_loc, slot_begin + nsplit).bytes;
   if (ws_bytes < need) {
@@ -424,6 +438,7 @@ extern "C" int nans_clip_loss_fwd_phase(const void* I_loc, const void* T_loc, in
   p.idesc = make_idesc(idesc_fmt(feat_dtype), idesc_fmt(feat_dtype), 0, 0, pair ? 2 * BM : BM, BN);
   p.nrb = static_cast<int>(ceil_div(n_loc, pair ? 2 * BM : BM));
   p.nsplit = nsplit;
+  p.strip0 = (flags & NANS_LOSS_STRIP_TXT) ? 1 : 0;
   p.ntiles = static_cast<int>(ceil_div(ncols, BN) - skip_col_count / BN);
   p.skip_begin = skip_col_count > 0 ? static_cast<int>(skip_col_begin / BN) : (1 << 30);
   p.skip_count = static_cast<int>(skip_col_count / BN);
@@ -450,7 +465,7 @@ extern "C" int nans_clip_loss_fwd_phase(const void* I_loc, const void* T_loc, in
   }
   NANS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     static_cast<int>(plan.bytes)));
-  const unsigned grid = static_cast<unsigned>((pair ? 2 : 1) * 2 * p.nrb * p.nsplit);
+  const unsigned grid = static_cast<unsigned>((pair ? 2 : 1) * nstrips * p.nrb * p.nsplit);
   kern<<<grid, NUM_THREADS, plan.bytes, static_cast<cudaStream_t>(stream)>>>(tmA0, tmB0, tmA1, tmB1, p);
   NANS_CUDA_OK(cudaGetLastError());
   return NANS_OK;

@@ -12,7 +12,8 @@ from __future__ import annotations
 import torch
 
 from . import _lib
-from ._lib import NANS_BF16, NANS_F16, NANS_F32, NANS_LOSS_WITH_ACC, check
+from ._lib import (NANS_BF16, NANS_F16, NANS_F32, NANS_LOSS_STRIP_IMG, NANS_LOSS_STRIP_TXT,
+                   NANS_LOSS_WITH_ACC, check)
 
 _DT = {torch.float32: NANS_F32, torch.float16: NANS_F16, torch.bfloat16: NANS_BF16}
 
@@ -32,8 +33,24 @@ def dtype_code(dt: torch.dtype) -> int:
         raise TypeError(f"unsupported dtype {dt}: expected float32, float16 or bfloat16") from None
 
 
-def _stream() -> int:
-    return torch.cuda.current_stream().cuda_stream
+class _on_device:
+    """`with torch.cuda.device(dev)` plus the raw handle of that device's current stream, without
+    the Python-level device bookkeeping when `dev` already is the current device (the usual case:
+    one process per GPU) — that bookkeeping was ~15 % of the host time of a loss step."""
+    __slots__ = ("idx", "prev")
+
+    def __init__(self, dev: torch.device):
+        self.idx = dev.index if dev.index is not None else torch._C._cuda_getDevice()
+
+    def __enter__(self) -> int:
+        self.prev = torch._C._cuda_getDevice()
+        if self.prev != self.idx:
+            torch.cuda.set_device(self.idx)
+        return torch._C._cuda_getCurrentRawStream(self.idx)
+
+    def __exit__(self, *exc) -> None:
+        if self.prev != self.idx:
+            torch.cuda.set_device(self.prev)
 
 
 def _ptr(t: torch.Tensor | None) -> int | None:
@@ -67,11 +84,11 @@ def l2norm_cast(x: torch.Tensor, out_dtype: torch.dtype | None = torch.bfloat16,
     y16 = torch.empty((rows, D), dtype=out_dtype, device=x.device) if out_dtype is not None else None
     y32 = torch.empty((rows, D), dtype=torch.float32, device=x.device) if want_fp32 else None
     inv = torch.empty((rows,), dtype=torch.float32, device=x.device) if want_inv_norm else None
-    with torch.cuda.device(x.device):
+    with _on_device(x.device) as stream:
         check(_lib.load().nans_l2norm_cast(
             x.data_ptr(), dtype_code(x.dtype), rows, D, x.stride(0) if rows > 1 else D,
             _ptr(y16), dtype_code(out_dtype) if out_dtype is not None else NANS_BF16,
-            _ptr(y32), _ptr(inv), 1 if normalize else 0, _stream()))
+            _ptr(y32), _ptr(inv), 1 if normalize else 0, stream))
     _count(1 if rows else 0)
     return y16, y32, inv
 
@@ -82,10 +99,10 @@ def l2norm_bwd(x: torch.Tensor, inv_norm: torch.Tensor, dy: torch.Tensor) -> tor
     dy = dy.to(torch.float32).contiguous()
     rows, D = x.shape
     dx = torch.empty((rows, D), dtype=torch.float32, device=x.device)
-    with torch.cuda.device(x.device):
+    with _on_device(x.device) as stream:
         check(_lib.load().nans_l2norm_bwd(x.data_ptr(), dtype_code(x.dtype),
                                           x.stride(0) if rows > 1 else D, inv_norm.data_ptr(),
-                                          dy.data_ptr(), rows, D, dx.data_ptr(), _stream()))
+                                          dy.data_ptr(), rows, D, dx.data_ptr(), stream))
     _count(1 if rows else 0)
     return dx
 
@@ -93,8 +110,14 @@ def l2norm_bwd(x: torch.Tensor, inv_norm: torch.Tensor, dy: torch.Tensor) -> tor
 # --------------------------------------------------------------------------------------------
 # (2) fused forward
 # --------------------------------------------------------------------------------------------
-def fwd_phase_slots(n_loc: int, ncols: int, D: int) -> int:
-    return int(_lib.load().nans_clip_loss_fwd_phase_slots(n_loc, ncols, D))
+_STRIP_FLAG = {None: 0, "img": NANS_LOSS_STRIP_IMG, "txt": NANS_LOSS_STRIP_TXT}
+
+
+def fwd_phase_slots(n_loc: int, ncols: int, D: int, strip: str | None = None) -> int:
+    """Workspace slots a phase over `ncols` columns occupies (`strip`: see fwd_phase)."""
+    if strip is None:
+        return int(_lib.load().nans_clip_loss_fwd_phase_slots(n_loc, ncols, D))
+    return int(_lib.load().nans_clip_loss_fwd_phase_slots_flags(n_loc, ncols, D, _STRIP_FLAG[strip]))
 
 
 def fwd_workspace(n_loc: int, total_slots: int, device) -> torch.Tensor:
@@ -104,21 +127,23 @@ def fwd_workspace(n_loc: int, total_slots: int, device) -> torch.Tensor:
 
 def fwd_phase(I_loc, T_loc, T_cols, I_cols, *, col_global_begin: int, label_begin: int,
               s_dev: torch.Tensor, with_acc: bool, ws: torch.Tensor, slot_begin: int,
-              skip_begin: int = 0, skip_count: int = 0) -> None:
+              skip_begin: int = 0, skip_count: int = 0, strip: str | None = None) -> None:
     """One phase of the forward column sweep; columns [skip_begin, skip_begin + skip_count) of the
-    operands (multiples of 256) are left to another phase."""
+    operands (multiples of 256) are left to another phase.  `strip` = "img" sweeps only the image
+    rows against `T_cols` (`I_cols` is not read), "txt" only the text rows against `I_cols`; the
+    two launches of one column range share their slot range."""
     _require_cuda(I_loc, T_loc, T_cols, I_cols, s_dev, ws)
     n_loc, D = I_loc.shape
     ncols = T_cols.shape[0]
     assert I_loc.dtype == T_loc.dtype == T_cols.dtype == I_cols.dtype
     assert I_loc.stride(0) == T_loc.stride(0) and T_cols.stride(0) == I_cols.stride(0)
-    with torch.cuda.device(I_loc.device):
+    with _on_device(I_loc.device) as stream:
         check(_lib.load().nans_clip_loss_fwd_phase(
             I_loc.data_ptr(), T_loc.data_ptr(), I_loc.stride(0), T_cols.data_ptr(),
             I_cols.data_ptr(), T_cols.stride(0), dtype_code(I_loc.dtype), n_loc, ncols, D,
             col_global_begin, label_begin, skip_begin, skip_count, s_dev.data_ptr(),
-            NANS_LOSS_WITH_ACC if with_acc else 0, ws.data_ptr(), ws.numel(), slot_begin,
-            _stream()))
+            (NANS_LOSS_WITH_ACC if with_acc else 0) | _STRIP_FLAG[strip], ws.data_ptr(), ws.numel(),
+            slot_begin, stream))
     _count(1)
 
 
@@ -132,11 +157,11 @@ def fwd_finalize(n_loc: int, total_slots: int, label_begin: int, s_dev: torch.Te
     packed = torch.empty((2 * pad + 8,), dtype=torch.float32, device=ws.device)
     lse = packed[:2 * pad].view(2, pad)[:, :n_loc]
     scalars = packed[2 * pad:]
-    with torch.cuda.device(ws.device):
+    with _on_device(ws.device) as stream:
         check(_lib.load().nans_clip_loss_fwd_finalize(
             n_loc, total_slots, label_begin, s_dev.data_ptr(),
             NANS_LOSS_WITH_ACC if with_acc else 0, ws.data_ptr(), ws.numel(),
-            lse[0].data_ptr(), lse[1].data_ptr(), scalars.data_ptr(), _stream()))
+            lse[0].data_ptr(), lse[1].data_ptr(), scalars.data_ptr(), stream))
     _count(1)
     return lse, scalars, packed
 
@@ -164,15 +189,54 @@ def bwd(I_loc, T_loc, T_all, I_all, *, label_begin: int, s_dev: torch.Tensor,
         buf.copy_(lse_all)
         lse_all = buf
     assert grad_out.dtype == torch.float32 and grad_out.numel() == 1
-    with torch.cuda.device(dev):
+    with _on_device(dev) as stream:
         check(lib.nans_clip_loss_bwd(
             I_loc.data_ptr(), T_loc.data_ptr(), I_loc.stride(0), T_all.data_ptr(),
             I_all.data_ptr(), T_all.stride(0), dtype_code(I_loc.dtype), n_loc, N, D, label_begin,
             s_dev.data_ptr(), lse_all[0].data_ptr(), lse_all[1].data_ptr(), grad_out.data_ptr(),
             float(grad_mult), row_begin, row_count, dI.data_ptr(), dT.data_ptr(),
-            dtype_code(out_dtype), ws.data_ptr(), ws.numel(), _stream()))
+            dtype_code(out_dtype), ws.data_ptr(), ws.numel(), stream))
     _count(2 if out_dtype == torch.float32 else 4)  # lse min/max + backward (+ 2 casts)
     return dI, dT
+
+
+# --------------------------------------------------------------------------------------------
+# (3b) label smoothing (train_lora.py:95-110)
+# --------------------------------------------------------------------------------------------
+def smooth_stats(I32: torch.Tensor, T32: torch.Tensor) -> torch.Tensor:
+    """[2 D + 1] fp32: column sums of I, column sums of T, sum_i I_i.T_i (this rank's rows)."""
+    _require_cuda(I32, T32)
+    I32, T32 = _rowmajor(I32), _rowmajor(T32)
+    assert I32.dtype == T32.dtype == torch.float32 and I32.shape == T32.shape
+    rows, D = I32.shape
+    if rows > 1 and I32.stride(0) != T32.stride(0):
+        I32, T32 = I32.contiguous(), T32.contiguous()
+    stats = torch.empty((2 * D + 1,), dtype=torch.float32, device=I32.device)
+    with _on_device(I32.device) as stream:
+        check(_lib.load().nans_label_smooth_stats(I32.data_ptr(), T32.data_ptr(),
+                                                  I32.stride(0) if rows > 1 else D, rows, D,
+                                                  stats.data_ptr(), stream))
+    _count(1 if rows else 0)
+    return stats
+
+
+def smooth_bwd(dI: torch.Tensor, dT: torch.Tensor, I_rows: torch.Tensor, T_rows: torch.Tensor,
+               stats: torch.Tensor, s_dev: torch.Tensor, grad_out: torch.Tensor, coef: float,
+               inv_n: float) -> None:
+    """In place: dI += a T_rows - a/N Tsum, dT += a I_rows - a/N Isum, a = grad_out * s * coef."""
+    _require_cuda(dI, dT, I_rows, T_rows, stats, s_dev, grad_out)
+    I_rows, T_rows = _rowmajor(I_rows), _rowmajor(T_rows)
+    rows, D = dI.shape
+    assert dI.dtype == dT.dtype == I_rows.dtype == T_rows.dtype == torch.float32
+    assert dI.is_contiguous() and dT.is_contiguous() and I_rows.shape == T_rows.shape == (rows, D)
+    if rows > 1 and I_rows.stride(0) != T_rows.stride(0):
+        I_rows, T_rows = I_rows.contiguous(), T_rows.contiguous()
+    with _on_device(dI.device) as stream:
+        check(_lib.load().nans_label_smooth_bwd(dI.data_ptr(), dT.data_ptr(), I_rows.data_ptr(),
+                                                T_rows.data_ptr(), I_rows.stride(0) if rows > 1 else D,
+                                                rows, D, stats.data_ptr(), s_dev.data_ptr(),
+                                                grad_out.data_ptr(), float(coef), float(inv_n), stream))
+    _count(1 if rows else 0)
 
 
 # --------------------------------------------------------------------------------------------
@@ -192,11 +256,11 @@ def topk_ip(Q16, G16, Q32, G32, k: int, k_cand: int, gallery_index_offset: int =
     lib = _lib.load()
     ws = torch.empty(int(lib.nans_topk_ip_workspace_bytes(Qn, Gn, D, k_cand)), dtype=torch.uint8,
                      device=dev)
-    with torch.cuda.device(dev):
+    with _on_device(dev) as stream:
         check(lib.nans_topk_ip(Q16.data_ptr(), G16.data_ptr(), dtype_code(Q16.dtype), _ptr(Q32),
                                _ptr(G32), Qn, Gn, D, k, k_cand, gallery_index_offset,
                                scores.data_ptr(), index.data_ptr(), ws.data_ptr(), ws.numel(),
-                               _stream()))
+                               stream))
     _count(0 if not Qn else (1 if not Gn else (3 if Gn >= 3 * 16384 else 2)))  # [pre-pass +] sweep + finalize
     return scores, index
 
@@ -208,8 +272,8 @@ def topk_merge(scores: torch.Tensor, index: torch.Tensor):
     scores, index = scores.contiguous(), index.contiguous()
     out_s = torch.empty((Qn, k), dtype=torch.float32, device=scores.device)
     out_i = torch.empty((Qn, k), dtype=torch.int64, device=scores.device)
-    with torch.cuda.device(scores.device):
+    with _on_device(scores.device) as stream:
         check(_lib.load().nans_topk_merge(scores.data_ptr(), index.data_ptr(), n_shards, Qn, k,
-                                          out_s.data_ptr(), out_i.data_ptr(), _stream()))
+                                          out_s.data_ptr(), out_i.data_ptr(), stream))
     _count(1)
     return out_s, out_i

@@ -37,6 +37,7 @@ class LossConfig:
     report_acc: bool = False            # args.report_training_batch_acc (params.py:52)
     feat_dtype: torch.dtype = torch.float16
     overlap_gather: bool = True
+    label_smoothing: float = 0.0        # F.cross_entropy(label_smoothing=...) of train_lora.py:95-110
 
 
 def _world(group) -> tuple[int, int]:
@@ -87,39 +88,46 @@ class _ClipLossFn(torch.autograd.Function):
         label_begin = rank * n_loc
 
         # ---- phases of the column sweep -----------------------------------------------------
-        # a phase = (T columns, I columns, global index of column 0, skipped range (begin, count))
+        # a phase = (T columns, I columns, global index of column 0, skipped range (begin, count),
+        #            strip (None = both), index of the gather it has to wait for (-1 = none))
         if W == 1:
             I_all, T_all = I16, T16
-            phases = [(T16, I16, 0, (0, 0))]
+            phases = [(T16, I16, 0, (0, 0), None, -1)]
             works = []
         else:
             I_all = torch.empty((N, D), dtype=cfg.feat_dtype, device=dev)
             T_all = torch.empty((N, D), dtype=cfg.feat_dtype, device=dev)
-            works = [dist.all_gather_into_tensor(I_all, I16, group=cfg.group, async_op=True),
-                     dist.all_gather_into_tensor(T_all, T16, group=cfg.group, async_op=True)]
+            # text first: the image strip only reads T_all and runs while I_all is still in flight
+            works = [dist.all_gather_into_tensor(T_all, T16, group=cfg.group, async_op=True),
+                     dist.all_gather_into_tensor(I_all, I16, group=cfg.group, async_op=True)]
             lo, hi = rank * n_loc, (rank + 1) * n_loc
-            phases = [(T16, I16, lo, (0, 0))]               # local block: needs no remote data
+            phases = [(T16, I16, lo, (0, 0), None, -1 if cfg.overlap_gather else 1)]  # local block
             if n_loc % 256 == 0:
-                # everything else in ONE launch over the gathered buffers, skipping the local tiles
-                phases.append((T_all, I_all, 0, (lo, n_loc)))
+                # everything else in one launch per strip over the gathered buffers, skipping the
+                # local tiles; both launches fill the same slots
+                phases.append((T_all, I_all, 0, (lo, n_loc), "img", 0))
+                phases.append((T_all, I_all, 0, (lo, n_loc), "txt", 1))
             else:
                 if lo > 0:
-                    phases.append((T_all[:lo], I_all[:lo], 0, (0, 0)))
+                    phases.append((T_all[:lo], I_all[:lo], 0, (0, 0), None, 1))
                 if hi < N:
-                    phases.append((T_all[hi:], I_all[hi:], hi, (0, 0)))
-        slots = [K.fwd_phase_slots(n_loc, tc.shape[0] - sk[1], D) for tc, _, _, sk in phases]
-        ws = K.fwd_workspace(n_loc, sum(slots), dev)
+                    phases.append((T_all[hi:], I_all[hi:], hi, (0, 0), None, 1))
+        slots = [K.fwd_phase_slots(n_loc, tc.shape[0] - sk[1], D, st) for tc, _, _, sk, st, _ in phases]
+        total_slots = sum(ns for ns, ph in zip(slots, phases) if ph[4] != "txt")
+        ws = K.fwd_workspace(n_loc, total_slots, dev)
         slot = 0
-        for i, (tc, ic, col0, sk) in enumerate(phases):
-            if i == 1 or (i == 0 and works and not cfg.overlap_gather):
-                for w in works:
-                    w.wait()
-                works = []
+        waited = -1
+        for i, (tc, ic, col0, sk, st, need) in enumerate(phases):
+            while waited < need:
+                waited += 1
+                works[waited].wait()
+            if st == "txt":
+                slot -= slots[i]      # the text strip fills the other half of the image strip's slots
             K.fwd_phase(I16, T16, tc, ic, col_global_begin=col0, label_begin=label_begin,
                         s_dev=s_dev, with_acc=cfg.report_acc, ws=ws, slot_begin=slot,
-                        skip_begin=sk[0], skip_count=sk[1])
+                        skip_begin=sk[0], skip_count=sk[1], strip=st)
             slot += slots[i]
-        for w in works:
+        for w in works[waited + 1:]:
             w.wait()
         lse, scalars, packed = K.fwd_finalize(n_loc, slot, label_begin, s_dev, cfg.report_acc, ws)
 
@@ -141,7 +149,20 @@ class _ClipLossFn(torch.autograd.Function):
         acc_i2t = red[4]
         acc_t2i = red[5]
 
-        ctx.save_for_backward(I16, T16, I_all, T_all, s_dev, lse_all, dscale)
+        # ---- label smoothing: the plain loss plus O(N D) terms (csrc/smooth.cu) ------------------
+        stats = I32 = T32 = None
+        eps = float(cfg.label_smoothing)
+        if eps != 0.0:
+            I32 = full_img.detach().to(torch.float32)
+            T32 = full_txt.detach().to(torch.float32)
+            stats = K.smooth_stats(I32, T32)
+            if W > 1:
+                dist.all_reduce(stats, group=cfg.group)
+            corr = (eps / N) * stats[2 * D] - (eps / (float(N) * N)) * torch.dot(stats[:D], stats[D:2 * D])
+            loss = loss + s_dev[0] * corr
+            dscale = dscale + corr
+
+        ctx.save_for_backward(I16, T16, I_all, T_all, s_dev, lse_all, dscale, stats, I32, T32)
         ctx.cfg = cfg
         ctx.meta = (W, label_begin, int(row_begin), chunk_img.shape[0], chunk_img.dtype,
                     chunk_txt.dtype)
@@ -150,18 +171,22 @@ class _ClipLossFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_loss, _g1, _g2):
-        I16, T16, I_all, T_all, s_dev, lse_all, dscale = ctx.saved_tensors
+        I16, T16, I_all, T_all, s_dev, lse_all, dscale, stats, I32, T32 = ctx.saved_tensors
         W, label_begin, row_begin, rows, dt_i, dt_t = ctx.meta
         cfg = ctx.cfg
         need_feat = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
         dI = dT = None
         if need_feat:
             g = g_loss.detach().to(torch.float32).reshape(1).contiguous()
-            out_dt = dt_i if dt_i == dt_t else torch.float32
+            out_dt = dt_i if (dt_i == dt_t and stats is None) else torch.float32
+            mult = float(W) if cfg.gather_with_grad else 1.0
             dI, dT = K.bwd(I16, T16, T_all, I_all, label_begin=label_begin, s_dev=s_dev,
-                           lse_all=lse_all, grad_out=g,
-                           grad_mult=float(W) if cfg.gather_with_grad else 1.0,
+                           lse_all=lse_all, grad_out=g, grad_mult=mult,
                            row_begin=row_begin, row_count=rows, out_dtype=out_dt)
+            if stats is not None:
+                N = T_all.shape[0]
+                K.smooth_bwd(dI, dT, I32[row_begin:row_begin + rows], T32[row_begin:row_begin + rows], stats,
+                             s_dev, g, mult * float(cfg.label_smoothing) / N, 1.0 / N)
             dI = dI.to(dt_i) if ctx.needs_input_grad[0] else None
             dT = dT.to(dt_t) if ctx.needs_input_grad[1] else None
         ds = g_loss * dscale if ctx.needs_input_grad[2] else None
@@ -173,18 +198,22 @@ def clip_contrastive_loss(image_features: torch.Tensor, text_features: torch.Ten
                           report_acc: bool = False, feat_dtype: torch.dtype = torch.float16,
                           full_image_features: Optional[torch.Tensor] = None,
                           full_text_features: Optional[torch.Tensor] = None, row_begin: int = 0,
-                          overlap_gather: bool = True):
+                          overlap_gather: bool = True, label_smoothing: float = 0.0):
     """Contrastive loss of unit-norm features against arange labels.
 
     Returns (loss, acc) with acc = None or {"i2t": t, "t2i": t} exactly as train.py:109-126.
     `logit_scale` is the already exponentiated scale s (what CLIP.forward returns, model.py:415).
     Pass `full_*` + `row_begin` on the gradient-accumulation path: the block the loss is computed
     on, of which `image_features` / `text_features` are rows [row_begin, row_begin + B).
+    `label_smoothing` = the `label_smoothing` of F.cross_entropy in the fork's train_lora.py:105-108.
     """
+    if not 0.0 <= float(label_smoothing) < 1.0:
+        raise ValueError(f"label_smoothing must be in [0, 1), got {label_smoothing}")
     if full_image_features is None:
         full_image_features, full_text_features, row_begin = image_features, text_features, 0
     cfg = LossConfig(group=group, gather_with_grad=gather_with_grad, report_acc=report_acc,
-                     feat_dtype=feat_dtype, overlap_gather=overlap_gather)
+                     feat_dtype=feat_dtype, overlap_gather=overlap_gather,
+                     label_smoothing=float(label_smoothing))
     loss, i2t, t2i = _ClipLossFn.apply(image_features, text_features, logit_scale,
                                        full_image_features, full_text_features, row_begin, cfg)
     acc = {"i2t": i2t, "t2i": t2i} if report_acc else None

@@ -32,15 +32,16 @@ def is_master(args):
 
 
 def _check_criterion(crit, name):
-    """The fused kernels implement nn.CrossEntropyLoss() with its defaults (train.py:145-146)."""
+    """The fused kernels implement nn.CrossEntropyLoss() with its defaults (train.py:145-146), plus
+    its `label_smoothing` (the variant of the fork's train_lora.py:105-108).  Returns the smoothing."""
     if crit is None:
-        return
+        return 0.0
     if not isinstance(crit, nn.CrossEntropyLoss):
         raise NotImplementedError(f"{name}: the fused loss implements nn.CrossEntropyLoss only")
-    if (crit.weight is not None or crit.reduction != "mean" or crit.ignore_index != -100
-            or getattr(crit, "label_smoothing", 0.0) != 0.0):
-        raise NotImplementedError(f"{name}: only default nn.CrossEntropyLoss() is supported "
-                                  "(mean reduction, no class weights, no label smoothing)")
+    if crit.weight is not None or crit.reduction != "mean" or crit.ignore_index != -100:
+        raise NotImplementedError(f"{name}: only nn.CrossEntropyLoss with mean reduction and no class "
+                                  "weights is supported")
+    return float(getattr(crit, "label_smoothing", 0.0))
 
 
 def cosineSimilarityLoss(feature1, feature2):
@@ -60,8 +61,9 @@ def _teacher_features(teacher_model, images):
 def get_loss(model, images, texts, loss_img, loss_txt, args, accum_image_features=None,
              accum_text_features=None, accum_idx=-1, teacher_model=None,
              teacher_accum_image_features=None):
-    _check_criterion(loss_img, "loss_img")
-    _check_criterion(loss_txt, "loss_txt")
+    smoothing = _check_criterion(loss_img, "loss_img")
+    if _check_criterion(loss_txt, "loss_txt") != smoothing:
+        raise NotImplementedError("loss_img and loss_txt must use the same label_smoothing")
     teacher_image_features = None
     if args.accum_freq == 1:
         image_features, text_features, logit_scale = model(images, texts, args.mask_ratio)
@@ -92,7 +94,7 @@ def get_loss(model, images, texts, loss_img, loss_txt, args, accum_image_feature
         gather_with_grad=bool(args.aggregate and args.gather_with_grad),
         report_acc=bool(args.report_training_batch_acc), feat_dtype=FEAT_DTYPE,
         full_image_features=full_image_features, full_text_features=full_text_features,
-        row_begin=row_begin)
+        row_begin=row_begin, label_smoothing=smoothing)
 
     if args.distillation:
         # outside the fused path: plain PyTorch, same gather order as train.py:90-100

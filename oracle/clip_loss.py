@@ -105,3 +105,27 @@ def global_loss_and_grads(I: torch.Tensor, T: torch.Tensor, s: float, dtype=torc
     return {"loss": loss.detach(), "i2t": acc["i2t"], "t2i": acc["t2i"], "dI": Ii.grad, "dT": Ti.grad,
             "ds": si.grad, "lse_img": torch.logsumexp(lpi.detach(), dim=1),
             "lse_txt": torch.logsumexp(lpt.detach(), dim=1)}
+
+
+def lora_contrastive_loss(image_features, text_features, logit_scale, label_smoothing: float = 0.05):
+    """train_lora.py:95-110 — the fork's LoRA script: F.normalize both feature sets, logits =
+    logit_scale * I @ T^T, mean of F.cross_entropy(label_smoothing=eps) over both directions."""
+    I = F.normalize(image_features, dim=-1)
+    T = F.normalize(text_features, dim=-1)
+    logits = logit_scale * I @ T.T
+    labels = torch.arange(logits.shape[0])
+    return (F.cross_entropy(logits, labels, label_smoothing=label_smoothing)
+            + F.cross_entropy(logits.T, labels, label_smoothing=label_smoothing)) / 2
+
+
+def global_smoothed_loss_and_grads(I: torch.Tensor, T: torch.Tensor, s: float, eps: float, dtype=torch.float32):
+    """Label-smoothed loss of already-normalised [N, D] features and its gradients: the CE of
+    cn_clip/training/train.py:109-115 with the label_smoothing of train_lora.py:105-108."""
+    Ii = I.to(dtype).clone().requires_grad_(True)
+    Ti = T.to(dtype).clone().requires_grad_(True)
+    si = torch.tensor(float(s), dtype=dtype, requires_grad=True)
+    lpi, lpt = logits_pair(Ii, Ti, si)
+    gt = torch.arange(len(lpi))
+    loss = (F.cross_entropy(lpi, gt, label_smoothing=eps) + F.cross_entropy(lpt, gt, label_smoothing=eps)) / 2
+    loss.backward()
+    return {"loss": loss.detach(), "dI": Ii.grad, "dT": Ti.grad, "ds": si.grad}

@@ -14,7 +14,7 @@ STATE = {}
 
 def install(K):
     for name in ("l2norm_cast", "fwd_phase_slots", "fwd_workspace", "fwd_phase", "fwd_finalize", "bwd",
-                 "topk_ip", "topk_merge"):
+                 "smooth_stats", "smooth_bwd", "topk_ip", "topk_merge"):
         setattr(K, name, globals()[name])
 
 
@@ -26,8 +26,9 @@ def l2norm_cast(x, out_dtype=torch.float16, *, normalize=True, want_fp32=False, 
             (1 / nrm).squeeze(-1) if want_inv_norm else None)
 
 
-def fwd_phase_slots(n_loc, ncols, D):
-    return 2 if ncols > 30 else 1  # exercise multi-slot merging
+def fwd_phase_slots(n_loc, ncols, D, strip=None):
+    base = 2 if ncols > 30 else 1  # exercise multi-slot merging
+    return base if strip is None else base + 1  # single-strip launches split differently
 
 
 def fwd_workspace(n_loc, total_slots, device):
@@ -37,34 +38,51 @@ def fwd_workspace(n_loc, total_slots, device):
 
 
 def fwd_phase(I_loc, T_loc, T_cols, I_cols, *, col_global_begin, label_begin, s_dev, with_acc, ws, slot_begin,
-              skip_begin=0, skip_count=0):
-    if skip_count:
-        raise NotImplementedError("the CPU stand-in only sees tile-unaligned (3-phase) cases")
+              skip_begin=0, skip_count=0, strip=None):
     st = STATE[ws.data_ptr()]
     s = float(s_dev)
     n_loc, ncols = I_loc.shape[0], T_cols.shape[0]
-    ns = fwd_phase_slots(n_loc, ncols, I_loc.shape[1])
-    bounds = [ncols * i // ns for i in range(ns + 1)]
+    assert skip_begin % 256 == 0 and skip_count % 256 == 0
+    keep = torch.cat([torch.arange(0, skip_begin), torch.arange(skip_begin + skip_count, ncols)])
+    ns = fwd_phase_slots(n_loc, keep.numel(), I_loc.shape[1], strip)
+    bounds = [keep.numel() * i // ns for i in range(ns + 1)]
+    strips = {None: (0, 1), "img": (0,), "txt": (1,)}[strip]
     for sl in range(ns):
-        lo, hi = bounds[sl], bounds[sl + 1]
-        part = []
-        for strip, (A, B) in enumerate(((I_loc, T_cols), (T_loc, I_cols))):
-            cos = A.float() @ B[lo:hi].float().t()
+        cols = keep[bounds[sl]:bounds[sl + 1]]
+        entry = st["slots"].setdefault(slot_begin + sl, {})
+        for k in strips:
+            A, B = ((I_loc, T_cols), (T_loc, I_cols))[k]
+            assert k not in entry, "a slot half was written twice"
+            cos = A.float() @ B[cols].float().t()
             t = cos * (s * math.log2(math.e))
             m = t.max(dim=1).values
             e = torch.exp2(t - m[:, None])
-            bv, bi = cos.max(dim=1)
-            part.append((m, e.sum(1), (e * cos).sum(1), bv, bi + lo + col_global_begin))
+            bv, bj = cos.max(dim=1)
+            entry[k] = (m, e.sum(1), (e * cos).sum(1), bv, cols[bj] + col_global_begin)
             lab = torch.arange(n_loc) + label_begin - col_global_begin
-            ok = (lab >= lo) & (lab < hi)
-            rows = torch.nonzero(ok).squeeze(1)
-            st["diag"][strip, rows] = cos[rows, lab[rows] - lo]
-        st["slots"][slot_begin + sl] = part
+            pos = torch.full((ncols + 1,), -1, dtype=torch.long)
+            pos[cols] = torch.arange(cols.numel())
+            where = pos[lab.clamp(0, ncols)]
+            where[(lab < 0) | (lab >= ncols)] = -1
+            rows = torch.nonzero(where >= 0).squeeze(1)
+            st["diag"][k, rows] = cos[rows, where[rows]]
+
+
+def smooth_stats(I32, T32):
+    return torch.cat([I32.sum(0), T32.sum(0), (I32 * T32).sum().reshape(1)])
+
+
+def smooth_bwd(dI, dT, I_rows, T_rows, stats, s_dev, grad_out, coef, inv_n):
+    D = dI.shape[1]
+    a = float(grad_out) * float(s_dev) * coef
+    dI += a * T_rows - a * inv_n * stats[D:2 * D]
+    dT += a * I_rows - a * inv_n * stats[:D]
 
 
 def fwd_finalize(n_loc, total_slots, label_begin, s_dev, with_acc, ws):
     st = STATE.pop(ws.data_ptr())
-    assert sorted(st["slots"]) == list(range(total_slots)), "a slot was skipped or written twice"
+    assert sorted(st["slots"]) == list(range(total_slots)), "a slot was skipped"
+    assert all(sorted(e) == [0, 1] for e in st["slots"].values()), "a slot half was left unwritten"
     s = float(s_dev)
     lse = torch.empty(2, n_loc)
     sc = torch.zeros(8)

@@ -14,6 +14,8 @@ at module load, and `Tensor.cuda` -> identity because `get_loss` hard-codes `.cu
   loss_accum_*.npz   get_loss on the gradient-accumulation path (train.py:34-51)
   tail_*.npz         CLIP.forward normalise lines + get_similarity (model.py:412-431)
   topk_*.npz         make_topk_predictions.py / _tr.py run as scripts on small JSONL files
+  lora_loss_*.npz    train_lora.py `contrastive_loss` (label-smoothed InfoNCE), value + gradients
+                     (third shim: a stub `lmdb` module, which train_lora.py imports at load)
 
 Nothing in the test-suite reads /root/reference: tests only read the .npz files written here.
 """
@@ -248,8 +250,33 @@ def gen_topk():
         print("topk", name, t2i[0])
 
 
+def gen_lora_loss():
+    """train_lora.py:95-110 imported from the reference (its module-level `import lmdb` is stubbed:
+    only the dataset class uses it)."""
+    sys.modules.setdefault("lmdb", types.ModuleType("lmdb"))
+    import train_lora
+    cases = {"a": (96, 64, 11, 0.5, 1 / 0.07, 0.05), "b": (300, 128, 12, 0.0, 20.0, 0.1),
+             "c": (257, 72, 13, 0.5, 100.0, 0.05), "d": (64, 512, 14, 0.5, 1.0, 0.3)}
+    for name, (n, d, seed, corr, scale, eps) in cases.items():
+        img, txt = synth(n, d, seed, corr)
+        g = torch.Generator().manual_seed(seed + 100)
+        # un-normalised inputs: the function normalises them itself (train_lora.py:97-98)
+        img = (img * (0.5 + torch.rand(n, 1, generator=g))).requires_grad_(True)
+        txt = (txt * (0.5 + 2 * torch.rand(n, 1, generator=g))).requires_grad_(True)
+        sc = torch.tensor(scale, requires_grad=True)
+        loss = train_lora.contrastive_loss(img, txt, sc, label_smoothing=eps)
+        loss.backward()
+        np.savez(HERE / f"lora_loss_{name}.npz", img=np_(img), txt=np_(txt), scale=np.float32(scale),
+                 eps=np.float32(eps), loss=np_(loss), dI=np_(img.grad), dT=np_(txt.grad), ds=np_(sc.grad))
+        print("lora_loss", name, float(loss))
+
+
 if __name__ == "__main__":
     install_shims()
+    if len(sys.argv) > 1 and sys.argv[1] == "lora":
+        gen_lora_loss()
+        sys.exit(0)
+    gen_lora_loss()
     gen_loss_w1()
     gen_loss_accum()
     gen_tail()

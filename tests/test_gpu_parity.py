@@ -230,7 +230,8 @@ def test_rank_strip_kernels_vs_oracle(dev, W, rank, gwg):
 
 
 @pytest.mark.parametrize("W,rank", [(4, 0), (4, 2), (3, 2)])
-def test_rank_strip_with_skipped_local_tiles(dev, W, rank):
+@pytest.mark.parametrize("split_strips", [False, True])
+def test_rank_strip_with_skipped_local_tiles(dev, W, rank, split_strips):
     """Tile-aligned local block (n_loc % 256 == 0): loss.py sweeps the gathered buffer in ONE phase
     that skips the local tiles (they were covered by the local phase)."""
     from nans_clip_b200 import kernels as K
@@ -242,12 +243,19 @@ def test_rank_strip_with_skipped_local_tiles(dev, W, rank):
     lo, hi = rank * n_loc, (rank + 1) * n_loc
     s_dev = torch.tensor([s], device=dev)
     n_other = W * n_loc - n_loc
-    slots = [K.fwd_phase_slots(n_loc, n_loc, d), K.fwd_phase_slots(n_loc, n_other, d)]
+    slots = [K.fwd_phase_slots(n_loc, n_loc, d),
+             K.fwd_phase_slots(n_loc, n_other, d, "img" if split_strips else None)]
+    if split_strips:
+        assert slots[1] == K.fwd_phase_slots(n_loc, n_other, d, "txt")
     ws = K.fwd_workspace(n_loc, sum(slots), dev)
     K.fwd_phase(I16[lo:hi], T16[lo:hi], T16[lo:hi], I16[lo:hi], col_global_begin=lo, label_begin=lo, s_dev=s_dev,
                 with_acc=True, ws=ws, slot_begin=0)
-    K.fwd_phase(I16[lo:hi], T16[lo:hi], T16, I16, col_global_begin=0, label_begin=lo, s_dev=s_dev,
-                with_acc=True, ws=ws, slot_begin=slots[0], skip_begin=lo, skip_count=n_loc)
+    # split: one launch per strip (what loss.py does while the second gather is in flight); the
+    # operand a strip does not read is poisoned
+    bad = torch.full_like(T16, float("nan"))
+    for strip, tc, ic in ([("img", T16, bad), ("txt", bad, I16)] if split_strips else [(None, T16, I16)]):
+        K.fwd_phase(I16[lo:hi], T16[lo:hi], tc, ic, col_global_begin=0, label_begin=lo, s_dev=s_dev,
+                    with_acc=True, ws=ws, slot_begin=slots[0], skip_begin=lo, skip_count=n_loc, strip=strip)
     lse, sc, _ = K.fwd_finalize(n_loc, sum(slots), lo, s_dev, True, ws)
     LN2 = math.log(2.0)
     assert torch.allclose(lse[0].cpu() * LN2, glob["lse_img"][lo:hi], rtol=1e-5, atol=1e-4)
@@ -306,8 +314,57 @@ def test_get_loss_dropin_signature_and_values(dev, golden_dir):
     assert abs(float(model.logit_scale.grad) - float(g["dlogit_scale_log"])) <= TOL * abs(float(g["dlogit_scale_log"]))
     args.report_training_batch_acc = False
     assert get_loss(model, None, None, nn.CrossEntropyLoss(), nn.CrossEntropyLoss(), args)[1] is None
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(NotImplementedError):   # the two criteria must agree
         get_loss(model, None, None, nn.CrossEntropyLoss(label_smoothing=0.05), nn.CrossEntropyLoss(), args)
+    with pytest.raises(NotImplementedError):
+        get_loss(model, None, None, nn.CrossEntropyLoss(reduction="sum"), nn.CrossEntropyLoss(reduction="sum"), args)
+    # label-smoothed criteria (the CE of train_lora.py:105-108 plugged into get_loss)
+    from oracle import clip_loss as OL
+    eps = 0.1
+    s = float(np.exp(g["logit_scale_log"]))
+    want = OL.global_smoothed_loss_and_grads(torch.from_numpy(g["img"]), torch.from_numpy(g["txt"]), s, eps, torch.float64)
+    model.zero_grad()
+    total, _ = get_loss(model, None, None, nn.CrossEntropyLoss(label_smoothing=eps),
+                        nn.CrossEntropyLoss(label_smoothing=eps), args)
+    total.backward()
+    n = g["img"].shape[0]
+    assert abs(float(total) - float(want["loss"])) <= TOL * float(want["loss"])
+    assert grad_ok(model.img.grad.cpu(), want["dI"], n, s) and grad_ok(model.txt.grad.cpu(), want["dT"], n, s)
+    assert abs(float(model.logit_scale.grad) - s * float(want["ds"])) <= TOL * abs(s * float(want["ds"])) + 1e-7
+
+
+@pytest.mark.parametrize("name", ["a", "b", "c", "d"])
+def test_lora_contrastive_loss_matches_reference(dev, golden_dir, name):
+    """Golden outputs of the reference's train_lora.py `contrastive_loss` (normalise + label-smoothed
+    InfoNCE) against the drop-in: kernel (1) + fused loss + smoothing kernels, all with backward."""
+    from nans_clip_b200.train_lora import contrastive_loss
+    g = np.load(golden_dir / f"lora_loss_{name}.npz")
+    img = torch.from_numpy(g["img"]).to(dev).requires_grad_(True)
+    txt = torch.from_numpy(g["txt"]).to(dev).requires_grad_(True)
+    sc = torch.tensor(float(g["scale"]), device=dev, requires_grad=True)
+    loss = contrastive_loss(img, txt, sc, label_smoothing=float(g["eps"]))
+    loss.backward()
+    assert loss.dim() == 0
+    assert abs(float(loss) - float(g["loss"])) <= TOL * abs(float(g["loss"]))
+    n, s = img.shape[0], float(g["scale"])
+    # gradients w.r.t. the UN-normalised features: the normalise backward divides by the row norms
+    # (0.5 .. 2.5 here), so the absolute floor of grad_ok is scaled by the largest 1 / norm
+    inv = float(1.0 / torch.from_numpy(g["img"]).norm(dim=-1).min())
+    for got, want in ((img.grad, g["dI"]), (txt.grad, g["dT"])):
+        want = torch.from_numpy(want)
+        err = float((got.cpu().double() - want.double()).norm())
+        assert err <= TOL * float(want.double().norm()) + 3e-5 * s / (2 * n) * math.sqrt(n) * 2 * inv
+    assert abs(float(sc.grad) - float(g["ds"])) <= TOL * abs(float(g["ds"])) + 1e-6
+
+
+def test_label_smoothing_zero_is_plain_and_range_checked(dev):
+    from nans_clip_b200.loss import clip_contrastive_loss
+    I, T = synth(300, 64, 5, 0.5)
+    a = clip_contrastive_loss(I.to(dev), T.to(dev), torch.tensor(10.0, device=dev))[0]
+    b = clip_contrastive_loss(I.to(dev), T.to(dev), torch.tensor(10.0, device=dev), label_smoothing=0.0)[0]
+    assert float(a) == float(b)
+    with pytest.raises(ValueError):
+        clip_contrastive_loss(I.to(dev), T.to(dev), torch.tensor(10.0, device=dev), label_smoothing=1.0)
 
 
 def test_full_size_properties(dev):

@@ -75,6 +75,83 @@ def test_distributed_loss_matches_reference(name, port):
         assert all(ok), f"rank {rank}: {ok} {info}"
 
 
+def _smoothing_worker(rank, W, port, gwg, q):
+    """Label smoothing across ranks: the column sums / diagonal sum are all-reduced, the fix-up uses
+    the global sums and the rank's rows (oracle: smoothed CE on the concatenated batch)."""
+    try:
+        _init(rank, W, port)
+        from nans_clip_b200.loss import clip_contrastive_loss
+        from oracle import clip_loss as OL
+        n_loc, D, s, eps = 40, 24, 15.0, 0.1
+        gen = torch.Generator().manual_seed(5)
+        img = torch.nn.functional.normalize(torch.randn(W * n_loc, D, generator=gen), dim=-1)
+        txt = torch.nn.functional.normalize(img + 0.7 * torch.randn(W * n_loc, D, generator=gen), dim=-1)
+        want = OL.global_smoothed_loss_and_grads(img, txt, s, eps, torch.float64)
+        sl = slice(rank * n_loc, (rank + 1) * n_loc)
+        I = img[sl].clone().requires_grad_(True)
+        T = txt[sl].clone().requires_grad_(True)
+        sc = torch.tensor(s, requires_grad=True)
+        loss, _ = clip_contrastive_loss(I, T, sc, group=dist.group.WORLD, gather_with_grad=gwg,
+                                        feat_dtype=torch.float32, label_smoothing=eps)
+        loss.backward()
+        mult = float(W) if gwg else 1.0
+        ok = [abs(float(loss) - float(want["loss"])) <= 1e-5 * abs(float(want["loss"]))]
+        for got, w in ((I.grad, want["dI"][sl]), (T.grad, want["dT"][sl])):
+            ok.append(float((got.double() - mult * w.double()).abs().max()) <= 1e-4 * mult * float(w.abs().max()))
+        ok.append(abs(float(sc.grad) - float(want["ds"])) <= 1e-4 * abs(float(want["ds"])) + 1e-9)
+        q.put((rank, ok, float(loss)))
+        dist.barrier()
+        dist.destroy_process_group()
+    except Exception:
+        import traceback
+        q.put((rank, [False], traceback.format_exc()))
+
+
+@pytest.mark.parametrize("gwg,port", [(False, 29721), (True, 29722)])
+def test_label_smoothing_under_gloo(gwg, port):
+    for rank, ok, info in _spawn(_smoothing_worker, 2, port, gwg):
+        assert all(ok), f"rank {rank}: {ok} {info}"
+
+
+def _strip_split_worker(rank, W, port, gwg, q):
+    """n_loc = 256: the tile-aligned path (local block, then one single-strip launch per gathered
+    tensor sharing their slots) against the oracle on the concatenated batch."""
+    try:
+        _init(rank, W, port)
+        from nans_clip_b200.loss import clip_contrastive_loss
+        from oracle import clip_loss as OL
+        n_loc, D, s = 256, 32, 20.0
+        gen = torch.Generator().manual_seed(99)
+        base = torch.randn(W * n_loc, D, generator=gen)
+        img = torch.nn.functional.normalize(0.5 * base + 0.5 * torch.randn(W * n_loc, D, generator=gen), dim=-1)
+        txt = torch.nn.functional.normalize(0.5 * base + 0.5 * torch.randn(W * n_loc, D, generator=gen), dim=-1)
+        want = OL.global_loss_and_grads(img, txt, s, torch.float64)
+        sl = slice(rank * n_loc, (rank + 1) * n_loc)
+        I = img[sl].clone().requires_grad_(True)
+        T = txt[sl].clone().requires_grad_(True)
+        sc = torch.tensor(s, requires_grad=True)
+        loss, acc = clip_contrastive_loss(I, T, sc, group=dist.group.WORLD, gather_with_grad=gwg,
+                                          report_acc=True, feat_dtype=torch.float32)
+        loss.backward()
+        mult = float(W) if gwg else 1.0
+        ok = [abs(float(loss) - float(want["loss"])) <= 1e-5 * abs(float(want["loss"]))]
+        for got, w in ((I.grad, want["dI"][sl]), (T.grad, want["dT"][sl])):
+            ok.append(float((got.double() - mult * w.double()).abs().max()) <= 1e-4 * mult * float(w.abs().max()))
+        ok.append(abs(float(sc.grad) - float(want["ds"])) <= 1e-4 * abs(float(want["ds"])) + 1e-9)
+        q.put((rank, ok, float(loss)))
+        dist.barrier()
+        dist.destroy_process_group()
+    except Exception:
+        import traceback
+        q.put((rank, [False], traceback.format_exc()))
+
+
+@pytest.mark.parametrize("gwg,port", [(False, 29711), (True, 29712)])
+def test_tile_aligned_strip_split_path(gwg, port):
+    for rank, ok, info in _spawn(_strip_split_worker, 2, port, gwg):
+        assert all(ok), f"rank {rank}: {ok} {info}"
+
+
 def _topk_worker(rank, W, port, q):
     try:
         _init(rank, W, port)

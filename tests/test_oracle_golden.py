@@ -151,6 +151,36 @@ def test_analytic_known_answers():
     assert abs(float(OL.local_loss(x, x, torch.tensor(s))[0]) - want) < 1e-5
 
 
+@pytest.mark.parametrize("name", ["a", "b", "c", "d"])
+def test_lora_label_smoothed_loss_matches_reference(golden_dir, name):
+    """train_lora.py:95-110 run from the reference itself -> oracle restatement, and the O(N D)
+    decomposition the CUDA path relies on (csrc/smooth.cu): smoothed = plain + closed-form terms."""
+    g = np.load(golden_dir / f"lora_loss_{name}.npz")
+    img = torch.from_numpy(g["img"]).requires_grad_(True)
+    txt = torch.from_numpy(g["txt"]).requires_grad_(True)
+    sc = torch.tensor(float(g["scale"]), requires_grad=True)
+    eps = float(g["eps"])
+    loss = OL.lora_contrastive_loss(img, txt, sc, eps)
+    loss.backward()
+    assert abs(float(loss) - float(g["loss"])) <= 1e-6 * abs(float(g["loss"]))
+    assert torch.allclose(img.grad, torch.from_numpy(g["dI"]), rtol=1e-4, atol=1e-7)
+    assert torch.allclose(txt.grad, torch.from_numpy(g["dT"]), rtol=1e-4, atol=1e-7)
+    assert abs(float(sc.grad) - float(g["ds"])) <= 1e-4 * abs(float(g["ds"])) + 1e-8
+    # decomposition on normalised features (fp64)
+    I = OL.normalize(img.detach().double())
+    T = OL.normalize(txt.detach().double())
+    s, n = float(sc), I.shape[0]
+    plain = OL.global_loss_and_grads(I, T, s, torch.float64)
+    smooth = OL.global_smoothed_loss_and_grads(I, T, s, eps, torch.float64)
+    isum, tsum, diag = I.sum(0), T.sum(0), (I * T).sum()
+    corr = eps / n * diag - eps / n ** 2 * (isum @ tsum)
+    assert abs(float(plain["loss"] + s * corr) - float(smooth["loss"])) < 1e-10
+    assert abs(float(plain["ds"] + corr) - float(smooth["ds"])) < 1e-10
+    assert torch.allclose(plain["dI"] + s * eps / n * T - s * eps / n ** 2 * tsum, smooth["dI"], atol=1e-12)
+    assert torch.allclose(plain["dT"] + s * eps / n * I - s * eps / n ** 2 * isum, smooth["dT"], atol=1e-12)
+    assert abs(float(smooth["loss"]) - float(g["loss"])) <= 1e-5 * abs(float(g["loss"]))
+
+
 def test_all_fixtures_are_covered(golden_dir):
     names = sorted(p.split("/")[-1] for p in glob.glob(str(golden_dir / "*.npz")))
-    assert len(names) == 18, names
+    assert len(names) == 22, names
