@@ -9,6 +9,9 @@ The per-query GEMV + Python sort of the reference (:71-85) is replaced by the fu
 top-k kernel; `--eval-batch-size` is kept for compatibility and bounds the QUERY block here (the
 gallery is resident in HBM once instead of being re-uploaded per query).
 
+Either feature file may also be a binary shard written by `feature_io`: no JSON
+parsing, memory-mapped, and a stored 16-bit copy of the matching type is used as the operand as is.
+
 Launched under torchrun (WORLD_SIZE > 1) the gallery is sharded over the ranks and rank 0 writes
 the output.  Extra, optional flags: --feat-dtype {fp16,bf16}, --k-cand {16,32}.
 """
@@ -43,21 +46,7 @@ def parse_args(argv=None):
     return parser.parse_args(argv)
 
 
-def load_jsonl_features(path, id_key):
-    """{"<id_key>": int, "feature": [floats]} per line -> (ids list, float32 [n, D] array)."""
-    ids, feats = [], []
-    with open(path, "r") as fin:
-        for line in fin:
-            line = line.strip()
-            if not line:
-                continue
-            obj = json.loads(line)
-            ids.append(obj[id_key])
-            feats.append(obj["feature"])
-    arr = np.array(feats, dtype=np.float32)
-    if arr.ndim != 2:
-        arr = arr.reshape(len(ids), -1)
-    return ids, arr
+from .feature_io import DT16_BF16, DT16_F16, load_features, load_jsonl_features  # noqa: F401  (re-export)
 
 
 def run(args, query_key=QUERY_KEY, query_path=None, gallery_key=GALLERY_KEY, gallery_path=None,
@@ -80,11 +69,12 @@ def run(args, query_key=QUERY_KEY, query_path=None, gallery_key=GALLERY_KEY, gal
         group = dist.group.WORLD
 
     log(f"Begin to load {GALLERY_NAME if gallery_key == GALLERY_KEY else 'gallery'} features...")
-    gallery_ids, gallery = load_jsonl_features(gallery_path, gallery_key)
+    gallery_ids, gallery, gallery16, g16_code = load_features(gallery_path, gallery_key)
     log("Finished loading features.")
     G = len(gallery_ids)
     lo, hi = (G * rank) // world, (G * (rank + 1)) // world
-    query_ids, queries = load_jsonl_features(query_path, query_key)
+    query_ids, queries, _, _ = load_features(query_path, query_key)
+    queries = np.ascontiguousarray(queries)
     k = min(args.top_k, 32)
     if args.top_k > 32:
         raise ValueError("--top-k above 32 is not supported by the fused kernel")
@@ -93,21 +83,25 @@ def run(args, query_key=QUERY_KEY, query_path=None, gallery_key=GALLERY_KEY, gal
     log(f"Begin to compute top-{args.top_k} predictions...")
     positions = []
     qb = max(int(args.eval_batch_size), 1)
-    shard = torch.from_numpy(gallery[lo:hi])
+    shard = torch.from_numpy(np.ascontiguousarray(gallery[lo:hi]))
+    shard16 = None
+    if gallery16 is not None and g16_code == (DT16_F16 if feat_dtype == torch.float16 else DT16_BF16):
+        shard16 = torch.from_numpy(np.ascontiguousarray(gallery16[lo:hi]).view(np.int16)).view(feat_dtype)
     if queries.shape[0] > 0 and G > 0:
         if group is None:
             from ..retrieval import GalleryShard
-            gs = GalleryShard(shard, None, feat_dtype, lo)
+            gs = GalleryShard(shard, None, feat_dtype, lo, gallery16=shard16)
             _, idx = gs.search(torch.from_numpy(queries), k, args.k_cand, query_block=qb)
         else:
             _, idx = topk_retrieve(torch.from_numpy(queries), shard, k, k_cand=args.k_cand, group=group,
-                                   index_offset=lo, feat_dtype=feat_dtype)
+                                   index_offset=lo, feat_dtype=feat_dtype, gallery16=shard16)
         positions = idx.cpu().numpy()
     if rank == 0:
         with open(args.output, "w") as fout:
             for qi, qid in enumerate(query_ids):
                 row = positions[qi] if len(positions) else []
-                ids = [gallery_ids[int(p)] for p in row if int(p) >= 0]
+                ids = [int(gallery_ids[int(p)]) for p in row if int(p) >= 0]
+                qid = int(qid) if isinstance(qid, np.integer) else qid
                 fout.write("{}\n".format(json.dumps({out_query_key: qid, out_list_key: ids})))
         log("Top-{} predictions are saved in {}".format(args.top_k, args.output))
     if group is not None:

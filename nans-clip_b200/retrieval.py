@@ -37,13 +37,19 @@ class GalleryShard:
     (tensor-core candidate pass).  Build once, query many times."""
 
     def __init__(self, gallery: torch.Tensor, device=None, feat_dtype: torch.dtype = torch.float16,
-                 index_offset: int = 0):
+                 index_offset: int = 0, gallery16: Optional[torch.Tensor] = None):
+        """`gallery16`: an existing 16-bit copy of `gallery` in `feat_dtype` (e.g. from a binary
+        feature shard, eval/feature_io.py); made by kernel (1) when absent."""
         device = torch.device(device) if device is not None else (
             gallery.device if gallery.is_cuda else torch.device("cuda", torch.cuda.current_device()))
         self.g32 = gallery.to(device=device, dtype=torch.float32, non_blocking=True).contiguous()
         self.feat_dtype = feat_dtype
         self.index_offset = int(index_offset)
-        if self.g32.shape[0] > 0:
+        if gallery16 is not None:
+            if gallery16.dtype != feat_dtype or gallery16.shape != gallery.shape:
+                raise ValueError("gallery16 must have the gallery's shape and dtype feat_dtype")
+            self.g16 = gallery16.to(device=device, non_blocking=True).contiguous()
+        elif self.g32.shape[0] > 0:
             self.g16, _, _ = K.l2norm_cast(self.g32, feat_dtype, normalize=False)
         else:
             self.g16 = torch.empty_like(self.g32, dtype=feat_dtype)
@@ -74,14 +80,15 @@ class GalleryShard:
 
 def topk_retrieve(queries: torch.Tensor, gallery_shard: torch.Tensor, k: int = 10, *,
                   k_cand: Optional[int] = None, group=None, index_offset: Optional[int] = None,
-                  feat_dtype: torch.dtype = torch.float16, device=None):
+                  feat_dtype: torch.dtype = torch.float16, device=None,
+                  gallery16: Optional[torch.Tensor] = None):
     """Global top-k of `queries` against the gallery whose local shard is `gallery_shard`.
 
     Without `group`: single GPU, `index_offset` (default 0) is added to the returned positions.
     With `group`: rank r passes its contiguous shard; offsets default to the exclusive prefix sum
     of the shard sizes in rank order.  Every rank returns the merged global result."""
     if group is None:
-        shard = GalleryShard(gallery_shard, device, feat_dtype, index_offset or 0)
+        shard = GalleryShard(gallery_shard, device, feat_dtype, index_offset or 0, gallery16=gallery16)
         return shard.search(queries, k, k_cand)
     W, rank = dist.get_world_size(group), dist.get_rank(group)
     dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
@@ -90,7 +97,7 @@ def topk_retrieve(queries: torch.Tensor, gallery_shard: torch.Tensor, k: int = 1
         sizes[rank] = gallery_shard.shape[0]
         dist.all_reduce(sizes, group=group)
         index_offset = int(sizes[:rank].sum().item())
-    shard = GalleryShard(gallery_shard, dev, feat_dtype, index_offset)
+    shard = GalleryShard(gallery_shard, dev, feat_dtype, index_offset, gallery16=gallery16)
     s, i = shard.search(queries, k, k_cand)
     Qn = s.shape[0]
     all_s = torch.empty((W * Qn, k), dtype=s.dtype, device=dev)

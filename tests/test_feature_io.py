@@ -1,0 +1,87 @@
+"""Binary feature shards: host-side format logic, no GPU."""
+import json
+import os
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+
+from nans_clip_b200.eval import feature_io as fio  # noqa: E402
+
+
+def _rows(n, d, seed=0):
+    rng = np.random.default_rng(seed)
+    return np.arange(n, dtype=np.int64) * 3 + 1000000, rng.standard_normal((n, d)).astype(np.float32)
+
+
+@pytest.mark.parametrize("n,d", [(0, 8), (1, 8), (7, 16), (1000, 72)])
+@pytest.mark.parametrize("with16", [False, True])
+def test_round_trip(tmp_path, n, d, with16):
+    ids, f32 = _rows(n, d)
+    f16 = f32.astype(np.float16).view(np.uint16) if with16 else None
+    p = str(tmp_path / "a.nansf")
+    fio.write_shard(p, ids, f32, f16, fio.DT16_F16 if with16 else fio.DT16_NONE, normalized=True)
+    assert fio.is_shard(p)
+    for mmap in (True, False):
+        i2, a32, a16, h = fio.read_shard(p, mmap=mmap)
+        assert h == {"rows": n, "D": d, "dtype16": fio.DT16_F16 if with16 else 0, "normalized": True}
+        assert np.array_equal(np.asarray(i2), ids) and np.array_equal(np.asarray(a32), f32)
+        assert (a16 is None) == (not with16)
+        if with16:
+            assert np.array_equal(np.asarray(a16), f16)
+    # every section is 64-byte aligned and the file has no tail
+    off_ids, off_f32, off_f16, end = fio._layout(n, d, fio.DT16_F16 if with16 else 0)
+    assert off_ids % 64 == 0 and off_f32 % 64 == 0 and off_f16 % 64 == 0 and os.path.getsize(p) == end
+
+
+def test_jsonl_compat_and_conversion(tmp_path):
+    ids, f32 = _rows(33, 24, 1)
+    j = tmp_path / "f.jsonl"
+    with open(j, "w") as f:
+        for i, r in zip(ids.tolist(), f32.tolist()):
+            f.write(json.dumps({"image_id": i, "feature": r}) + "\n")
+        f.write("\n")  # blank lines are skipped like the reference's strip()
+    a_ids, a32, a16, code = fio.load_features(str(j), "image_id")
+    assert a_ids == ids.tolist() and np.allclose(a32, f32, atol=0) and a16 is None and code == 0
+    s = tmp_path / "f.nansf"
+    assert fio.jsonl_to_shard(str(j), "image_id", str(s)) == 33
+    b_ids, b32, b16, code = fio.load_features(str(s), "image_id")
+    assert np.array_equal(np.asarray(b_ids), ids) and np.array_equal(np.asarray(b32), a32) and b16 is None
+    assert not fio.is_shard(str(j)) and not fio.is_shard(str(tmp_path / "missing"))
+
+
+def test_bad_files_are_rejected(tmp_path):
+    ids, f32 = _rows(10, 8)
+    p = str(tmp_path / "a.nansf")
+    fio.write_shard(p, ids, f32)
+    raw = open(p, "rb").read()
+    open(tmp_path / "trunc.nansf", "wb").write(raw[:-16])
+    with pytest.raises(ValueError, match="truncated"):
+        fio.read_shard(str(tmp_path / "trunc.nansf"))
+    open(tmp_path / "ver.nansf", "wb").write(raw[:8] + (99).to_bytes(4, "little") + raw[12:])
+    with pytest.raises(ValueError, match="version"):
+        fio.read_shard(str(tmp_path / "ver.nansf"))
+    open(tmp_path / "magic.nansf", "wb").write(b"XXXXXXXX" + raw[8:])
+    with pytest.raises(ValueError, match="magic"):
+        fio.read_header(str(tmp_path / "magic.nansf"))
+    with pytest.raises(ValueError):
+        fio.write_shard(p, ids[:5], f32)                       # row mismatch
+    with pytest.raises(ValueError):
+        fio.write_shard(p, ids, f32, f32.astype(np.float16).view(np.uint16))  # feat16 without its dtype
+
+
+def test_shard_slices_are_rank_shards(tmp_path):
+    """A contiguous row range of the mmap is what a rank of the sharded retrieval loads."""
+    ids, f32 = _rows(101, 16, 2)
+    p = str(tmp_path / "g.nansf")
+    fio.write_shard(p, ids, f32, f32.astype(np.float16).view(np.uint16), fio.DT16_F16)
+    _, a32, a16, _ = fio.read_shard(p)
+    W = 4
+    parts = [np.ascontiguousarray(a32[101 * r // W:101 * (r + 1) // W]) for r in range(W)]
+    assert np.array_equal(np.concatenate(parts), f32)
+    assert np.array_equal(np.concatenate([np.asarray(a16[101 * r // W:101 * (r + 1) // W]) for r in range(W)]).view(np.float16),
+                          f32.astype(np.float16))

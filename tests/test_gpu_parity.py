@@ -522,6 +522,49 @@ def test_cli_dropin_writes_the_reference_output(dev, golden_dir, tmp_path):
     assert [o["text_ids"] for o in got] == g["i2t_text_ids"].tolist()
 
 
+def test_cli_reads_binary_feature_shards(dev, golden_dir, tmp_path):
+    """the same CLI on binary shards (converted JSONL, and a shard written by the
+    device-side FeatureWriter with a stored fp16 copy) gives the reference's output."""
+    from nans_clip_b200.eval import feature_io as fio, make_topk_predictions as t2i
+    g = np.load(golden_dir / "topk_b.npz")
+    fi, ft = tmp_path / "img.jsonl", tmp_path / "txt.jsonl"
+    with open(fi, "w") as f:
+        for iid, feat in zip(g["image_ids"].tolist(), g["gallery"].tolist()):
+            f.write(json.dumps({"image_id": iid, "feature": feat}) + "\n")
+    with open(ft, "w") as f:
+        for tid, feat in zip(g["text_ids"].tolist(), g["queries"].tolist()):
+            f.write(json.dumps({"text_id": tid, "feature": feat}) + "\n")
+    si, st = tmp_path / "img.nansf", tmp_path / "txt.nansf"
+    assert fio.jsonl_to_shard(str(fi), "image_id", str(si)) == len(g["image_ids"])
+    fio.main(["--input", str(ft), "--id-key", "text_id", "--output", str(st)])
+    # device-side writer: un-normalised rows in, normalised fp32 + fp16 out, in two appends
+    gal = torch.from_numpy(g["gallery"]).to(dev)
+    scale = 0.5 + torch.rand(gal.shape[0], 1, device=dev)
+    sw = tmp_path / "img_w.nansf"
+    with fio.FeatureWriter(str(sw), D=gal.shape[1], capacity=gal.shape[0] + 5, feat_dtype=torch.float16) as w:
+        h = gal.shape[0] // 3
+        w.append(g["image_ids"][:h], (gal * scale)[:h])
+        w.append(torch.from_numpy(g["image_ids"][h:]), (gal * scale)[h:])
+    ids, f32, f16, hd = fio.read_shard(str(sw))
+    assert hd == {"rows": gal.shape[0], "D": gal.shape[1], "dtype16": fio.DT16_F16, "normalized": True}
+    assert np.array_equal(ids, g["image_ids"])
+    want = torch.nn.functional.normalize(gal * scale, dim=-1).cpu()
+    assert torch.allclose(torch.from_numpy(np.array(f32)), want, atol=2e-7)
+    assert torch.equal(torch.from_numpy(np.array(f16).view(np.int16)).view(torch.float16),
+                       torch.from_numpy(np.array(f32)).half())
+    for gpath in (si, sw):
+        out = tmp_path / "out.jsonl"
+        t2i.main(["--image-feats", str(gpath), "--text-feats", str(st), "--top-k", "10",
+                  "--eval-batch-size", "64", "--output", str(out)])
+        got = [json.loads(l) for l in open(out)]
+        assert [o["text_id"] for o in got] == g["t2i_text_ids"].tolist()
+        if gpath == si:   # identical rows -> identical lists; the re-normalised shard only changes scores by ulps
+            assert [o["image_ids"] for o in got] == g["t2i_image_ids"].tolist()
+        else:
+            same = sum(a["image_ids"] == b for a, b in zip(got, g["t2i_image_ids"].tolist()))
+            assert same >= 0.95 * len(got)
+
+
 def test_topk_full_gallery_properties(dev):
     """G = 1e6 (BASELINE config 5 gallery), 2048 queries: checked against an fp32 GEMM + sort on
     the device in blocks (the checker), plus structural properties."""
