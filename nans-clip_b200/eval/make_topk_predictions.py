@@ -74,7 +74,7 @@ def run(args, query_key=QUERY_KEY, query_path=None, gallery_key=GALLERY_KEY, gal
     G = len(gallery_ids)
     lo, hi = (G * rank) // world, (G * (rank + 1)) // world
     query_ids, queries, _, _ = load_features(query_path, query_key)
-    queries = np.ascontiguousarray(queries)
+    queries = np.array(queries, dtype=np.float32)
     k = min(args.top_k, 32)
     if args.top_k > 32:
         raise ValueError("--top-k above 32 is not supported by the fused kernel")
@@ -83,10 +83,10 @@ def run(args, query_key=QUERY_KEY, query_path=None, gallery_key=GALLERY_KEY, gal
     log(f"Begin to compute top-{args.top_k} predictions...")
     positions = []
     qb = max(int(args.eval_batch_size), 1)
-    shard = torch.from_numpy(np.ascontiguousarray(gallery[lo:hi]))
+    shard = torch.from_numpy(np.array(gallery[lo:hi], dtype=np.float32))  # a writable copy of the mmap slice
     shard16 = None
     if gallery16 is not None and g16_code == (DT16_F16 if feat_dtype == torch.float16 else DT16_BF16):
-        shard16 = torch.from_numpy(np.ascontiguousarray(gallery16[lo:hi]).view(np.int16)).view(feat_dtype)
+        shard16 = torch.from_numpy(np.array(gallery16[lo:hi]).view(np.int16)).view(feat_dtype)
     if queries.shape[0] > 0 and G > 0:
         if group is None:
             from ..retrieval import GalleryShard

@@ -539,7 +539,7 @@ def test_cli_reads_binary_feature_shards(dev, golden_dir, tmp_path):
     fio.main(["--input", str(ft), "--id-key", "text_id", "--output", str(st)])
     # device-side writer: un-normalised rows in, normalised fp32 + fp16 out, in two appends
     gal = torch.from_numpy(g["gallery"]).to(dev)
-    scale = 0.5 + torch.rand(gal.shape[0], 1, device=dev)
+    scale = 0.5 + torch.rand(gal.shape[0], 1, device=dev, generator=torch.Generator(device=dev).manual_seed(3))
     sw = tmp_path / "img_w.nansf"
     with fio.FeatureWriter(str(sw), D=gal.shape[1], capacity=gal.shape[0] + 5, feat_dtype=torch.float16) as w:
         h = gal.shape[0] // 3
@@ -549,20 +549,21 @@ def test_cli_reads_binary_feature_shards(dev, golden_dir, tmp_path):
     assert hd == {"rows": gal.shape[0], "D": gal.shape[1], "dtype16": fio.DT16_F16, "normalized": True}
     assert np.array_equal(ids, g["image_ids"])
     want = torch.nn.functional.normalize(gal * scale, dim=-1).cpu()
-    assert torch.allclose(torch.from_numpy(np.array(f32)), want, atol=2e-7)
+    assert torch.allclose(torch.from_numpy(np.array(f32)), want, atol=1e-6)
     assert torch.equal(torch.from_numpy(np.array(f16).view(np.int16)).view(torch.float16),
                        torch.from_numpy(np.array(f32)).half())
+    from oracle import topk as OT
     for gpath in (si, sw):
         out = tmp_path / "out.jsonl"
         t2i.main(["--image-feats", str(gpath), "--text-feats", str(st), "--top-k", "10",
                   "--eval-batch-size", "64", "--output", str(out)])
         got = [json.loads(l) for l in open(out)]
         assert [o["text_id"] for o in got] == g["t2i_text_ids"].tolist()
-        if gpath == si:   # identical rows -> identical lists; the re-normalised shard only changes scores by ulps
+        if gpath == si:   # identical rows -> the reference script's own lists
             assert [o["image_ids"] for o in got] == g["t2i_image_ids"].tolist()
-        else:
-            same = sum(a["image_ids"] == b for a, b in zip(got, g["t2i_image_ids"].tolist()))
-            assert same >= 0.95 * len(got)
+        else:             # re-normalised rows: the oracle on exactly what the shard stores
+            _, pos = OT.topk_vectorised(torch.from_numpy(np.array(f32)), torch.from_numpy(g["queries"]), 10)
+            assert [o["image_ids"] for o in got] == g["image_ids"][pos.numpy()].tolist()
 
 
 def test_topk_full_gallery_properties(dev):
