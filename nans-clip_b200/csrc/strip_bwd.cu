@@ -94,6 +94,9 @@ struct BwdParams {
   int accumulate;           // 1: red.add into out (column splits), 0: plain stores
   const int* lse_minmax;    // [2] order-preserving int encodings of min / max of all lse values
   int debug;                // bring-up experiments (NANS_BWD_DEBUG): 1 = no exp in the softmax warps
+  int n_full, ns_tail;      // narrow pairs: units [0, n_full) sweep all columns, the rest are split ns_tail ways
+  long long total_tiles;    // persistent kernel: 2 * nrb * ntiles tile steps shared out over npairs CTA pairs
+  int npairs;
 };
 
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
@@ -965,17 +968,25 @@ clip_bwd_np_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
 
+  // units [0, n_full) fill whole waves of CTA pairs and sweep all columns with plain stores; the
+  // remaining units (a partial wave) are split ns_tail ways by columns and accumulate with red.add
   int unit = blockIdx.x >> 1;
-  const int split = unit % p.nsplit;
-  unit /= p.nsplit;
+  int split = 0, nsplit_u = 1;
+  if (unit >= p.n_full) {
+    const int j = unit - p.n_full;
+    unit = p.n_full + j / p.ns_tail;
+    split = j % p.ns_tail;
+    nsplit_u = p.ns_tail;
+  }
+  const bool accumulate = nsplit_u > 1;
   const int rb = unit % p.nrb;
   const int strip = unit / p.nrb;
 
   const CUtensorMap* tmA = strip == 0 ? &tmA0 : &tmA1;     // box [64 rows, 64 features]
   const CUtensorMap* tmBm = strip == 0 ? &tmBm0 : &tmBm1;  // box [128 rows, 64 features]
   const int row0 = p.row_begin + rb * 2 * NP_ROWS + static_cast<int>(rank) * NP_ROWS;
-  const int tile_begin = static_cast<int>(static_cast<long long>(split) * p.ntiles / p.nsplit);
-  const int tile_end = static_cast<int>(static_cast<long long>(split + 1) * p.ntiles / p.nsplit);
+  const int tile_begin = static_cast<int>(static_cast<long long>(split) * p.ntiles / nsplit_u);
+  const int tile_end = static_cast<int>(static_cast<long long>(split + 1) * p.ntiles / nsplit_u);
   const int ntiles = tile_end - tile_begin;
   const int n1 = (p.kchunks + 1) / 2;  // MMA1 stages per tile (2 chunks each)
   const int nfb = (p.kchunks + 3) / 4; // 256-feature blocks of dA; MMA2 stages per tile = 2 nfb
@@ -1228,19 +1239,396 @@ clip_bwd_np_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
             for (int k = 0; k < 32; k += 4) {
               const float a0 = __uint_as_float(r[k]) * coef, a1 = __uint_as_float(r[k + 1]) * coef;
               const float a2 = __uint_as_float(r[k + 2]) * coef, a3 = __uint_as_float(r[k + 3]) * coef;
-              if (p.accumulate) red_add_v4(out + f0 + k, a0, a1, a2, a3);
+              if (accumulate) red_add_v4(out + f0 + k, a0, a1, a2, a3);
               else *reinterpret_cast<float4*>(out + f0 + k) = make_float4(a0, a1, a2, a3);
             }
           } else {
 #pragma unroll
             for (int k = 0; k < 32; ++k)
               if (f0 + k < p.D) {
-                if (p.accumulate) atomicAdd(out + f0 + k, __uint_as_float(r[k]) * coef);
+                if (accumulate) atomicAdd(out + f0 + k, __uint_as_float(r[k]) * coef);
                 else out[f0 + k] = __uint_as_float(r[k]) * coef;
               }
           }
         }
       }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, TMEM_COLS);
+  }
+}
+
+// ================================================================================================
+// Persistent, load-balanced form of the narrow-pair kernel (NANS_BWD_PERSIST=1; not the default, see the dispatch).  The (strip, row block, tile)
+// space is linearised (row-block major, tiles inside) and cut into `npairs` equal contiguous ranges,
+// one per resident CTA pair, so that the SMs stay busy whatever 2 * nrb is (with one unit per CTA
+// pair, 64 units on 74 pairs leave 14 % of the machine idle at n_loc = 4096).  A pair's range
+// crosses row-block boundaries: each piece is a SEGMENT with its own A block, its own dA
+// accumulation and a red.add write-out; the MMA1 / softmax / MMA2 pipeline runs straight through
+// segment boundaries (MMA1 of the next segment's first tile is issued before MMA2 of the previous
+// segment's last tile).  Extra barriers: a_empty (A may be overwritten), da_empty (dA drained).
+struct NppCursor {
+  int strip, rb, tile, seg;
+  bool first, last;  // first / last tile of its segment
+};
+__device__ __forceinline__ NppCursor npp_begin(long long g0, long long nt, const BwdParams& p) {
+  NppCursor c;
+  const int unit = static_cast<int>(g0 / p.ntiles);
+  c.tile = static_cast<int>(g0 - static_cast<long long>(unit) * p.ntiles);
+  c.strip = unit / p.nrb;
+  c.rb = unit - c.strip * p.nrb;
+  c.seg = 0;
+  c.first = true;
+  c.last = (nt == 1) || (c.tile == p.ntiles - 1);
+  return c;
+}
+// advance to local tile t + 1 (t1 = t + 1 is the new local index)
+__device__ __forceinline__ void npp_next(NppCursor& c, long long t1, long long nt, const BwdParams& p) {
+  if (++c.tile == p.ntiles) {
+    c.tile = 0;
+    if (++c.rb == p.nrb) { c.rb = 0; ++c.strip; }
+  }
+  c.first = c.tile == 0;
+  if (c.first) ++c.seg;
+  c.last = (t1 == nt - 1) || (c.tile == p.ntiles - 1);
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+clip_bwd_npp_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmBm0,
+                    const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmBm1,
+                    const BwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* smA = smem;
+  uint8_t* smG = smA + static_cast<size_t>(p.kchunks) * NP_ACH;
+  uint8_t* smR = smG + static_cast<size_t>(NP_NG) * NP_GBUF;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smR + static_cast<size_t>(p.nr) * NP_STAGE);
+  {
+    uint32_t dyn;
+    asm volatile("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn));
+    if (reinterpret_cast<uint8_t*>(bars) + NP_BAR_BYTES > smem_raw + dyn) __trap();  // carve-up does not fit
+  }
+  uint64_t* fullR = bars;                 // leader only
+  uint64_t* emptyR = fullR + NP_MAXR;
+  uint64_t* a_full = emptyR + NP_MAXR;    // leader only
+  uint64_t* a_empty = a_full + 1;         // both CTAs (multicast commit)
+  uint64_t* s_full = a_empty + 1;         // [NP_NS]
+  uint64_t* g_ready = s_full + NP_NS;     // [NP_NS] leader only, 16 arrivals
+  uint64_t* g_empty = g_ready + NP_NS;    // [NP_NG]
+  uint64_t* da_full = g_empty + NP_NG;    // both CTAs (multicast commit)
+  uint64_t* da_empty = da_full + 1;       // leader only, 16 arrivals
+  uint64_t* b_full = da_empty + 1;        // [2]
+  uint64_t* b_empty = b_full + 2;         // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(b_empty + 2);
+  float* cfbuf = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + NP_CF_OFF);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  const long long pair = blockIdx.x >> 1;
+  const long long g0 = pair * p.total_tiles / p.npairs;
+  const long long nt = (pair + 1) * p.total_tiles / p.npairs - g0;  // >= 1 (host: npairs <= total_tiles)
+  const int n1 = (p.kchunks + 1) / 2;  // MMA1 stages per tile (2 chunks each)
+  const int nfb = (p.kchunks + 3) / 4; // 256-feature blocks of dA; MMA2 stages per tile = 2 nfb
+
+  if (warp == 0) {
+    if (elect_one()) {
+      tma_prefetch_desc(&tmA0);
+      tma_prefetch_desc(&tmBm0);
+      tma_prefetch_desc(&tmA1);
+      tma_prefetch_desc(&tmBm1);
+      for (int i = 0; i < NP_MAXR; ++i) { mbar_init(&fullR[i], 1); mbar_init(&emptyR[i], 1); }
+      mbar_init(a_full, 1);
+      mbar_init(a_empty, 1);
+      for (int i = 0; i < NP_NS; ++i) { mbar_init(&s_full[i], 1); mbar_init(&g_ready[i], 2 * SM_WARPS); }
+      for (int i = 0; i < NP_NG; ++i) mbar_init(&g_empty[i], 1);
+      mbar_init(da_full, 1);
+      mbar_init(da_empty, 2 * SM_WARPS);
+      for (int i = 0; i < 2; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], SM_WARPS); }
+      fence_barrier_init();
+    }
+  } else if (warp == 2) {
+    tmem_alloc_pair(tmem_ptr, TMEM_COLS);
+    tmem_relinquish_pair();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  float lse_mu;
+  bool factored;
+  {
+    int lo = __ldg(p.lse_minmax), hi = __ldg(p.lse_minmax + 1);
+    lo = lo >= 0 ? lo : lo ^ 0x7fffffff;
+    hi = hi >= 0 ? hi : hi ^ 0x7fffffff;
+    const float fmin = __int_as_float(lo), fmax = __int_as_float(hi);
+    factored = (fmax - fmin) < kFactorRange;
+    lse_mu = 0.5f * (fmax + fmin);
+  }
+
+  // schedule shared by producer and issuer: step tau: [tau < nt] MMA1(tau); [tau >= 1] MMA2(tau - 1)
+  if (warp == 0) {
+    int sr = 0;
+    uint32_t pr = 0;
+    NppCursor cur = npp_begin(g0, nt, p), prv = cur;
+    for (long long tau = 0; tau <= nt; ++tau) {
+      if (tau < nt) {
+        const CUtensorMap* tmBm = cur.strip == 0 ? &tmBm0 : &tmBm1;
+        if (cur.first) {
+          // the previous segment's MMA1s have finished reading A
+          mbar_wait_parked(a_empty, (static_cast<uint32_t>(cur.seg) & 1u) ^ 1u);
+          if (elect_one()) {
+            const CUtensorMap* tmA = cur.strip == 0 ? &tmA0 : &tmA1;
+            const int row0 = p.row_begin + cur.rb * 2 * NP_ROWS + static_cast<int>(rank) * NP_ROWS;
+            if (leader) mbar_arrive_expect_tx(a_full, 2u * static_cast<uint32_t>(p.kchunks) * NP_ACH);
+            for (int c = 0; c < p.kchunks; ++c)
+              tma_load_2d_pair(smA + static_cast<size_t>(c) * NP_ACH, tmA, a_full, c * BK, row0);
+          }
+          __syncwarp();
+        }
+        const int col0 = cur.tile * NP_KT + static_cast<int>(rank) * (NP_KT / 2);
+        for (int j = 0; j < n1; ++j) {
+          const int nck = min(2, p.kchunks - 2 * j);
+          mbar_wait_parked(&emptyR[sr], pr ^ 1u);
+          if (elect_one()) {
+            uint8_t* st = smR + static_cast<size_t>(sr) * NP_STAGE;
+            if (leader) mbar_arrive_expect_tx(&fullR[sr], 2u * static_cast<uint32_t>(nck) * B_CHUNK);
+            for (int ci = 0; ci < nck; ++ci)
+              tma_load_2d_pair(st + ci * B_CHUNK, tmBm, &fullR[sr], (2 * j + ci) * BK, col0);
+          }
+          __syncwarp();
+          if (++sr == p.nr) { sr = 0; pr ^= 1u; }
+        }
+      }
+      if (tau >= 1) {
+        const CUtensorMap* tmBm = prv.strip == 0 ? &tmBm0 : &tmBm1;
+        const int col0 = prv.tile * NP_KT;
+        for (int kh = 0; kh < 2; ++kh) {
+          for (int fb = 0; fb < nfb; ++fb) {
+            mbar_wait_parked(&emptyR[sr], pr ^ 1u);
+            if (elect_one()) {
+              uint8_t* st = smR + static_cast<size_t>(sr) * NP_STAGE;
+              if (leader) mbar_arrive_expect_tx(&fullR[sr], 2u * 2u * B_CHUNK);
+              for (int ci = 0; ci < 2; ++ci)
+                tma_load_2d_pair(st + ci * B_CHUNK, tmBm, &fullR[sr],
+                                 (4 * fb + 2 * static_cast<int>(rank) + ci) * BK, col0 + kh * (NP_KT / 2));
+            }
+            __syncwarp();
+            if (++sr == p.nr) { sr = 0; pr ^= 1u; }
+          }
+        }
+      }
+      prv = cur;
+      if (tau + 1 < nt) npp_next(cur, tau + 1, nt, p);
+    }
+  } else if (warp == 1 && leader) {
+    const uint32_t fmt = p.idesc1_fmt;
+    const uint32_t idesc1 = make_idesc(fmt, fmt, 0, 0, 2 * NP_ROWS, NP_KT);
+    const uint32_t idesc2 = make_idesc(p.g_fmt, fmt, 0, 1, 2 * NP_ROWS, SLICE);
+    const uint32_t smA_addr = smem_u32(smA), smR_addr = smem_u32(smR), smG_addr = smem_u32(smG);
+    int sr = 0;
+    uint32_t pr = 0;
+    NppCursor cur = npp_begin(g0, nt, p), prv = cur;
+    for (long long tau = 0; tau <= nt; ++tau) {
+      if (tau < nt) {
+        if (cur.first) {
+          mbar_wait(a_full, static_cast<uint32_t>(cur.seg) & 1u);
+          tc_fence_after();
+        }
+        const uint32_t d_S = tmem_base + TMEM_S + static_cast<uint32_t>((tau % NP_NS) * (NP_KT / 2));
+        for (int j = 0; j < n1; ++j) {
+          const int nck = min(2, p.kchunks - 2 * j);
+          mbar_wait(&fullR[sr], pr);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint64_t ad0 = make_smem_desc(smA_addr + static_cast<uint32_t>(2 * j) * NP_ACH, 16, 1024);
+            const uint64_t bd0 = make_smem_desc(smR_addr + static_cast<uint32_t>(sr) * NP_STAGE, 16, 1024);
+            for (int ci = 0; ci < nck; ++ci) {
+              const uint64_t ad = ad0 + static_cast<uint64_t>(ci * (NP_ACH >> 4));
+              const uint64_t bd = bd0 + static_cast<uint64_t>(ci * (B_CHUNK >> 4));
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k)
+                mma_ss_pair(d_S, ad + 2 * k, bd + 2 * k, idesc1, (j | ci | k) != 0 ? 1u : 0u);
+            }
+            tc_commit_pair(&emptyR[sr], 3);
+            if (j == n1 - 1) {
+              tc_commit_pair(&s_full[tau % NP_NS], 3);
+              if (cur.last) tc_commit_pair(a_empty, 3);  // A may be replaced by the next segment's rows
+            }
+          }
+          __syncwarp();
+          if (++sr == p.nr) { sr = 0; pr ^= 1u; }
+        }
+      }
+      if (tau >= 1) {
+        const long long u = tau - 1;
+        mbar_wait(&g_ready[u % NP_NS], static_cast<uint32_t>(u / NP_NS) & 1u);
+        if (prv.first && prv.seg > 0)  // the softmax warps have drained the previous segment's dA
+          mbar_wait(da_empty, static_cast<uint32_t>(prv.seg - 1) & 1u);
+        tc_fence_after();
+        const uint32_t g_addr = smG_addr + static_cast<uint32_t>(u % NP_NG) * NP_GBUF;
+        for (int kh = 0; kh < 2; ++kh) {
+          for (int fb = 0; fb < nfb; ++fb) {
+            mbar_wait(&fullR[sr], pr);
+            tc_fence_after();
+            if (elect_one()) {
+              const uint64_t gd0 = make_smem_desc(g_addr + static_cast<uint32_t>(2 * kh) * NP_ACH, 16, 1024);
+              const uint64_t bd = make_smem_desc(smR_addr + static_cast<uint32_t>(sr) * NP_STAGE, B_CHUNK, 1024);
+              const uint32_t d_dA = tmem_base + static_cast<uint32_t>(fb * (SLICE / 2));
+              const bool fresh = prv.first && kh == 0;  // first MMA into this block of a new segment
+#pragma unroll
+              for (int kk = 0; kk < 8; ++kk) {
+                const uint64_t gd = gd0 + static_cast<uint64_t>((kk >> 2) * (NP_ACH >> 4) + (kk & 3) * 2);
+                mma_ss_pair(d_dA, gd, bd + 128 * kk, idesc2, (fresh && kk == 0) ? 0u : 1u);
+              }
+              tc_commit_pair(&emptyR[sr], 3);
+              if (kh == 1 && fb == nfb - 1) {
+                tc_commit_pair(&g_empty[u % NP_NG], 3);
+                if (prv.last) tc_commit_pair(da_full, 3);
+              }
+            }
+            __syncwarp();
+            if (++sr == p.nr) { sr = 0; pr ^= 1u; }
+          }
+        }
+      }
+      prv = cur;
+      if (tau + 1 < nt) npp_next(cur, tau + 1, nt, p);
+    }
+  } else if (warp == 3) {
+    NppCursor cur = npp_begin(g0, nt, p);
+    for (long long t = 0; t < nt; ++t) {
+      const float* lse_col = p.lse_col[cur.strip];
+      const int bb = static_cast<int>(t & 1);
+      mbar_wait_parked(&b_empty[bb], (static_cast<uint32_t>(t >> 1) & 1u) ^ 1u);
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const int cb = cur.tile * NP_KT + hh * 128 + lane * 4;
+        float v[4];
+        if (cb + 4 <= p.ncols) {
+          const float4 f = __ldg(reinterpret_cast<const float4*>(lse_col + cb));
+          v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
+        } else {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) v[k] = __ldg(lse_col + max(min(cb + k, p.ncols - 1), 0));
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = factored ? fast_exp2(lse_mu - v[k]) : v[k] - kGShiftLog2;
+        *reinterpret_cast<float4*>(cfbuf + bb * NP_KT + hh * 128 + lane * 4) = make_float4(v[0], v[1], v[2], v[3]);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&b_full[bb]);
+      if (t + 1 < nt) npp_next(cur, t + 1, nt, p);
+    }
+  } else if (warp >= 4) {
+    const int q = warp & 3;
+    const int h = (warp - 4) >> 2;
+    const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
+    const int rloc = (q & 1) * 32 + lane;
+    const int ctile = (q >> 1) * 128 + h * 64;  // first tile column of this thread
+    const float s = __ldg(p.s_dev);
+    const float c = s * kLog2e;
+    const float coef = __ldg(p.grad_out_dev) * s * p.coef_host;
+    const bool g_bf16 = p.g_fmt != 0;
+    const uint32_t cf_addr0 = smem_u32(cfbuf) + static_cast<uint32_t>(ctile) * 4;
+    const uint32_t g_row_addr = smem_u32(smG) + static_cast<uint32_t>((q >> 1) * 2 + h) * NP_ACH +
+                                static_cast<uint32_t>(rloc) * 128;
+    // per-segment row state
+    int row = 0, label = 0, warp_label_lo = 0;
+    bool valid = false;
+    float lr2 = INFINITY, a_i = 0.f;
+
+    NppCursor cur = npp_begin(g0, nt, p);
+    for (long long t = 0; t < nt; ++t) {
+      if (cur.first) {
+        row = p.row_begin + cur.rb * 2 * NP_ROWS + static_cast<int>(rank) * NP_ROWS + rloc;
+        valid = row < p.row_end;
+        const float lr = valid ? __ldg(p.lse_row[cur.strip] + row) : 0.f;
+        lr2 = valid ? lr - kGShiftLog2 : INFINITY;
+        a_i = valid ? fast_exp2(lr - lse_mu) : 0.f;
+        label = row + p.label_shift;
+        warp_label_lo = label - lane;
+      }
+      const int sb = static_cast<int>(t % NP_NS);
+      const int bb = static_cast<int>(t & 1);
+      const int cb = cur.tile * NP_KT + ctile;
+      mbar_wait_parked(&b_full[bb], static_cast<uint32_t>(t >> 1) & 1u);
+      mbar_wait_parked(&s_full[sb], static_cast<uint32_t>(t / NP_NS) & 1u);
+      tc_fence_after();
+      uint32_t go[32];
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        const int cbh = cb + 32 * hf;
+        const bool has_label = (warp_label_lo < cbh + 32) && (warp_label_lo + 31 >= cbh);
+        uint32_t r[32];
+        tmem_ld32(tmem_base + lane_base + TMEM_S + sb * (NP_KT / 2) + h * 64 + hf * 32, r);
+        tmem_wait_ld();
+        const uint32_t cfa = cf_addr0 + static_cast<uint32_t>(bb * NP_KT + 32 * hf) * 4;
+        const int label_rel = label - cbh;
+        if (factored) {
+          if (g_bf16) np_grad32_dispatch<true, true>(has_label, r, cfa, c, lr2, a_i, label_rel, go + 16 * hf);
+          else np_grad32_dispatch<true, false>(has_label, r, cfa, c, lr2, a_i, label_rel, go + 16 * hf);
+        } else {
+          if (g_bf16) np_grad32_dispatch<false, true>(has_label, r, cfa, c, lr2, a_i, label_rel, go + 16 * hf);
+          else np_grad32_dispatch<false, false>(has_label, r, cfa, c, lr2, a_i, label_rel, go + 16 * hf);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&b_empty[bb]);
+      const int gbi = static_cast<int>(t % NP_NG);
+      mbar_wait_parked(&g_empty[gbi], (static_cast<uint32_t>(t / NP_NG) & 1u) ^ 1u);
+      {
+        const uint32_t grow = g_row_addr + static_cast<uint32_t>(gbi) * NP_GBUF;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          sts_v4(grow + static_cast<uint32_t>((j ^ (rloc & 7)) * 16), go[4 * j], go[4 * j + 1], go[4 * j + 2], go[4 * j + 3]);
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(&g_ready[sb], 0);
+
+      if (cur.last) {
+        // ---- end of a segment: dA (lanes 0-63 features [0,128) of each 256-block, 64-127 [128,256)) ----
+        mbar_wait_parked(da_full, static_cast<uint32_t>(cur.seg) & 1u);
+        tc_fence_after();
+        float* out = p.out[cur.strip] + static_cast<long long>(row - p.row_begin) * p.D;
+        for (int fb = 0; fb < nfb; ++fb) {
+          for (int ch = h; ch < 4; ch += 2) {
+            uint32_t r[32];
+            tmem_ld32(tmem_base + lane_base + fb * (SLICE / 2) + ch * 32, r);
+            tmem_wait_ld();
+            const int f0 = fb * SLICE + (q >> 1) * (SLICE / 2) + ch * 32;
+            if (valid && f0 < p.D) {
+              if (f0 + 32 <= p.D) {
+#pragma unroll
+                for (int k = 0; k < 32; k += 4)
+                  red_add_v4(out + f0 + k, __uint_as_float(r[k]) * coef, __uint_as_float(r[k + 1]) * coef,
+                             __uint_as_float(r[k + 2]) * coef, __uint_as_float(r[k + 3]) * coef);
+              } else {
+#pragma unroll
+                for (int k = 0; k < 32; ++k)
+                  if (f0 + k < p.D) atomicAdd(out + f0 + k, __uint_as_float(r[k]) * coef);
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(da_empty, 0);
+      }
+      if (t + 1 < nt) npp_next(cur, t + 1, nt, p);
     }
   }
 
@@ -1319,6 +1707,31 @@ __global__ void cast_out_kernel(const float* __restrict__ in, void* __restrict__
   }
 }
 
+// Narrow pairs: whole waves of units run unsplit; the partial last wave (r units) is cut ns ways by
+// columns so that r * ns sub-units fill the pairs again.  Per-unit overhead (cluster start, A load,
+// pipeline fill, dA write-out) is worth about 3 tiles of 256 columns.
+struct NpTail {
+  int n_full, ns_tail;
+};
+NpTail plan_np_tail(int64_t units, int64_t ntiles, int slots) {
+  NpTail t;
+  t.n_full = static_cast<int>(units / slots * slots);
+  t.ns_tail = 1;
+  const int64_t r = units - t.n_full;
+  if (r == 0) return t;
+  const int64_t max_ns = std::max<int64_t>(1, std::min<int64_t>(32, ntiles / 4));
+  double best = 1e300;
+  for (int64_t ns = 1; ns <= max_ns; ++ns) {
+    const double waves = static_cast<double>(ceil_div(r * ns, slots));
+    const double cost = waves * (static_cast<double>(ceil_div(ntiles, ns)) + 3.0);
+    if (cost < best - 1e-9) {
+      best = cost;
+      t.ns_tail = static_cast<int>(ns);
+    }
+  }
+  return t;
+}
+
 int choose_bwd_nsplit(int64_t rows, int64_t N, int npass, int rows_per_unit, int slots) {
   const int64_t base = 2 * ceil_div(rows, rows_per_unit) * npass;
   const int64_t ntiles = ceil_div(N, KT);
@@ -1394,10 +1807,28 @@ extern "C" int nans_clip_loss_bwd(const void* I_loc, const void* T_loc, int64_t 
     const char* e = getenv("NANS_BWD_NP");
     if (e && e[0] == '0') use_np = false;
   }
+  // persistent load-balanced form of the narrow-pair kernel: NANS_BWD_PERSIST=1
+  bool use_npp = false;
+  if (use_np) {
+    // worth it when whole waves of one unit per CTA pair would leave SMs idle (64 units on 74 pairs at
+    // n_loc = 4096); with many waves (N = 32768 on one GPU: 512 units, 98.8 % full) the plain-store
+    // kernel wins: no output memset, no red.add, no segment hand-overs
+    const int64_t units = 2 * ceil_div(grad_row_count, 2 * NP_ROWS);
+    const int64_t slots = sm_count() / 2;
+    const double fill = static_cast<double>(units) / static_cast<double>(ceil_div(units, slots) * slots);
+    (void)fill;
+    // measured at 2 GPUs (n_loc = 16384): 2.61 ms/step persistent vs 2.50 ms — the pairs no longer walk
+    // the column tiles in lockstep, so the column operands stop hitting in L2.  Opt-in only.
+    const char* e = getenv("NANS_BWD_PERSIST");
+    use_npp = e && e[0] == '1';
+  }
   const BwdPlan plan = plan_bwd(kchunks);
   const PairPlan pplan = plan_pair(kchunks);
   const NpPlan nplan = plan_np(kchunks);
-  const int nsplit = use_np     ? choose_bwd_nsplit(grad_row_count, N, 1, 2 * NP_ROWS, sm_count() / 2)
+  const int64_t np_units = 2 * ceil_div(grad_row_count, 2 * NP_ROWS);
+  const NpTail tail = plan_np_tail(np_units, ceil_div(N, NP_KT), sm_count() / 2);
+  const int nsplit = use_npp    ? 2  /* outputs are always accumulated (zeroed below) */
+                     : use_np   ? 1  /* per-unit: see plan_np_tail */
                      : use_pair ? choose_bwd_nsplit(grad_row_count, N, npass, 2 * BM, sm_count() / 2)
                                 : choose_bwd_nsplit(grad_row_count, N, npass, BM, sm_count());
   const size_t out_bytes = static_cast<size_t>(grad_row_count) * D * 4;
@@ -1428,6 +1859,16 @@ extern "C" int nans_clip_loss_bwd(const void* I_loc, const void* T_loc, int64_t 
   if (nsplit > 1) {
     NANS_CUDA_OK(cudaMemsetAsync(out32[0], 0, out_bytes, st));
     NANS_CUDA_OK(cudaMemsetAsync(out32[1], 0, out_bytes, st));
+  } else if (use_np && !use_npp && tail.ns_tail > 1) {
+    // only the rows of the column-split tail units are accumulated
+    const int64_t nrb_np = np_units / 2;
+    for (int strip = 0; strip < 2; ++strip) {
+      const int64_t u0 = std::max<int64_t>(tail.n_full, strip * nrb_np), u1 = (strip + 1) * nrb_np;
+      if (u0 >= u1) continue;
+      const int64_t r0 = (u0 - strip * nrb_np) * 2 * NP_ROWS;
+      const int64_t r1 = std::min<int64_t>(grad_row_count, (u1 - strip * nrb_np) * 2 * NP_ROWS);
+      NANS_CUDA_OK(cudaMemsetAsync(out32[strip] + r0 * D, 0, static_cast<size_t>(r1 - r0) * D * 4, st));
+    }
   }
 
   CUtensorMap tmA0, tmB0, tmA1, tmB1, tmBk0, tmBk1;
@@ -1477,10 +1918,21 @@ extern "C" int nans_clip_loss_bwd(const void* I_loc, const void* T_loc, int64_t 
     p.debug = e ? atoi(e) : 0;
   }
 
-  if (use_np) {
+  if (use_npp) {
+    p.total_tiles = 2ll * p.nrb * p.ntiles;
+    // at least ~4 tiles per pair, at most one pair per two SMs
+    const long long want = std::max<long long>(1, p.total_tiles / 4);
+    p.npairs = static_cast<int>(std::min<long long>(sm_count() / 2, want));
+    NANS_CUDA_OK(cudaFuncSetAttribute(clip_bwd_npp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(nplan.bytes)));
+    clip_bwd_npp_kernel<<<static_cast<unsigned>(2 * p.npairs), NUM_THREADS, nplan.bytes, st>>>(tmAn0, tmB0, tmAn1,
+                                                                                            tmB1, p);
+  } else if (use_np) {
     NANS_CUDA_OK(cudaFuncSetAttribute(clip_bwd_np_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       static_cast<int>(nplan.bytes)));
-    const unsigned grid = static_cast<unsigned>(2 * 2 * p.nrb * p.nsplit);
+    p.n_full = tail.n_full;
+    p.ns_tail = tail.ns_tail;
+    const unsigned grid = static_cast<unsigned>(2 * (tail.n_full + (np_units - tail.n_full) * tail.ns_tail));
     clip_bwd_np_kernel<<<grid, NUM_THREADS, nplan.bytes, st>>>(tmAn0, tmB0, tmAn1, tmB1, p);
   } else if (use_pair) {
     auto kern = pplan.a_resident ? clip_bwd_pair_kernel<true> : clip_bwd_pair_kernel<false>;

@@ -562,8 +562,14 @@ def test_cli_reads_binary_feature_shards(dev, golden_dir, tmp_path):
         if gpath == si:   # identical rows -> the reference script's own lists
             assert [o["image_ids"] for o in got] == g["t2i_image_ids"].tolist()
         else:             # re-normalised rows: the oracle on exactly what the shard stores
-            _, pos = OT.topk_vectorised(torch.from_numpy(np.array(f32)), torch.from_numpy(g["queries"]), 10)
-            assert [o["image_ids"] for o in got] == g["image_ids"][pos.numpy()].tolist()
+            gal32, qry = torch.from_numpy(np.array(f32)), torch.from_numpy(g["queries"])
+            rs, ri = OT.topk_vectorised(gal32, qry, 11)
+            pos_of = {int(i): n for n, i in enumerate(g["image_ids"].tolist())}
+            idx = torch.tensor([[pos_of[i] for i in o["image_ids"]] for o in got])
+            mism = idx != ri[:, :10]
+            # BASELINE tolerance: positions are pinned only where the score gap exceeds 1e-4
+            assert int((mism & ~OT.excusable(rs, 1e-4)).sum()) == 0
+            assert all(len(set(o["image_ids"])) == 10 for o in got)
 
 
 def test_topk_full_gallery_properties(dev):
@@ -607,6 +613,34 @@ def test_single_cta_fallback_kernels(dev, monkeypatch, n, d, s):
     assert abs(float(ds) - float(want["ds"])) <= TOL * abs(float(want["ds"])) + 1e-6
     sc, idx = K.topk_ip(I.half().to(dev), T.half().to(dev), I.to(dev), T.to(dev), 10, 16, 0)
     check_topk(idx.cpu(), sc.cpu(), T, I, 10)
+
+
+@pytest.mark.parametrize("persist", ["0", "1"])
+@pytest.mark.parametrize("n,d,s,dt", [(300, 512, 14.2857, torch.float16), (1000, 256, 100.0, torch.float16),
+                                      (2050, 448, 30.0, torch.bfloat16), (4099, 72, 5.0, torch.float16),
+                                      (129, 512, 20.0, torch.float16)])
+def test_narrow_pair_backward_both_schedules(dev, monkeypatch, persist, n, d, s, dt):
+    """NANS_BWD_PERSIST=0: one (row block, column split) unit per CTA pair, plain stores;
+    =1: the persistent load-balanced schedule whose tile ranges cross row-block boundaries
+    (segments, red.add outputs).  The default picks between them by wave fill."""
+    from oracle import clip_loss as OL
+    monkeypatch.setenv("NANS_BWD_PERSIST", persist)
+    I, T = synth(n, d, 7 * n + d, 0.5)
+    want = OL.global_loss_and_grads(I, T, s, torch.float64)
+    loss, acc, dI, dT, ds = run_loss(dev, I, T, s, dt=dt)
+    tol = TOL if dt == torch.float16 else 3e-3
+    assert grad_ok(dI, want["dI"], n, s, tol) and grad_ok(dT, want["dT"], n, s, tol)
+    # accumulate-path rows: a gradient row range that starts inside a row block
+    if n >= 1000:
+        from nans_clip_b200.loss import clip_contrastive_loss
+        r0, rows = 130, 300
+        Ic = I[r0:r0 + rows].to(dev).requires_grad_(True)
+        Tc = T[r0:r0 + rows].to(dev).requires_grad_(True)
+        l2, _ = clip_contrastive_loss(Ic, Tc, torch.tensor(float(s), device=dev), feat_dtype=dt,
+                                      full_image_features=I.to(dev), full_text_features=T.to(dev), row_begin=r0)
+        l2.backward()
+        assert grad_ok(Ic.grad.cpu(), want["dI"][r0:r0 + rows], n, s, tol)
+        assert grad_ok(Tc.grad.cpu(), want["dT"][r0:r0 + rows], n, s, tol)
 
 
 @pytest.mark.parametrize("n,d,s,dt", [(300, 512, 14.2857, torch.float16), (1000, 256, 100.0, torch.float16),
