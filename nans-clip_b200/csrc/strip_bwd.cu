@@ -873,9 +873,9 @@ struct NpPlan {
   int nr;
   size_t bytes;
 };
-NpPlan plan_np(int kchunks) {
+NpPlan plan_np(int kchunks, int tk = NP_KT) {
   NpPlan p;
-  const size_t fixed = static_cast<size_t>(kchunks) * NP_ACH + static_cast<size_t>(NP_NG) * NP_GBUF + NP_BAR_BYTES;
+  const size_t fixed = static_cast<size_t>(kchunks) * NP_ACH + static_cast<size_t>(NP_NG) * NP_ROWS * tk * 2 + NP_BAR_BYTES;
   // the 1 KB of alignment slack is dropped when it would cost a ring stage (D = 512): the kernel
   // checks that its aligned carve-up fits and traps otherwise
   size_t pad = 1024;
@@ -935,16 +935,28 @@ __device__ __forceinline__ void np_grad32_dispatch(bool has_label, const uint32_
   else np_grad32<FACTORED, BF16, false>(r, cf_addr, c, lr2, a_i, label_rel, g16);
 }
 
+// TK = tile width in columns: 256 for D <= 512 (two 128-column S buffers beside 256 columns of dA),
+// 128 for 512 < D <= 768 (dA takes 384 TMEM columns, two 64-column S buffers are left).
+//   tmS* : column operand for MMA1, box [TK/2 rows, 64 features] (this CTA's half of the tile)
+//   tmBm*: column operand for MMA2, box [128 rows, 64 features]
+template <int TK>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
-clip_bwd_np_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmBm0,
-                   const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmBm1,
+clip_bwd_np_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmS0,
+                   const __grid_constant__ CUtensorMap tmBm0, const __grid_constant__ CUtensorMap tmA1,
+                   const __grid_constant__ CUtensorMap tmS1, const __grid_constant__ CUtensorMap tmBm1,
                    const BwdParams p) {
+  constexpr int SW = TK / 2;                       // TMEM columns of one S buffer
+  constexpr int GBUF = NP_ROWS * TK * 2;           // bytes of one G buffer (TK / 64 chunks of 8 KB)
+  constexpr int S_CH = (TK / 2) * BK * 2;          // MMA1: this CTA's rows of a tile, one 64-feature chunk
+  constexpr int CPS = NP_STAGE / S_CH;             // MMA1 chunks per ring stage (2 or 4)
+  constexpr int KH = TK / 128;                     // MMA2: 128-row K halves per tile
+  constexpr int TPT = TK / 4;                      // tile columns per softmax thread (64 or 32)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* smA = smem;
   uint8_t* smG = smA + static_cast<size_t>(p.kchunks) * NP_ACH;
-  uint8_t* smR = smG + static_cast<size_t>(NP_NG) * NP_GBUF;
+  uint8_t* smR = smG + static_cast<size_t>(NP_NG) * GBUF;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smR + static_cast<size_t>(p.nr) * NP_STAGE);
   {
     uint32_t dyn;
@@ -983,18 +995,21 @@ clip_bwd_np_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
   const int strip = unit / p.nrb;
 
   const CUtensorMap* tmA = strip == 0 ? &tmA0 : &tmA1;     // box [64 rows, 64 features]
-  const CUtensorMap* tmBm = strip == 0 ? &tmBm0 : &tmBm1;  // box [128 rows, 64 features]
+  const CUtensorMap* tmS = strip == 0 ? &tmS0 : &tmS1;
+  const CUtensorMap* tmBm = strip == 0 ? &tmBm0 : &tmBm1;
   const int row0 = p.row_begin + rb * 2 * NP_ROWS + static_cast<int>(rank) * NP_ROWS;
   const int tile_begin = static_cast<int>(static_cast<long long>(split) * p.ntiles / nsplit_u);
   const int tile_end = static_cast<int>(static_cast<long long>(split + 1) * p.ntiles / nsplit_u);
   const int ntiles = tile_end - tile_begin;
-  const int n1 = (p.kchunks + 1) / 2;  // MMA1 stages per tile (2 chunks each)
+  const int n1 = (p.kchunks + CPS - 1) / CPS;  // MMA1 stages per tile
+  const uint32_t tmem_s = static_cast<uint32_t>(512 - NP_NS * SW);  // S buffers sit at the top of TMEM
   const int nfb = (p.kchunks + 3) / 4; // 256-feature blocks of dA; MMA2 stages per tile = 2 nfb
 
   if (warp == 0) {
     if (elect_one()) {
       tma_prefetch_desc(tmA);
       tma_prefetch_desc(tmBm);
+      tma_prefetch_desc(tmS);
       for (int i = 0; i < NP_MAXR; ++i) { mbar_init(&fullR[i], 1); mbar_init(&emptyR[i], 1); }
       mbar_init(a_full, 1);
       for (int i = 0; i < NP_NS; ++i) { mbar_init(&s_full[i], 1); mbar_init(&g_ready[i], 2 * SM_WARPS); }
@@ -1036,23 +1051,23 @@ clip_bwd_np_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
     uint32_t pr = 0;
     for (int tau = 0; tau <= ntiles; ++tau) {
       if (tau < ntiles) {
-        const int col0 = (tile_begin + tau) * NP_KT + static_cast<int>(rank) * (NP_KT / 2);
+        const int col0 = (tile_begin + tau) * TK + static_cast<int>(rank) * (TK / 2);
         for (int j = 0; j < n1; ++j) {
-          const int nck = min(2, p.kchunks - 2 * j);
+          const int nck = min(CPS, p.kchunks - CPS * j);
           mbar_wait_parked(&emptyR[sr], pr ^ 1u);
           if (elect_one()) {
             uint8_t* st = smR + static_cast<size_t>(sr) * NP_STAGE;
-            if (leader) mbar_arrive_expect_tx(&fullR[sr], 2u * static_cast<uint32_t>(nck) * B_CHUNK);
+            if (leader) mbar_arrive_expect_tx(&fullR[sr], 2u * static_cast<uint32_t>(nck) * S_CH);
             for (int ci = 0; ci < nck; ++ci)
-              tma_load_2d_pair(st + ci * B_CHUNK, tmBm, &fullR[sr], (2 * j + ci) * BK, col0);
+              tma_load_2d_pair(st + ci * S_CH, tmS, &fullR[sr], (CPS * j + ci) * BK, col0);
           }
           __syncwarp();
           if (++sr == p.nr) { sr = 0; pr ^= 1u; }
         }
       }
       if (tau >= 1) {
-        const int col0 = (tile_begin + tau - 1) * NP_KT;
-        for (int kh = 0; kh < 2; ++kh) {
+        const int col0 = (tile_begin + tau - 1) * TK;
+        for (int kh = 0; kh < KH; ++kh) {
           for (int fb = 0; fb < nfb; ++fb) {
             mbar_wait_parked(&emptyR[sr], pr ^ 1u);
             if (elect_one()) {
@@ -1061,7 +1076,7 @@ clip_bwd_np_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
               // this CTA's 128 of the block's 256 features: chunks 4 fb + 2 rank, + 1 (zero fill past D)
               for (int ci = 0; ci < 2; ++ci)
                 tma_load_2d_pair(st + ci * B_CHUNK, tmBm, &fullR[sr],
-                                 (4 * fb + 2 * static_cast<int>(rank) + ci) * BK, col0 + kh * (NP_KT / 2));
+                                 (4 * fb + 2 * static_cast<int>(rank) + ci) * BK, col0 + kh * 128);
             }
             __syncwarp();
             if (++sr == p.nr) { sr = 0; pr ^= 1u; }
@@ -1071,7 +1086,7 @@ clip_bwd_np_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
     }
   } else if (warp == 1 && leader) {
     const uint32_t fmt = p.idesc1_fmt;
-    const uint32_t idesc1 = make_idesc(fmt, fmt, 0, 0, 2 * NP_ROWS, NP_KT);
+    const uint32_t idesc1 = make_idesc(fmt, fmt, 0, 0, 2 * NP_ROWS, TK);
     const uint32_t idesc2 = make_idesc(p.g_fmt, fmt, 0, 1, 2 * NP_ROWS, SLICE);
     const uint32_t smA_addr = smem_u32(smA), smR_addr = smem_u32(smR), smG_addr = smem_u32(smG);
     mbar_wait(a_full, 0);
@@ -1080,17 +1095,17 @@ clip_bwd_np_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
     uint32_t pr = 0;
     for (int tau = 0; tau <= ntiles; ++tau) {
       if (tau < ntiles) {
-        const uint32_t d_S = tmem_base + TMEM_S + static_cast<uint32_t>((tau % NP_NS) * (NP_KT / 2));
+        const uint32_t d_S = tmem_base + tmem_s + static_cast<uint32_t>((tau % NP_NS) * SW);
         for (int j = 0; j < n1; ++j) {
-          const int nck = min(2, p.kchunks - 2 * j);
+          const int nck = min(CPS, p.kchunks - CPS * j);
           mbar_wait(&fullR[sr], pr);
           tc_fence_after();
           if (elect_one()) {
-            const uint64_t ad0 = make_smem_desc(smA_addr + static_cast<uint32_t>(2 * j) * NP_ACH, 16, 1024);
+            const uint64_t ad0 = make_smem_desc(smA_addr + static_cast<uint32_t>(CPS * j) * NP_ACH, 16, 1024);
             const uint64_t bd0 = make_smem_desc(smR_addr + static_cast<uint32_t>(sr) * NP_STAGE, 16, 1024);
             for (int ci = 0; ci < nck; ++ci) {
               const uint64_t ad = ad0 + static_cast<uint64_t>(ci * (NP_ACH >> 4));
-              const uint64_t bd = bd0 + static_cast<uint64_t>(ci * (B_CHUNK >> 4));
+              const uint64_t bd = bd0 + static_cast<uint64_t>(ci * (S_CH >> 4));
 #pragma unroll
               for (int k = 0; k < BK / 16; ++k)
                 mma_ss_pair(d_S, ad + 2 * k, bd + 2 * k, idesc1, (j | ci | k) != 0 ? 1u : 0u);
@@ -1106,8 +1121,8 @@ clip_bwd_np_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
         const int u = tau - 1;
         mbar_wait(&g_ready[u % NP_NS], static_cast<uint32_t>(u / NP_NS) & 1u);
         tc_fence_after();
-        const uint32_t g_addr = smG_addr + static_cast<uint32_t>(u % NP_NG) * NP_GBUF;
-        for (int kh = 0; kh < 2; ++kh) {
+        const uint32_t g_addr = smG_addr + static_cast<uint32_t>(u % NP_NG) * GBUF;
+        for (int kh = 0; kh < KH; ++kh) {
           for (int fb = 0; fb < nfb; ++fb) {
             mbar_wait(&fullR[sr], pr);
             tc_fence_after();
@@ -1123,7 +1138,7 @@ clip_bwd_np_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
                 mma_ss_pair(d_dA, gd, bd + 128 * kk, idesc2, (u > 0 || kh > 0 || kk > 0) ? 1u : 0u);
               }
               tc_commit_pair(&emptyR[sr], 3);
-              if (kh == 1 && fb == nfb - 1) {
+              if (kh == KH - 1 && fb == nfb - 1) {
                 tc_commit_pair(&g_empty[u % NP_NG], 3);
                 if (u == ntiles - 1) tc_commit_pair(da_full, 3);
               }
@@ -1140,8 +1155,8 @@ clip_bwd_np_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
       const int bb = t & 1;
       mbar_wait_parked(&b_empty[bb], (static_cast<uint32_t>(t >> 1) & 1u) ^ 1u);
 #pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {
-        const int cb = (tile_begin + t) * NP_KT + hh * 128 + lane * 4;
+      for (int hh = 0; hh < KH; ++hh) {
+        const int cb = (tile_begin + t) * TK + hh * 128 + lane * 4;
         float v[4];
         if (cb + 4 <= p.ncols) {
           const float4 f = __ldg(reinterpret_cast<const float4*>(lse_col + cb));
@@ -1152,7 +1167,7 @@ clip_bwd_np_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
         }
 #pragma unroll
         for (int k = 0; k < 4; ++k) v[k] = factored ? fast_exp2(lse_mu - v[k]) : v[k] - kGShiftLog2;
-        *reinterpret_cast<float4*>(cfbuf + bb * NP_KT + hh * 128 + lane * 4) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4*>(cfbuf + bb * TK + hh * 128 + lane * 4) = make_float4(v[0], v[1], v[2], v[3]);
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&b_full[bb]);
@@ -1168,7 +1183,7 @@ clip_bwd_np_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
     const int rloc = (q & 1) * 32 + lane;
     const int row = row0 + rloc;
     const bool valid = row < p.row_end;
-    const int ctile = (q >> 1) * 128 + h * 64;  // first tile column of this thread
+    const int ctile = (q >> 1) * (TK / 2) + h * TPT;  // first tile column of this thread
     const float s = __ldg(p.s_dev);
     const float c = s * kLog2e;
     const float lr2 = valid ? __ldg(p.lse_row[strip] + row) - kGShiftLog2 : INFINITY;
@@ -1177,25 +1192,28 @@ clip_bwd_np_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
     const int warp_label_lo = label - lane;
     const bool g_bf16 = p.g_fmt != 0;
     const uint32_t cf_addr0 = smem_u32(cfbuf) + static_cast<uint32_t>(ctile) * 4;
-    const uint32_t g_row_addr = smem_u32(smG) + static_cast<uint32_t>((q >> 1) * 2 + h) * NP_ACH +
+    // this thread's TPT columns of G: 64-wide K chunk ctile / 64, 16-byte units (ctile % 64) / 8 onwards
+    const uint32_t g_row_addr = smem_u32(smG) + static_cast<uint32_t>(ctile / 64) * NP_ACH +
                                 static_cast<uint32_t>(rloc) * 128;
+    constexpr int G_UNITS = TPT / 8;
+    const int g_unit0 = (ctile % 64) / 8;
 
     for (int t = 0; t < ntiles; ++t) {
       const int sb = t % NP_NS;
       const int bb = t & 1;
-      const int cb = (tile_begin + t) * NP_KT + ctile;
+      const int cb = (tile_begin + t) * TK + ctile;
       mbar_wait_parked(&b_full[bb], static_cast<uint32_t>(t >> 1) & 1u);
       mbar_wait_parked(&s_full[sb], static_cast<uint32_t>(t / NP_NS) & 1u);
       tc_fence_after();
-      uint32_t go[32];
+      uint32_t go[TPT / 2];
 #pragma unroll
-      for (int hf = 0; hf < 2; ++hf) {
+      for (int hf = 0; hf < TPT / 32; ++hf) {
         const int cbh = cb + 32 * hf;
         const bool has_label = (warp_label_lo < cbh + 32) && (warp_label_lo + 31 >= cbh);
         uint32_t r[32];
-        tmem_ld32(tmem_base + lane_base + TMEM_S + sb * (NP_KT / 2) + h * 64 + hf * 32, r);
+        tmem_ld32(tmem_base + lane_base + tmem_s + sb * SW + h * TPT + hf * 32, r);
         tmem_wait_ld();
-        const uint32_t cfa = cf_addr0 + static_cast<uint32_t>(bb * NP_KT + 32 * hf) * 4;
+        const uint32_t cfa = cf_addr0 + static_cast<uint32_t>(bb * TK + 32 * hf) * 4;
         const int label_rel = label - cbh;
         if (factored) {
           if (g_bf16) np_grad32_dispatch<true, true>(has_label, r, cfa, c, lr2, a_i, label_rel, go + 16 * hf);
@@ -1211,10 +1229,11 @@ clip_bwd_np_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
       const int gbi = t % NP_NG;
       mbar_wait_parked(&g_empty[gbi], (static_cast<uint32_t>(t / NP_NG) & 1u) ^ 1u);
       {
-        const uint32_t grow = g_row_addr + static_cast<uint32_t>(gbi) * NP_GBUF;
+        const uint32_t grow = g_row_addr + static_cast<uint32_t>(gbi) * GBUF;
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          sts_v4(grow + static_cast<uint32_t>((j ^ (rloc & 7)) * 16), go[4 * j], go[4 * j + 1], go[4 * j + 2], go[4 * j + 3]);
+        for (int j = 0; j < G_UNITS; ++j)
+          sts_v4(grow + static_cast<uint32_t>(((g_unit0 + j) ^ (rloc & 7)) * 16), go[4 * j], go[4 * j + 1],
+                 go[4 * j + 2], go[4 * j + 3]);
       }
       fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core's async proxy
       tc_fence_before();         // the S reads above are ordered before the hand-over as well
@@ -1709,11 +1728,11 @@ __global__ void cast_out_kernel(const float* __restrict__ in, void* __restrict__
 
 // Narrow pairs: whole waves of units run unsplit; the partial last wave (r units) is cut ns ways by
 // columns so that r * ns sub-units fill the pairs again.  Per-unit overhead (cluster start, A load,
-// pipeline fill, dA write-out) is worth about 3 tiles of 256 columns.
+// pipeline fill, dA write-out) is worth about 3 tiles of 256 columns (6 of 128).
 struct NpTail {
   int n_full, ns_tail;
 };
-NpTail plan_np_tail(int64_t units, int64_t ntiles, int slots) {
+NpTail plan_np_tail(int64_t units, int64_t ntiles, int slots, double overhead_tiles) {
   NpTail t;
   t.n_full = static_cast<int>(units / slots * slots);
   t.ns_tail = 1;
@@ -1723,7 +1742,7 @@ NpTail plan_np_tail(int64_t units, int64_t ntiles, int slots) {
   double best = 1e300;
   for (int64_t ns = 1; ns <= max_ns; ++ns) {
     const double waves = static_cast<double>(ceil_div(r * ns, slots));
-    const double cost = waves * (static_cast<double>(ceil_div(ntiles, ns)) + 3.0);
+    const double cost = waves * (static_cast<double>(ceil_div(ntiles, ns)) + overhead_tiles);
     if (cost < best - 1e-9) {
       best = cost;
       t.ns_tail = static_cast<int>(ns);
@@ -1802,7 +1821,8 @@ extern "C" int nans_clip_loss_bwd(const void* I_loc, const void* T_loc, int64_t 
   }
   // narrow pairs (64 rows per CTA, no S recompute per feature slice) whenever D <= 512;
   // NANS_BWD_NP=0 falls back to the 128-row pair kernel
-  bool use_np = use_pair && kchunks <= 8;
+  bool use_np = use_pair && kchunks <= 12;  // D <= 768: dA of 64 rows fits TMEM beside two S buffers
+  const int np_tk = kchunks <= 8 ? NP_KT : 128;
   {
     const char* e = getenv("NANS_BWD_NP");
     if (e && e[0] == '0') use_np = false;
@@ -1820,13 +1840,13 @@ extern "C" int nans_clip_loss_bwd(const void* I_loc, const void* T_loc, int64_t 
     // measured at 2 GPUs (n_loc = 16384): 2.61 ms/step persistent vs 2.50 ms — the pairs no longer walk
     // the column tiles in lockstep, so the column operands stop hitting in L2.  Opt-in only.
     const char* e = getenv("NANS_BWD_PERSIST");
-    use_npp = e && e[0] == '1';
+    use_npp = e && e[0] == '1' && kchunks <= 8;
   }
   const BwdPlan plan = plan_bwd(kchunks);
   const PairPlan pplan = plan_pair(kchunks);
-  const NpPlan nplan = plan_np(kchunks);
+  const NpPlan nplan = plan_np(kchunks, np_tk);
   const int64_t np_units = 2 * ceil_div(grad_row_count, 2 * NP_ROWS);
-  const NpTail tail = plan_np_tail(np_units, ceil_div(N, NP_KT), sm_count() / 2);
+  const NpTail tail = plan_np_tail(np_units, ceil_div(N, np_tk), sm_count() / 2, np_tk == NP_KT ? 3.0 : 6.0);
   const int nsplit = use_npp    ? 2  /* outputs are always accumulated (zeroed below) */
                      : use_np   ? 1  /* per-unit: see plan_np_tail */
                      : use_pair ? choose_bwd_nsplit(grad_row_count, N, npass, 2 * BM, sm_count() / 2)
@@ -1891,7 +1911,7 @@ extern "C" int nans_clip_loss_bwd(const void* I_loc, const void* T_loc, int64_t 
   p.nrb = static_cast<int>(ceil_div(grad_row_count, use_np ? 2 * NP_ROWS : (use_pair ? 2 * BM : BM)));
   p.npass = npass;
   p.nsplit = nsplit;
-  p.ntiles = static_cast<int>(ceil_div(N, use_np ? NP_KT : KT));
+  p.ntiles = static_cast<int>(ceil_div(N, use_np ? np_tk : KT));
   p.nr = use_np ? nplan.nr : (use_pair ? pplan.nr : plan.nr);
   p.idesc1_fmt = static_cast<uint32_t>(idesc_fmt(feat_dtype));
   // tcgen05.mma kind::f16 wants A and B in the same 16-bit format (a mixed f16 x bf16 descriptor
@@ -1928,12 +1948,18 @@ extern "C" int nans_clip_loss_bwd(const void* I_loc, const void* T_loc, int64_t 
     clip_bwd_npp_kernel<<<static_cast<unsigned>(2 * p.npairs), NUM_THREADS, nplan.bytes, st>>>(tmAn0, tmB0, tmAn1,
                                                                                             tmB1, p);
   } else if (use_np) {
-    NANS_CUDA_OK(cudaFuncSetAttribute(clip_bwd_np_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      static_cast<int>(nplan.bytes)));
     p.n_full = tail.n_full;
     p.ns_tail = tail.ns_tail;
     const unsigned grid = static_cast<unsigned>(2 * (tail.n_full + (np_units - tail.n_full) * tail.ns_tail));
-    clip_bwd_np_kernel<<<grid, NUM_THREADS, nplan.bytes, st>>>(tmAn0, tmB0, tmAn1, tmB1, p);
+    if (np_tk == NP_KT) {
+      NANS_CUDA_OK(cudaFuncSetAttribute(clip_bwd_np_kernel<NP_KT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        static_cast<int>(nplan.bytes)));
+      clip_bwd_np_kernel<NP_KT><<<grid, NUM_THREADS, nplan.bytes, st>>>(tmAn0, tmB0, tmB0, tmAn1, tmB1, tmB1, p);
+    } else {
+      NANS_CUDA_OK(cudaFuncSetAttribute(clip_bwd_np_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        static_cast<int>(nplan.bytes)));
+      clip_bwd_np_kernel<128><<<grid, NUM_THREADS, nplan.bytes, st>>>(tmAn0, tmBk0, tmB0, tmAn1, tmBk1, tmB1, p);
+    }
   } else if (use_pair) {
     auto kern = pplan.a_resident ? clip_bwd_pair_kernel<true> : clip_bwd_pair_kernel<false>;
     NANS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,

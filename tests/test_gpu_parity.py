@@ -643,8 +643,32 @@ def test_narrow_pair_backward_both_schedules(dev, monkeypatch, persist, n, d, s,
         assert grad_ok(Tc.grad.cpu(), want["dT"][r0:r0 + rows], n, s, tol)
 
 
+@pytest.mark.parametrize("n,d,s,dt", [(1500, 768, 14.2857, torch.float16), (700, 576, 50.0, torch.float16),
+                                      (2100, 640, 5.0, torch.bfloat16), (257, 704, 20.0, torch.float16)])
+def test_narrow_pair_backward_wide_features(dev, n, d, s, dt):
+    """512 < D <= 768: the 128-column-tile instance of the narrow-pair kernel (dA takes 384 TMEM
+    columns), including ragged feature widths and the accumulate-path row window."""
+    from oracle import clip_loss as OL
+    from nans_clip_b200.loss import clip_contrastive_loss
+    I, T = synth(n, d, 11 * n + d, 0.5)
+    want = OL.global_loss_and_grads(I, T, s, torch.float64)
+    loss, acc, dI, dT, ds = run_loss(dev, I, T, s, dt=dt)
+    tol = TOL if dt == torch.float16 else 3e-3
+    assert abs(float(loss) - float(want["loss"])) <= TOL * abs(float(want["loss"])) + 1e-6 * s
+    assert grad_ok(dI, want["dI"], n, s, tol) and grad_ok(dT, want["dT"], n, s, tol)
+    r0, rows = 70, 200
+    Ic = I[r0:r0 + rows].to(dev).requires_grad_(True)
+    Tc = T[r0:r0 + rows].to(dev).requires_grad_(True)
+    l2, _ = clip_contrastive_loss(Ic, Tc, torch.tensor(float(s), device=dev), feat_dtype=dt,
+                                  full_image_features=I.to(dev), full_text_features=T.to(dev), row_begin=r0)
+    l2.backward()
+    assert grad_ok(Ic.grad.cpu(), want["dI"][r0:r0 + rows], n, s, tol)
+    assert grad_ok(Tc.grad.cpu(), want["dT"][r0:r0 + rows], n, s, tol)
+
+
 @pytest.mark.parametrize("n,d,s,dt", [(300, 512, 14.2857, torch.float16), (1000, 256, 100.0, torch.float16),
-                                      (2050, 448, 30.0, torch.bfloat16), (513, 64, 5.0, torch.float16)])
+                                      (2050, 448, 30.0, torch.bfloat16), (513, 64, 5.0, torch.float16),
+                                      (600, 768, 14.2857, torch.float16)])
 def test_wide_pair_backward_fallback(dev, monkeypatch, n, d, s, dt):
     """NANS_BWD_NP=0: the 128-row CTA-pair backward (the D > 512 kernel) on D <= 512 shapes; the
     default there is the 64-row pair kernel, covered by every other test."""

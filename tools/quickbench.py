@@ -34,7 +34,7 @@ if "l2norm" in which:
     ms = timeit(lambda: K.l2norm_cast(x, torch.bfloat16))
     print(f"l2norm 1M x512 fp32->bf16: {ms:.3f} ms  {1e6*512*6/ms/1e6:.0f} GB/s")
 for dt in (torch.float16, torch.bfloat16):
-    for (n, d) in [(32768, 512), (4096, 512), (32768, 1024)]:
+    for (n, d) in [(32768, 512), (4096, 512), (32768, 768), (32768, 1024)]:
         if "fwd" in which or "bwd" in which:
             I = feats(n, d, dt).requires_grad_(True); T = feats(n, d, dt).requires_grad_(True)
             s = torch.tensor(14.285, device=dev, requires_grad=True)
