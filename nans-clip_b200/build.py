@@ -28,7 +28,7 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC",
     "--expt-relaxed-constexpr",
     "-Xptxas", "-v",
-]
+] + os.environ.get("NANS_EXTRA_NVCC_FLAGS", "").split()   # bring-up experiments only (e.g. -DNANS_NP_CF_SHFL)
 
 
 def _nvcc() -> str:

@@ -898,14 +898,19 @@ __device__ __forceinline__ void sts_v4(uint32_t addr, uint32_t a, uint32_t b, ui
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
-// softmax_grad32 with the column factors read through ld.shared (one wavefront per broadcast load)
+// softmax_grad32 for the narrow-pair kernels (column factors through one load + warp shuffles)
 template <bool FACTORED, bool BF16, bool LABEL>
 __device__ __forceinline__ void np_grad32(const uint32_t (&r)[32], uint32_t cf_addr, float c, float lr2,
                                           float a_i, int label_rel, uint32_t* __restrict__ g16) {
+  // the 32 column factors of this group: ONE lane-distributed load + 32 shuffles.  Eight broadcast
+  // LDS.128 per thread cost two wavefronts each on the shared-memory data pipe, which is what bounds
+  // this kernel (tensor-core operand reads share it); the shuffles do not (3.11 -> 2.98 ms).
+  float cfl;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(cfl) : "r"(cf_addr + 4 * (threadIdx.x & 31)));
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
-    const float4 f = lds_v4(cf_addr + 16 * q);
-    const float cfv[4] = {f.x, f.y, f.z, f.w};
+    const float cfv[4] = {__shfl_sync(0xffffffffu, cfl, 4 * q), __shfl_sync(0xffffffffu, cfl, 4 * q + 1),
+                          __shfl_sync(0xffffffffu, cfl, 4 * q + 2), __shfl_sync(0xffffffffu, cfl, 4 * q + 3)};
     float g[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
