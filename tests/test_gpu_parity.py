@@ -367,11 +367,13 @@ def test_label_smoothing_zero_is_plain_and_range_checked(dev):
         clip_contrastive_loss(I.to(dev), T.to(dev), torch.tensor(10.0, device=dev), label_smoothing=1.0)
 
 
-def test_full_size_properties(dev):
-    """BASELINE size (N = 32768, D = 512): checks that need no N x N oracle on the host."""
+@pytest.mark.parametrize("d", [512, 768, 1024])
+def test_full_size_properties(dev, d):
+    """BASELINE sizes (N = 32768; D = 512 / 768 / 1024 = configs 2, 3, 4): checks that need no
+    N x N oracle on the host."""
     from nans_clip_b200 import kernels as K
     from nans_clip_b200.loss import clip_contrastive_loss
-    n, d, s0 = 32768, 512, 14.2857
+    n, s0 = 32768, 14.2857
     g = torch.Generator(device=dev).manual_seed(3)
     base = torch.randn(n, d, device=dev, generator=g)
     I = torch.nn.functional.normalize(0.5 * base + 0.5 * torch.randn(n, d, device=dev, generator=g), dim=-1).half().float()
@@ -403,6 +405,9 @@ def test_full_size_properties(dev):
     G[torch.arange(len(rows), device=dev), rows] -= 2
     want = s0 / (2 * n) * (G @ T)
     assert relerr(dI1[rows], want) < TOL
+    GT = torch.exp(s0 * T[rows] @ I.t() - lse[1][rows][:, None]) + torch.exp(s0 * T[rows] @ I.t() - lse[0][None, :])
+    GT[torch.arange(len(rows), device=dev), rows] -= 2
+    assert relerr(dT1[rows], s0 / (2 * n) * (GT @ I)) < TOL
     # (c) linearity in the upstream gradient
     l2, dI2, dT2, ds2, _ = run(s0, 3.0)
     assert relerr(dI2, 3 * dI1) < 1e-6 and relerr(dT2, 3 * dT1) < 1e-6
