@@ -862,10 +862,11 @@ constexpr int NP_ROWS = 64;
 constexpr int NP_KT = 256;
 constexpr int NP_ACH = NP_ROWS * BK * 2;      // 8 KB  : one 64-feature chunk of this CTA's A rows / of G
 constexpr int NP_STAGE = 2 * B_CHUNK;         // 32 KB
+constexpr int NP_STAGE_STREAM = 3 * B_CHUNK;  // 48 KB: two MMA1 chunks of [64 A rows | 128 tile rows] x 64 features
 constexpr int NP_GBUF = NP_ROWS * NP_KT * 2;  // 32 KB
 constexpr int NP_NG = 2;
 constexpr int NP_NS = 2;                      // S buffers (128 TMEM columns each)
-constexpr int NP_MAXR = 4;
+constexpr int NP_MAXR = 6;
 constexpr int NP_BAR_BYTES = 2560;            // mbarriers + TMEM pointer (256 B) + two 256-float column-factor buffers
 constexpr int NP_CF_OFF = 256;
 
@@ -873,9 +874,11 @@ struct NpPlan {
   int nr;
   size_t bytes;
 };
-NpPlan plan_np(int kchunks, int tk = NP_KT) {
+NpPlan plan_np(int kchunks, int tk = NP_KT, bool a_resident = true) {
   NpPlan p;
-  const size_t fixed = static_cast<size_t>(kchunks) * NP_ACH + static_cast<size_t>(NP_NG) * NP_ROWS * tk * 2 + NP_BAR_BYTES;
+  const size_t NP_STAGE = a_resident ? nans::NP_STAGE : nans::NP_STAGE_STREAM;  // shadows the constant below
+  const size_t fixed = (a_resident ? static_cast<size_t>(kchunks) * NP_ACH : 0) +
+                       static_cast<size_t>(NP_NG) * NP_ROWS * tk * 2 + NP_BAR_BYTES;
   // the 1 KB of alignment slack is dropped when it would cost a ring stage (D = 512): the kernel
   // checks that its aligned carve-up fits and traps otherwise
   size_t pad = 1024;
@@ -944,7 +947,10 @@ __device__ __forceinline__ void np_grad32_dispatch(bool has_label, const uint32_
 // 128 for 512 < D <= 768 (dA takes 384 TMEM columns, two 64-column S buffers are left).
 //   tmS* : column operand for MMA1, box [TK/2 rows, 64 features] (this CTA's half of the tile)
 //   tmBm*: column operand for MMA2, box [128 rows, 64 features]
-template <int TK>
+// ARES = false (768 < D <= 1024): A does not stay resident (128 KB) — its chunks travel through the
+// ring with the column chunks of MMA1 — and dA is produced in two passes of 512 features (256 TMEM
+// columns each); a unit is then (strip, row block, pass) and S is recomputed once per pass.
+template <int TK, bool ARES>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 clip_bwd_np_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmS0,
                    const __grid_constant__ CUtensorMap tmBm0, const __grid_constant__ CUtensorMap tmA1,
@@ -953,16 +959,18 @@ clip_bwd_np_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
   constexpr int SW = TK / 2;                       // TMEM columns of one S buffer
   constexpr int GBUF = NP_ROWS * TK * 2;           // bytes of one G buffer (TK / 64 chunks of 8 KB)
   constexpr int S_CH = (TK / 2) * BK * 2;          // MMA1: this CTA's rows of a tile, one 64-feature chunk
-  constexpr int CPS = NP_STAGE / S_CH;             // MMA1 chunks per ring stage (2 or 4)
+  constexpr int STG = ARES ? NP_STAGE : NP_STAGE_STREAM;  // ring stage bytes
+  constexpr int CPS = ARES ? STG / S_CH : STG / (S_CH + NP_ACH);  // MMA1 chunks per ring stage
+  constexpr int MCH = ARES ? S_CH : S_CH + NP_ACH;  // bytes of one MMA1 chunk in a stage ([A rows |] tile rows)
   constexpr int KH = TK / 128;                     // MMA2: 128-row K halves per tile
   constexpr int TPT = TK / 4;                      // tile columns per softmax thread (64 or 32)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* smA = smem;
-  uint8_t* smG = smA + static_cast<size_t>(p.kchunks) * NP_ACH;
+  uint8_t* smG = smA + (ARES ? static_cast<size_t>(p.kchunks) * NP_ACH : 0);
   uint8_t* smR = smG + static_cast<size_t>(NP_NG) * GBUF;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smR + static_cast<size_t>(p.nr) * NP_STAGE);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smR + static_cast<size_t>(p.nr) * STG);
   {
     uint32_t dyn;
     asm volatile("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn));
@@ -996,8 +1004,11 @@ clip_bwd_np_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
     nsplit_u = p.ns_tail;
   }
   const bool accumulate = nsplit_u > 1;
+  const int pass = unit % p.npass;
+  unit /= p.npass;
   const int rb = unit % p.nrb;
   const int strip = unit / p.nrb;
+  const int f_off = pass * 2 * SLICE;  // first feature of this pass's 512-feature slice of dA
 
   const CUtensorMap* tmA = strip == 0 ? &tmA0 : &tmA1;     // box [64 rows, 64 features]
   const CUtensorMap* tmS = strip == 0 ? &tmS0 : &tmS1;
@@ -1008,7 +1019,7 @@ clip_bwd_np_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
   const int ntiles = tile_end - tile_begin;
   const int n1 = (p.kchunks + CPS - 1) / CPS;  // MMA1 stages per tile
   const uint32_t tmem_s = static_cast<uint32_t>(512 - NP_NS * SW);  // S buffers sit at the top of TMEM
-  const int nfb = (p.kchunks + 3) / 4; // 256-feature blocks of dA; MMA2 stages per tile = 2 nfb
+  const int nfb = min((p.D - f_off + SLICE - 1) / SLICE, ARES ? 3 : 2);  // 256-feature blocks of dA in this pass
 
   if (warp == 0) {
     if (elect_one()) {
@@ -1046,12 +1057,14 @@ clip_bwd_np_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
 
   // schedule shared by producer and issuer: step tau: [tau < ntiles] MMA1(tau); [tau >= 1] MMA2(tau - 1)
   if (warp == 0) {
-    if (elect_one()) {
-      if (leader) mbar_arrive_expect_tx(a_full, 2u * static_cast<uint32_t>(p.kchunks) * NP_ACH);
-      for (int c = 0; c < p.kchunks; ++c)
-        tma_load_2d_pair(smA + static_cast<size_t>(c) * NP_ACH, tmA, a_full, c * BK, row0);
+    if (ARES) {
+      if (elect_one()) {
+        if (leader) mbar_arrive_expect_tx(a_full, 2u * static_cast<uint32_t>(p.kchunks) * NP_ACH);
+        for (int c = 0; c < p.kchunks; ++c)
+          tma_load_2d_pair(smA + static_cast<size_t>(c) * NP_ACH, tmA, a_full, c * BK, row0);
+      }
+      __syncwarp();
     }
-    __syncwarp();
     int sr = 0;
     uint32_t pr = 0;
     for (int tau = 0; tau <= ntiles; ++tau) {
@@ -1061,10 +1074,12 @@ clip_bwd_np_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
           const int nck = min(CPS, p.kchunks - CPS * j);
           mbar_wait_parked(&emptyR[sr], pr ^ 1u);
           if (elect_one()) {
-            uint8_t* st = smR + static_cast<size_t>(sr) * NP_STAGE;
-            if (leader) mbar_arrive_expect_tx(&fullR[sr], 2u * static_cast<uint32_t>(nck) * S_CH);
-            for (int ci = 0; ci < nck; ++ci)
-              tma_load_2d_pair(st + ci * S_CH, tmS, &fullR[sr], (CPS * j + ci) * BK, col0);
+            uint8_t* st = smR + static_cast<size_t>(sr) * STG;
+            if (leader) mbar_arrive_expect_tx(&fullR[sr], 2u * static_cast<uint32_t>(nck) * MCH);
+            for (int ci = 0; ci < nck; ++ci) {
+              if (!ARES) tma_load_2d_pair(st + ci * MCH, tmA, &fullR[sr], (CPS * j + ci) * BK, row0);
+              tma_load_2d_pair(st + ci * MCH + (ARES ? 0 : NP_ACH), tmS, &fullR[sr], (CPS * j + ci) * BK, col0);
+            }
           }
           __syncwarp();
           if (++sr == p.nr) { sr = 0; pr ^= 1u; }
@@ -1076,12 +1091,12 @@ clip_bwd_np_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
           for (int fb = 0; fb < nfb; ++fb) {
             mbar_wait_parked(&emptyR[sr], pr ^ 1u);
             if (elect_one()) {
-              uint8_t* st = smR + static_cast<size_t>(sr) * NP_STAGE;
+              uint8_t* st = smR + static_cast<size_t>(sr) * STG;
               if (leader) mbar_arrive_expect_tx(&fullR[sr], 2u * 2u * B_CHUNK);
               // this CTA's 128 of the block's 256 features: chunks 4 fb + 2 rank, + 1 (zero fill past D)
               for (int ci = 0; ci < 2; ++ci)
                 tma_load_2d_pair(st + ci * B_CHUNK, tmBm, &fullR[sr],
-                                 (4 * fb + 2 * static_cast<int>(rank) + ci) * BK, col0 + kh * 128);
+                                 f_off + (4 * fb + 2 * static_cast<int>(rank) + ci) * BK, col0 + kh * 128);
             }
             __syncwarp();
             if (++sr == p.nr) { sr = 0; pr ^= 1u; }
@@ -1094,8 +1109,10 @@ clip_bwd_np_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
     const uint32_t idesc1 = make_idesc(fmt, fmt, 0, 0, 2 * NP_ROWS, TK);
     const uint32_t idesc2 = make_idesc(p.g_fmt, fmt, 0, 1, 2 * NP_ROWS, SLICE);
     const uint32_t smA_addr = smem_u32(smA), smR_addr = smem_u32(smR), smG_addr = smem_u32(smG);
-    mbar_wait(a_full, 0);
-    tc_fence_after();
+    if (ARES) {
+      mbar_wait(a_full, 0);
+      tc_fence_after();
+    }
     int sr = 0;
     uint32_t pr = 0;
     for (int tau = 0; tau <= ntiles; ++tau) {
@@ -1106,11 +1123,13 @@ clip_bwd_np_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
           mbar_wait(&fullR[sr], pr);
           tc_fence_after();
           if (elect_one()) {
-            const uint64_t ad0 = make_smem_desc(smA_addr + static_cast<uint32_t>(CPS * j) * NP_ACH, 16, 1024);
-            const uint64_t bd0 = make_smem_desc(smR_addr + static_cast<uint32_t>(sr) * NP_STAGE, 16, 1024);
+            const uint32_t st_addr = smR_addr + static_cast<uint32_t>(sr) * STG;
+            const uint64_t ad0 = ARES ? make_smem_desc(smA_addr + static_cast<uint32_t>(CPS * j) * NP_ACH, 16, 1024)
+                                      : make_smem_desc(st_addr, 16, 1024);
+            const uint64_t bd0 = make_smem_desc(st_addr + (ARES ? 0 : NP_ACH), 16, 1024);
             for (int ci = 0; ci < nck; ++ci) {
-              const uint64_t ad = ad0 + static_cast<uint64_t>(ci * (NP_ACH >> 4));
-              const uint64_t bd = bd0 + static_cast<uint64_t>(ci * (S_CH >> 4));
+              const uint64_t ad = ad0 + static_cast<uint64_t>(ci * ((ARES ? NP_ACH : MCH) >> 4));
+              const uint64_t bd = bd0 + static_cast<uint64_t>(ci * (MCH >> 4));
 #pragma unroll
               for (int k = 0; k < BK / 16; ++k)
                 mma_ss_pair(d_S, ad + 2 * k, bd + 2 * k, idesc1, (j | ci | k) != 0 ? 1u : 0u);
@@ -1135,7 +1154,7 @@ clip_bwd_np_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
               // A = G from shared memory (K-major, 64 rows per CTA, 64-wide K chunks of 8 KB)
               const uint64_t gd0 = make_smem_desc(g_addr + static_cast<uint32_t>(2 * kh) * NP_ACH, 16, 1024);
               // B = 128 tile rows as K, 2 x 64 features of this CTA as MN blocks 16 KB apart
-              const uint64_t bd = make_smem_desc(smR_addr + static_cast<uint32_t>(sr) * NP_STAGE, B_CHUNK, 1024);
+              const uint64_t bd = make_smem_desc(smR_addr + static_cast<uint32_t>(sr) * STG, B_CHUNK, 1024);
               const uint32_t d_dA = tmem_base + static_cast<uint32_t>(fb * (SLICE / 2));
 #pragma unroll
               for (int kk = 0; kk < 8; ++kk) {
@@ -1256,7 +1275,7 @@ clip_bwd_np_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
         uint32_t r[32];
         tmem_ld32(tmem_base + lane_base + fb * (SLICE / 2) + ch * 32, r);
         tmem_wait_ld();
-        const int f0 = fb * SLICE + (q >> 1) * (SLICE / 2) + ch * 32;
+        const int f0 = f_off + fb * SLICE + (q >> 1) * (SLICE / 2) + ch * 32;
         if (valid && f0 < p.D) {
           if (f0 + 32 <= p.D) {
 #pragma unroll
@@ -1826,8 +1845,11 @@ extern "C" int nans_clip_loss_bwd(const void* I_loc, const void* T_loc, int64_t 
   }
   // narrow pairs (64 rows per CTA, no S recompute per feature slice) whenever D <= 512;
   // NANS_BWD_NP=0 falls back to the 128-row pair kernel
-  bool use_np = use_pair && kchunks <= 12;  // D <= 768: dA of 64 rows fits TMEM beside two S buffers
-  const int np_tk = kchunks <= 8 ? NP_KT : 128;
+  // D <= 768: dA of 64 rows fits TMEM beside two S buffers; D <= 1024: two passes of 512 features, A streamed
+  bool use_np = use_pair && kchunks <= 16;
+  const bool np_ares = kchunks <= 12;
+  const int np_tk = (kchunks <= 8 || !np_ares) ? NP_KT : 128;  // 128-column tiles only for 512 < D <= 768
+  const int np_npass = np_ares ? 1 : 2;
   {
     const char* e = getenv("NANS_BWD_NP");
     if (e && e[0] == '0') use_np = false;
@@ -1849,8 +1871,8 @@ extern "C" int nans_clip_loss_bwd(const void* I_loc, const void* T_loc, int64_t 
   }
   const BwdPlan plan = plan_bwd(kchunks);
   const PairPlan pplan = plan_pair(kchunks);
-  const NpPlan nplan = plan_np(kchunks, np_tk);
-  const int64_t np_units = 2 * ceil_div(grad_row_count, 2 * NP_ROWS);
+  const NpPlan nplan = plan_np(kchunks, np_tk, np_ares);
+  const int64_t np_units = 2 * ceil_div(grad_row_count, 2 * NP_ROWS) * np_npass;
   const NpTail tail = plan_np_tail(np_units, ceil_div(N, np_tk), sm_count() / 2, np_tk == NP_KT ? 3.0 : 6.0);
   const int nsplit = use_npp    ? 2  /* outputs are always accumulated (zeroed below) */
                      : use_np   ? 1  /* per-unit: see plan_np_tail */
@@ -1882,6 +1904,9 @@ extern "C" int nans_clip_loss_bwd(const void* I_loc, const void* T_loc, int64_t 
     out32[1] = reinterpret_cast<float*>(static_cast<uint8_t*>(ws) + 256 + align_up(out_bytes, 256));
   }
   if (nsplit > 1) {
+    NANS_CUDA_OK(cudaMemsetAsync(out32[0], 0, out_bytes, st));
+    NANS_CUDA_OK(cudaMemsetAsync(out32[1], 0, out_bytes, st));
+  } else if (use_np && !use_npp && tail.ns_tail > 1 && np_npass > 1) {
     NANS_CUDA_OK(cudaMemsetAsync(out32[0], 0, out_bytes, st));
     NANS_CUDA_OK(cudaMemsetAsync(out32[1], 0, out_bytes, st));
   } else if (use_np && !use_npp && tail.ns_tail > 1) {
@@ -1956,14 +1981,19 @@ extern "C" int nans_clip_loss_bwd(const void* I_loc, const void* T_loc, int64_t 
     p.n_full = tail.n_full;
     p.ns_tail = tail.ns_tail;
     const unsigned grid = static_cast<unsigned>(2 * (tail.n_full + (np_units - tail.n_full) * tail.ns_tail));
-    if (np_tk == NP_KT) {
-      NANS_CUDA_OK(cudaFuncSetAttribute(clip_bwd_np_kernel<NP_KT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    p.npass = np_npass;
+    if (np_tk == NP_KT && !np_ares) {
+      NANS_CUDA_OK(cudaFuncSetAttribute(clip_bwd_np_kernel<NP_KT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         static_cast<int>(nplan.bytes)));
-      clip_bwd_np_kernel<NP_KT><<<grid, NUM_THREADS, nplan.bytes, st>>>(tmAn0, tmB0, tmB0, tmAn1, tmB1, tmB1, p);
+      clip_bwd_np_kernel<NP_KT, false><<<grid, NUM_THREADS, nplan.bytes, st>>>(tmAn0, tmB0, tmB0, tmAn1, tmB1, tmB1, p);
+    } else if (np_tk == NP_KT) {
+      NANS_CUDA_OK(cudaFuncSetAttribute(clip_bwd_np_kernel<NP_KT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        static_cast<int>(nplan.bytes)));
+      clip_bwd_np_kernel<NP_KT, true><<<grid, NUM_THREADS, nplan.bytes, st>>>(tmAn0, tmB0, tmB0, tmAn1, tmB1, tmB1, p);
     } else {
-      NANS_CUDA_OK(cudaFuncSetAttribute(clip_bwd_np_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      NANS_CUDA_OK(cudaFuncSetAttribute(clip_bwd_np_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         static_cast<int>(nplan.bytes)));
-      clip_bwd_np_kernel<128><<<grid, NUM_THREADS, nplan.bytes, st>>>(tmAn0, tmBk0, tmB0, tmAn1, tmBk1, tmB1, p);
+      clip_bwd_np_kernel<128, true><<<grid, NUM_THREADS, nplan.bytes, st>>>(tmAn0, tmBk0, tmB0, tmAn1, tmBk1, tmB1, p);
     }
   } else if (use_pair) {
     auto kern = pplan.a_resident ? clip_bwd_pair_kernel<true> : clip_bwd_pair_kernel<false>;
