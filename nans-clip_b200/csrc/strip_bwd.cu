@@ -97,6 +97,8 @@ struct BwdParams {
   int n_full, ns_tail;      // narrow pairs: units [0, n_full) sweep all columns, the rest are split ns_tail ways
   long long total_tiles;    // persistent kernel: 2 * nrb * ntiles tile steps shared out over npairs CTA pairs
   int npairs;
+  int npp_units, npp_t1;    // persistent kernel, helper mode (npp_t1 > 0): pairs [0, npp_units) sweep tiles [0, npp_t1) of
+                            // their own unit, the remaining pairs share the tiles [npp_t1, ntiles) of all units
 };
 
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
@@ -1308,7 +1310,7 @@ clip_bwd_np_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
 }
 
 // ================================================================================================
-// Persistent, load-balanced form of the narrow-pair kernel (NANS_BWD_PERSIST=1; not the default, see the dispatch).  The (strip, row block, tile)
+// Persistent, load-balanced forms of the narrow-pair kernel (see the dispatch for when each is used).  The (strip, row block, tile)
 // space is linearised (row-block major, tiles inside) and cut into `npairs` equal contiguous ranges,
 // one per resident CTA pair, so that the SMs stay busy whatever 2 * nrb is (with one unit per CTA
 // pair, 64 units on 74 pairs leave 14 % of the machine idle at n_loc = 4096).  A pair's range
@@ -1318,28 +1320,50 @@ clip_bwd_np_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
 // segment's last tile).  Extra barriers: a_empty (A may be overwritten), da_empty (dA drained).
 struct NppCursor {
   int strip, rb, tile, seg;
-  bool first, last;  // first / last tile of its segment
+  int tile_lo, tile_hi;  // the window of column tiles this pair sweeps in every unit it touches
+  bool first, last;      // first / last tile of its segment
 };
-__device__ __forceinline__ NppCursor npp_begin(long long g0, long long nt, const BwdParams& p) {
+// This pair's share: `nt` tile steps starting at linear index g0 of the space (unit, tile in window).
+__device__ __forceinline__ void npp_range(long long pair, const BwdParams& p, long long& g0, long long& nt,
+                                          int& tile_lo, int& tile_hi) {
+  if (p.npp_t1 > 0) {
+    if (pair < p.npp_units) {  // main pair: the first npp_t1 tiles of its own unit
+      tile_lo = 0; tile_hi = p.npp_t1;
+      g0 = pair * p.npp_t1; nt = p.npp_t1;
+    } else {                   // helper pair: an equal share of the last tiles of ALL units
+      tile_lo = p.npp_t1; tile_hi = p.ntiles;
+      const long long tot = static_cast<long long>(p.npp_units) * (p.ntiles - p.npp_t1);
+      const long long h = pair - p.npp_units, nh = p.npairs - p.npp_units;
+      g0 = h * tot / nh; nt = (h + 1) * tot / nh - g0;
+    }
+  } else {
+    tile_lo = 0; tile_hi = p.ntiles;
+    g0 = pair * p.total_tiles / p.npairs; nt = (pair + 1) * p.total_tiles / p.npairs - g0;
+  }
+}
+__device__ __forceinline__ NppCursor npp_begin(long long g0, long long nt, const BwdParams& p, int tile_lo,
+                                               int tile_hi) {
   NppCursor c;
-  const int unit = static_cast<int>(g0 / p.ntiles);
-  c.tile = static_cast<int>(g0 - static_cast<long long>(unit) * p.ntiles);
+  const int lt = tile_hi - tile_lo;
+  const int unit = static_cast<int>(g0 / lt);
+  c.tile_lo = tile_lo; c.tile_hi = tile_hi;
+  c.tile = tile_lo + static_cast<int>(g0 - static_cast<long long>(unit) * lt);
   c.strip = unit / p.nrb;
   c.rb = unit - c.strip * p.nrb;
   c.seg = 0;
   c.first = true;
-  c.last = (nt == 1) || (c.tile == p.ntiles - 1);
+  c.last = (nt == 1) || (c.tile == tile_hi - 1);
   return c;
 }
 // advance to local tile t + 1 (t1 = t + 1 is the new local index)
 __device__ __forceinline__ void npp_next(NppCursor& c, long long t1, long long nt, const BwdParams& p) {
-  if (++c.tile == p.ntiles) {
-    c.tile = 0;
+  if (++c.tile == c.tile_hi) {
+    c.tile = c.tile_lo;
     if (++c.rb == p.nrb) { c.rb = 0; ++c.strip; }
   }
-  c.first = c.tile == 0;
+  c.first = c.tile == c.tile_lo;
   if (c.first) ++c.seg;
-  c.last = (t1 == nt - 1) || (c.tile == p.ntiles - 1);
+  c.last = (t1 == nt - 1) || (c.tile == c.tile_hi - 1);
 }
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
@@ -1377,9 +1401,9 @@ clip_bwd_npp_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
 
-  const long long pair = blockIdx.x >> 1;
-  const long long g0 = pair * p.total_tiles / p.npairs;
-  const long long nt = (pair + 1) * p.total_tiles / p.npairs - g0;  // >= 1 (host: npairs <= total_tiles)
+  long long g0, nt;  // nt >= 1 (host: every pair gets at least one tile)
+  int tile_lo, tile_hi;
+  npp_range(blockIdx.x >> 1, p, g0, nt, tile_lo, tile_hi);
   const int n1 = (p.kchunks + 1) / 2;  // MMA1 stages per tile (2 chunks each)
   const int nfb = (p.kchunks + 3) / 4; // 256-feature blocks of dA; MMA2 stages per tile = 2 nfb
 
@@ -1424,7 +1448,7 @@ clip_bwd_npp_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
   if (warp == 0) {
     int sr = 0;
     uint32_t pr = 0;
-    NppCursor cur = npp_begin(g0, nt, p), prv = cur;
+    NppCursor cur = npp_begin(g0, nt, p, tile_lo, tile_hi), prv = cur;
     for (long long tau = 0; tau <= nt; ++tau) {
       if (tau < nt) {
         const CUtensorMap* tmBm = cur.strip == 0 ? &tmBm0 : &tmBm1;
@@ -1482,7 +1506,7 @@ clip_bwd_npp_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     const uint32_t smA_addr = smem_u32(smA), smR_addr = smem_u32(smR), smG_addr = smem_u32(smG);
     int sr = 0;
     uint32_t pr = 0;
-    NppCursor cur = npp_begin(g0, nt, p), prv = cur;
+    NppCursor cur = npp_begin(g0, nt, p, tile_lo, tile_hi), prv = cur;
     for (long long tau = 0; tau <= nt; ++tau) {
       if (tau < nt) {
         if (cur.first) {
@@ -1550,7 +1574,7 @@ clip_bwd_npp_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
       if (tau + 1 < nt) npp_next(cur, tau + 1, nt, p);
     }
   } else if (warp == 3) {
-    NppCursor cur = npp_begin(g0, nt, p);
+    NppCursor cur = npp_begin(g0, nt, p, tile_lo, tile_hi);
     for (long long t = 0; t < nt; ++t) {
       const float* lse_col = p.lse_col[cur.strip];
       const int bb = static_cast<int>(t & 1);
@@ -1592,7 +1616,7 @@ clip_bwd_npp_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     bool valid = false;
     float lr2 = INFINITY, a_i = 0.f;
 
-    NppCursor cur = npp_begin(g0, nt, p);
+    NppCursor cur = npp_begin(g0, nt, p, tile_lo, tile_hi);
     for (long long t = 0; t < nt; ++t) {
       if (cur.first) {
         row = p.row_begin + cur.rb * 2 * NP_ROWS + static_cast<int>(rank) * NP_ROWS + rloc;
@@ -1856,6 +1880,7 @@ extern "C" int nans_clip_loss_bwd(const void* I_loc, const void* T_loc, int64_t 
   }
   // persistent load-balanced form of the narrow-pair kernel: NANS_BWD_PERSIST=1
   bool use_npp = false;
+  int npp_t1 = 0, npp_units = 0;
   if (use_np) {
     // worth it when whole waves of one unit per CTA pair would leave SMs idle (64 units on 74 pairs at
     // n_loc = 4096); with many waves (N = 32768 on one GPU: 512 units, 98.8 % full) the plain-store
@@ -1863,11 +1888,30 @@ extern "C" int nans_clip_loss_bwd(const void* I_loc, const void* T_loc, int64_t 
     const int64_t units = 2 * ceil_div(grad_row_count, 2 * NP_ROWS);
     const int64_t slots = sm_count() / 2;
     const double fill = static_cast<double>(units) / static_cast<double>(ceil_div(units, slots) * slots);
-    (void)fill;
-    // measured at 2 GPUs (n_loc = 16384): 2.61 ms/step persistent vs 2.50 ms — the pairs no longer walk
-    // the column tiles in lockstep, so the column operands stop hitting in L2.  Opt-in only.
+    // Equal contiguous ranges (NANS_BWD_PERSIST=1): measured at 2 GPUs (n_loc = 16384) 2.61 ms/step
+    // against 2.50 — the pairs no longer walk the column tiles in lockstep, so the column operands
+    // stop hitting in L2.  Opt-in only.
+    // Helper mode (default when there are FEWER units than CTA pairs, e.g. 64 units on 74 pairs at
+    // n_loc = 4096): every unit keeps its own pair for the first T1 tiles (lockstep preserved) and the
+    // idle pairs share the last ntiles - T1 tiles of all units.  NANS_BWD_PERSIST=0 disables it.
     const char* e = getenv("NANS_BWD_PERSIST");
-    use_npp = e && e[0] == '1' && kchunks <= 8;
+    const int64_t nt256 = ceil_div(N, NP_KT);
+    const bool force_helpers = e && e[0] == '2';  // tests: helper mode wherever it is feasible
+    if (e && e[0] == '1') {
+      use_npp = kchunks <= 8;
+    } else if (!(e && e[0] == '0') && kchunks <= 8 && units < slots && nt256 >= 2 &&
+               (force_helpers || (fill < 0.95 && slots - units >= 2 && nt256 >= 32))) {
+      // main pair: T1 tiles + start/drain (~3 tiles); helper: units * (nt - T1) / helpers tiles + ~1.2
+      // tiles per unit boundary + the same start/drain  =>  T1 = units * (nt + 1.2) / slots
+      int64_t t1 = std::max<int64_t>(1, std::min<int64_t>(
+          nt256 - 1, (units * (10 * nt256 + 12) + 10 * slots - 1) / (10 * slots)));
+      if (const char* o = getenv("NANS_NPP_T1")) t1 = std::max<int64_t>(1, std::min<int64_t>(nt256 - 1, atoi(o)));  // tuning
+      if (units * (nt256 - t1) >= slots - units) {  // every helper pair gets at least one tile
+        use_npp = true;
+        npp_t1 = static_cast<int>(t1);
+        npp_units = static_cast<int>(units);
+      }
+    }
   }
   const BwdPlan plan = plan_bwd(kchunks);
   const PairPlan pplan = plan_pair(kchunks);
@@ -1970,9 +2014,15 @@ extern "C" int nans_clip_loss_bwd(const void* I_loc, const void* T_loc, int64_t 
 
   if (use_npp) {
     p.total_tiles = 2ll * p.nrb * p.ntiles;
-    // at least ~4 tiles per pair, at most one pair per two SMs
-    const long long want = std::max<long long>(1, p.total_tiles / 4);
-    p.npairs = static_cast<int>(std::min<long long>(sm_count() / 2, want));
+    p.npp_t1 = npp_t1;
+    p.npp_units = npp_units;
+    if (npp_t1 > 0) {
+      p.npairs = sm_count() / 2;  // npp_units main pairs + the helpers
+    } else {
+      // at least ~4 tiles per pair, at most one pair per two SMs
+      const long long want = std::max<long long>(1, p.total_tiles / 4);
+      p.npairs = static_cast<int>(std::min<long long>(sm_count() / 2, want));
+    }
     NANS_CUDA_OK(cudaFuncSetAttribute(clip_bwd_npp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       static_cast<int>(nplan.bytes)));
     clip_bwd_npp_kernel<<<static_cast<unsigned>(2 * p.npairs), NUM_THREADS, nplan.bytes, st>>>(tmAn0, tmB0, tmAn1,

@@ -620,14 +620,16 @@ def test_single_cta_fallback_kernels(dev, monkeypatch, n, d, s):
     check_topk(idx.cpu(), sc.cpu(), T, I, 10)
 
 
-@pytest.mark.parametrize("persist", ["0", "1"])
+@pytest.mark.parametrize("persist", ["0", "1", "2"])
 @pytest.mark.parametrize("n,d,s,dt", [(300, 512, 14.2857, torch.float16), (1000, 256, 100.0, torch.float16),
                                       (2050, 448, 30.0, torch.bfloat16), (4099, 72, 5.0, torch.float16),
                                       (129, 512, 20.0, torch.float16)])
 def test_narrow_pair_backward_both_schedules(dev, monkeypatch, persist, n, d, s, dt):
     """NANS_BWD_PERSIST=0: one (row block, column split) unit per CTA pair, plain stores;
-    =1: the persistent load-balanced schedule whose tile ranges cross row-block boundaries
-    (segments, red.add outputs).  The default picks between them by wave fill."""
+    =1: the persistent schedule with equal contiguous tile ranges that cross row-block boundaries
+    (segments, red.add outputs); =2: the persistent helper schedule (every unit keeps a pair for its
+    first tiles, the idle pairs share the last tiles of all units) wherever it is feasible.  The
+    default is the helper schedule when there are fewer units than CTA pairs, else the first."""
     from oracle import clip_loss as OL
     monkeypatch.setenv("NANS_BWD_PERSIST", persist)
     I, T = synth(n, d, 7 * n + d, 0.5)
@@ -646,6 +648,35 @@ def test_narrow_pair_backward_both_schedules(dev, monkeypatch, persist, n, d, s,
         l2.backward()
         assert grad_ok(Ic.grad.cpu(), want["dI"][r0:r0 + rows], n, s, tol)
         assert grad_ok(Tc.grad.cpu(), want["dT"][r0:r0 + rows], n, s, tol)
+
+
+def test_backward_helper_schedule_is_the_default_with_few_units(dev):
+    """n_loc = 4096 rows against N = 8192 columns (rank 1 of 2): 64 units on 74 CTA pairs, 32 column
+    tiles -> the helper schedule runs by default; gradients against the oracle's rank strip."""
+    from nans_clip_b200 import kernels as K
+    from oracle import clip_loss as OL
+    W, rank, n_loc, d, s = 2, 1, 4096, 64, 20.0
+    I, T = synth(W * n_loc, d, 123, 0.5)
+    glob = OL.global_loss_and_grads(I, T, s, torch.float64)
+    I16, T16 = I.half().to(dev), T.half().to(dev)
+    lo, hi = rank * n_loc, (rank + 1) * n_loc
+    lse_all = (torch.stack([glob["lse_img"], glob["lse_txt"]]) / math.log(2.0)).float().to(dev)
+    outs = {}
+    for mode in ("default", "0"):
+        if mode == "0":
+            import os
+            os.environ["NANS_BWD_PERSIST"] = "0"
+        try:
+            outs[mode] = K.bwd(I16[lo:hi], T16[lo:hi], T16, I16, label_begin=lo, s_dev=torch.tensor([s], device=dev),
+                               lse_all=lse_all, grad_out=torch.ones(1, device=dev), grad_mult=1.0, row_begin=0,
+                               row_count=n_loc, out_dtype=torch.float32)
+        finally:
+            if mode == "0":
+                del os.environ["NANS_BWD_PERSIST"]
+    for dI, dT in outs.values():
+        assert grad_ok(dI.cpu(), glob["dI"][lo:hi], W * n_loc, s) and grad_ok(dT.cpu(), glob["dT"][lo:hi], W * n_loc, s)
+    # the two schedules add the same per-tile products in a different order
+    assert relerr(outs["default"][0].cpu(), outs["0"][0].cpu()) < 1e-5
 
 
 @pytest.mark.parametrize("n,d,s,dt", [(1500, 768, 14.2857, torch.float16), (700, 576, 50.0, torch.float16),

@@ -1,5 +1,6 @@
 """Backward kernel alone (CUDA events, L2 flushed) at N=32768 for several D; development aid.
-usage: python tools/bwd_time.py [D ...]"""
+usage: python tools/bwd_time.py [D ...]      (env NLOC=4096: time one rank's strip of an 8-rank job)"""
+import os
 import sys
 import torch
 sys.path.insert(0, ".")
@@ -8,6 +9,7 @@ from nans_clip_b200 import kernels as K
 dev = torch.device("cuda:0")
 flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
 n = 32768
+nloc = int(os.environ.get('NLOC', n))
 for d in [int(a) for a in sys.argv[1:]] or [512, 768, 1024]:
     I = torch.nn.functional.normalize(torch.randn(n, d, device=dev), dim=-1).half()
     T = torch.nn.functional.normalize(torch.randn(n, d, device=dev), dim=-1).half()
@@ -19,8 +21,8 @@ for d in [int(a) for a in sys.argv[1:]] or [512, 768, 1024]:
     g = torch.ones(1, device=dev)
 
     def bwd():
-        K.bwd(I, T, T, I, label_begin=0, s_dev=s_dev, lse_all=lse, grad_out=g, grad_mult=1.0, row_begin=0,
-              row_count=n, out_dtype=torch.float32)
+        K.bwd(I[:nloc], T[:nloc], T, I, label_begin=0, s_dev=s_dev, lse_all=lse, grad_out=g, grad_mult=1.0,
+              row_begin=0, row_count=nloc, out_dtype=torch.float32)
 
     def fwd():
         K.fwd_phase(I, T, T, I, col_global_begin=0, label_begin=0, s_dev=s_dev, with_acc=False, ws=ws, slot_begin=0)
@@ -36,4 +38,5 @@ for d in [int(a) for a in sys.argv[1:]] or [512, 768, 1024]:
             ts.append(a.elapsed_time(b))
         ts.sort()
         ms = ts[len(ts) // 2]
-        print(f"{name} N={n} D={d}: {ms:.3f} ms  alg {alg * n * n * d / ms / 1e9:.0f} TF/s", flush=True)
+        rows = nloc if name == "bwd" else n
+        print(f"{name} rows={rows} N={n} D={d}: {ms:.3f} ms  alg {alg * rows * n * d / ms / 1e9:.0f} TF/s", flush=True)
