@@ -3,20 +3,24 @@
 // schedules).  Included by strip_bwd.cu only.
 #pragma once
 // ================================================================================================
-// Narrow CTA-pair version (D <= 512): the pair owns 128 rows, 64 per CTA (cta_group::2, M = 128).
-// With 64 rows per CTA the fp32 dA for ALL D <= 512 features takes 256 TMEM columns (the M = 128
-// pair layout puts the two N halves of an accumulator on lanes 0-63 / 64-127), which leaves room for
-// two S buffers of a 256-column tile: the logits are recomputed ONCE per tile instead of once per
-// 256-feature slice.  The kernel is bound by the shared-memory data pipe (tensor-core operand reads
-// + the softmax warps' TMEM / shared traffic, ncu: 98 % with 128-column tiles), so MMA1 uses the
-// widest N (256: A is re-read once per 256 columns) and the softmax warps use ld/st.shared.
-//   TMEM : [0,128) dA features 0-255 | [128,256) dA features 256-511 | [256,512) S buffers 0-1
+// Narrow CTA pairs: the pair owns 128 rows, 64 per CTA (cta_group::2, M = 128).  With 64 rows per CTA
+// the fp32 dA of D features takes D / 2 TMEM columns (the M = 128 pair layout puts the two N halves
+// of an accumulator on lanes 0-63 / 64-127), which leaves room for two S buffers:
+//     D <=  512 : dA 256 columns, S 2 x 128 columns -> 256-column tiles  (TK = 256, A resident)
+//     D <=  768 : dA 384 columns, S 2 x  64 columns -> 128-column tiles  (TK = 128, A resident)
+//     D <= 1024 : two passes of 512 features (dA 256 columns each), TK = 256, A streamed (ARES = false)
+// so the logits are recomputed ONCE per tile (and pass) instead of once per 256-feature slice.
+// The kernel is bound by the shared-memory data pipe (tensor-core operand reads + the softmax warps'
+// shared traffic; ncu: tc 60 % + LSU 37 %), hence the widest MMA1 N that fits (A is re-read once per
+// tile), ld/st.shared, one lane-distributed load + shuffles for the column factors, parked waits.
+//   TMEM : dA blocks of 256 features (128 columns each) from column 0 | S buffers at the top.
 //          S / dA rows 0-63 of the CTA sit on lanes 0-63 (first N half) and 64-127 (second N half).
-//   SMEM : A (64 rows, resident) | 2 G buffers (64 rows x 256 K, 16-bit, K-major swizzled: G goes
+//   SMEM : [A (64 rows, resident)] | 2 G buffers (64 rows x TK K, 16-bit, K-major swizzled: G goes
 //          through shared memory because the TMEM-A form of a pair MMA wants a duplicated layout)
-//          | ring of 32 KB stages: MMA1 = 2 chunks of [128 tile rows x 64 features] of this CTA's
-//          half of the tile; MMA2 = [128 tile rows x 64 features] x 2 of this CTA's 128 features of
-//          a 256-feature block.  MMA2 of tile t is issued after MMA1 of tile t + 1.
+//          | ring of 32 KB (48 KB when A is streamed) stages: MMA1 = chunks of [TK/2 tile rows x 64
+//          features] of this CTA's half of the tile [+ the matching A chunk]; MMA2 = [128 tile rows
+//          x 64 features] x 2 of this CTA's 128 features of a 256-feature block.
+//          MMA2 of tile t is issued after MMA1 of tile t + 1.
 constexpr int NP_ROWS = 64;
 constexpr int NP_KT = 256;
 constexpr int NP_ACH = NP_ROWS * BK * 2;      // 8 KB  : one 64-feature chunk of this CTA's A rows / of G
