@@ -137,6 +137,28 @@ int nans_clip_loss_fwd_finalize(int64_t n_loc, int64_t total_slots, int64_t labe
                                 float* lse_img_loc, float* lse_txt_loc, float* scalars,
                                 void* stream);
 
+/* The two entry points above with the extras of the incremental gradient-accumulation path
+ * (python: nans_clip_b200/accum.py):
+ *   _phase_rows   : only rows [label_row_begin, label_row_begin + label_row_count) have their label
+ *                   column inside this phase's columns (label_begin then refers to those rows:
+ *                   label column of row r = label_begin + r in global column coordinates); the other
+ *                   rows contribute to the log-sum-exp only.  nans_clip_loss_fwd_phase = (0, n_loc).
+ *   _finalize_rows: additionally writes per-row terms, row_stats[3][2 * n_loc] (strip-major like the
+ *                   lse arrays): [0] lse_r - logit_rr, [1] E_softmax_r[cos] - cos_rr, [2] the arg-max
+ *                   column as int32 bits (-1 without NANS_LOSS_WITH_ACC).  NULL = not wanted. */
+int nans_clip_loss_fwd_phase_rows(const void* I_loc, const void* T_loc, int64_t ld_loc,
+                                  const void* T_cols, const void* I_cols, int64_t ld_cols,
+                                  int feat_dtype, int64_t n_loc, int64_t ncols, int64_t D,
+                                  int64_t col_global_begin, int64_t label_begin,
+                                  int64_t label_row_begin, int64_t label_row_count,
+                                  int64_t skip_col_begin, int64_t skip_col_count, const float* s_dev,
+                                  int flags, void* ws, size_t ws_bytes, int64_t slot_begin,
+                                  void* stream);
+int nans_clip_loss_fwd_finalize_rows(int64_t n_loc, int64_t total_slots, int64_t label_begin,
+                                     const float* s_dev, int flags, void* ws, size_t ws_bytes,
+                                     float* lse_img_loc, float* lse_txt_loc, float* scalars,
+                                     float* row_stats, void* stream);
+
 /* Convenience: one phase over all columns + finalize (single-GPU / after a blocking gather). */
 int nans_clip_loss_fwd(const void* I_loc, const void* T_loc, int64_t ld_loc, const void* T_all,
                        const void* I_all, int64_t ld_all, int feat_dtype, int64_t n_loc,

@@ -43,6 +43,12 @@ _SIGNATURES = {
                                          c_int, c_int64, c_int64, c_int64, c_int64, c_int64,
                                          c_int64, c_int64,
                                          c_void_p, c_int, c_void_p, c_size_t, c_int64, c_void_p]),
+    "nans_clip_loss_fwd_phase_rows": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64,
+                                              c_int, c_int64, c_int64, c_int64, c_int64, c_int64,
+                                              c_int64, c_int64, c_int64, c_int64,
+                                              c_void_p, c_int, c_void_p, c_size_t, c_int64, c_void_p]),
+    "nans_clip_loss_fwd_finalize_rows": (c_int, [c_int64, c_int64, c_int64, c_void_p, c_int, c_void_p,
+                                                 c_size_t, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "nans_clip_loss_fwd_finalize": (c_int, [c_int64, c_int64, c_int64, c_void_p, c_int, c_void_p,
                                             c_size_t, c_void_p, c_void_p, c_void_p, c_void_p]),
     "nans_clip_loss_fwd": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int,

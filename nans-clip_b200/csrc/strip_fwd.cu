@@ -28,7 +28,8 @@ struct FwdParams {
   uint32_t idesc;
   int nrb, nsplit, ntiles;
   int strip0;       // first strip of this launch (1 for a text-rows-only launch)
-  int label_shift;  // label column of row r in phase coordinates = r + label_shift
+  int label_shift;  // label column of row r in phase coordinates = r + label_shift ...
+  int lab_row0, lab_row1;  // ... for rows in [lab_row0, lab_row1); the other rows have no label in this phase
   int col_global_begin;  // global column of phase column 0
   int skip_begin, skip_count;  // tiles of the column operand this phase does not sweep
   const float* s_dev;
@@ -150,7 +151,8 @@ clip_fwd_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
   const int row = a.row0 + (warp & 3) * 32 + lane;
 
   LseEpi<WITH_ACC> epi;
-  epi.init(__ldg(p.s_dev) * kLog2e, p.ncols, row + p.label_shift, lane);
+  epi.init(__ldg(p.s_dev) * kLog2e, p.ncols,
+           (row >= p.lab_row0 && row < p.lab_row1) ? row + p.label_shift : -(1 << 29), lane);
 
   uint8_t* scratch = run<A_RES, CP>(a, epi);
 
@@ -224,6 +226,7 @@ struct FinParams {
   double* block_part;  // [gridDim.x][6]
   unsigned* counter;
   float* scalars;  // [8]
+  float* row_stats;  // optional [3][2 * n_loc]: per-row loss term, d/ds term, arg-max column (int bits)
 };
 
 __global__ void __launch_bounds__(256) clip_fwd_finalize_kernel(const FinParams p) {
@@ -261,6 +264,11 @@ __global__ void __launch_bounds__(256) clip_fwd_finalize_kernel(const FinParams 
     acc[strip] = static_cast<double>(lse) - static_cast<double>(sc) * cosd;
     acc[2 + strip] = static_cast<double>(Wt) / static_cast<double>(L) - cosd;
     if (p.with_acc) acc[4 + strip] = (bi == p.label_begin + row) ? 1.0 : 0.0;
+    if (p.row_stats) {
+      p.row_stats[gid] = static_cast<float>(acc[strip]);
+      p.row_stats[total + gid] = static_cast<float>(acc[2 + strip]);
+      p.row_stats[2 * total + gid] = __int_as_float(bi);
+    }
   }
   // block reduction (fixed order -> deterministic)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -391,6 +399,19 @@ extern "C" int nans_clip_loss_fwd_phase(const void* I_loc, const void* T_loc, in
                                         int64_t skip_col_begin, int64_t skip_col_count,
                                         const float* s_dev, int flags, void* ws, size_t ws_bytes,
                                         int64_t slot_begin, void* stream) {
+  return nans_clip_loss_fwd_phase_rows(I_loc, T_loc, ld_loc, T_cols, I_cols, ld_cols, feat_dtype, n_loc, ncols, D,
+                                       col_global_begin, label_begin, 0, n_loc, skip_col_begin, skip_col_count,
+                                       s_dev, flags, ws, ws_bytes, slot_begin, stream);
+}
+
+extern "C" int nans_clip_loss_fwd_phase_rows(const void* I_loc, const void* T_loc, int64_t ld_loc,
+                                             const void* T_cols, const void* I_cols, int64_t ld_cols,
+                                             int feat_dtype, int64_t n_loc, int64_t ncols, int64_t D,
+                                             int64_t col_global_begin, int64_t label_begin,
+                                             int64_t label_row_begin, int64_t label_row_count,
+                                             int64_t skip_col_begin, int64_t skip_col_count,
+                                             const float* s_dev, int flags, void* ws, size_t ws_bytes,
+                                             int64_t slot_begin, void* stream) {
   int rc = check_device();
   if (rc != NANS_OK) return rc;
   NANS_REQUIRE(feat_dtype == NANS_F16 || feat_dtype == NANS_BF16,
@@ -402,6 +423,8 @@ extern "C" int nans_clip_loss_fwd_phase(const void* I_loc, const void* T_loc, in
   NANS_REQUIRE(I_loc && T_loc && T_cols && I_cols && s_dev && ws, "loss_fwd: null pointer");
   NANS_REQUIRE(ld_loc >= D && ld_cols >= D, "loss_fwd: leading dimension smaller than D");
   NANS_REQUIRE(slot_begin >= 0, "loss_fwd: negative slot");
+  NANS_REQUIRE(label_row_begin >= 0 && label_row_count >= 0 && label_row_begin + label_row_count <= n_loc,
+               "loss_fwd: the label row range must lie inside the local rows");
   NANS_REQUIRE(skip_col_begin >= 0 && skip_col_count >= 0 && skip_col_begin % BN == 0 &&
                    skip_col_count % BN == 0 && skip_col_begin + skip_col_count <= ncols,
                "loss_fwd: the skipped column range must be made of whole 256-column tiles inside the operand");
@@ -443,6 +466,8 @@ extern "C" int nans_clip_loss_fwd_phase(const void* I_loc, const void* T_loc, in
   p.skip_begin = skip_col_count > 0 ? static_cast<int>(skip_col_begin / BN) : (1 << 30);
   p.skip_count = static_cast<int>(skip_col_count / BN);
   p.label_shift = static_cast<int>(label_begin - col_global_begin);
+  p.lab_row0 = static_cast<int>(label_row_begin);
+  p.lab_row1 = static_cast<int>(label_row_begin + label_row_count);
   p.col_global_begin = static_cast<int>(col_global_begin);
   p.s_dev = s_dev;
   p.part_m = w.part_m;
@@ -475,6 +500,14 @@ extern "C" int nans_clip_loss_fwd_finalize(int64_t n_loc, int64_t total_slots, i
                                            const float* s_dev, int flags, void* ws, size_t ws_bytes,
                                            float* lse_img_loc, float* lse_txt_loc, float* scalars,
                                            void* stream) {
+  return nans_clip_loss_fwd_finalize_rows(n_loc, total_slots, label_begin, s_dev, flags, ws, ws_bytes, lse_img_loc,
+                                          lse_txt_loc, scalars, nullptr, stream);
+}
+
+extern "C" int nans_clip_loss_fwd_finalize_rows(int64_t n_loc, int64_t total_slots, int64_t label_begin,
+                                                const float* s_dev, int flags, void* ws, size_t ws_bytes,
+                                                float* lse_img_loc, float* lse_txt_loc, float* scalars,
+                                                float* row_stats, void* stream) {
   int rc = check_device();
   if (rc != NANS_OK) return rc;
   NANS_REQUIRE(n_loc > 0 && total_slots > 0, "loss_fwd_finalize: empty problem");
@@ -504,6 +537,7 @@ extern "C" int nans_clip_loss_fwd_finalize(int64_t n_loc, int64_t total_slots, i
   p.block_part = w.block_part;
   p.counter = w.counter;
   p.scalars = scalars;
+  p.row_stats = row_stats;
   const unsigned grid = static_cast<unsigned>(ceil_div(2 * n_loc, 256));
   clip_fwd_finalize_kernel<<<grid, 256, 0, st>>>(p);
   NANS_CUDA_OK(cudaGetLastError());

@@ -125,44 +125,59 @@ def fwd_workspace(n_loc: int, total_slots: int, device) -> torch.Tensor:
     return torch.empty(nbytes, dtype=torch.uint8, device=device)
 
 
+def clone_workspace(ws: torch.Tensor) -> torch.Tensor:
+    """A copy of a forward workspace with its slots (the incremental accumulate path keeps the slots of
+    the cached features and overwrites one column chunk's slots per call)."""
+    return ws.clone()
+
+
 def fwd_phase(I_loc, T_loc, T_cols, I_cols, *, col_global_begin: int, label_begin: int,
               s_dev: torch.Tensor, with_acc: bool, ws: torch.Tensor, slot_begin: int,
-              skip_begin: int = 0, skip_count: int = 0, strip: str | None = None) -> None:
+              skip_begin: int = 0, skip_count: int = 0, strip: str | None = None,
+              label_rows: tuple[int, int] | None = None) -> None:
     """One phase of the forward column sweep; columns [skip_begin, skip_begin + skip_count) of the
     operands (multiples of 256) are left to another phase.  `strip` = "img" sweeps only the image
     rows against `T_cols` (`I_cols` is not read), "txt" only the text rows against `I_cols`; the
-    two launches of one column range share their slot range."""
+    two launches of one column range share their slot range.  `label_rows` = (first row, count): only
+    these rows have their label column among this phase's columns (`label_begin` refers to them:
+    label column of row r = label_begin + r); default all rows."""
     _require_cuda(I_loc, T_loc, T_cols, I_cols, s_dev, ws)
     n_loc, D = I_loc.shape
     ncols = T_cols.shape[0]
     assert I_loc.dtype == T_loc.dtype == T_cols.dtype == I_cols.dtype
     assert I_loc.stride(0) == T_loc.stride(0) and T_cols.stride(0) == I_cols.stride(0)
+    lr0, lrn = label_rows if label_rows is not None else (0, n_loc)
     with _on_device(I_loc.device) as stream:
-        check(_lib.load().nans_clip_loss_fwd_phase(
+        check(_lib.load().nans_clip_loss_fwd_phase_rows(
             I_loc.data_ptr(), T_loc.data_ptr(), I_loc.stride(0), T_cols.data_ptr(),
             I_cols.data_ptr(), T_cols.stride(0), dtype_code(I_loc.dtype), n_loc, ncols, D,
-            col_global_begin, label_begin, skip_begin, skip_count, s_dev.data_ptr(),
+            col_global_begin, label_begin, lr0, lrn, skip_begin, skip_count, s_dev.data_ptr(),
             (NANS_LOSS_WITH_ACC if with_acc else 0) | _STRIP_FLAG[strip], ws.data_ptr(), ws.numel(),
             slot_begin, stream))
     _count(1)
 
 
 def fwd_finalize(n_loc: int, total_slots: int, label_begin: int, s_dev: torch.Tensor,
-                 with_acc: bool, ws: torch.Tensor):
+                 with_acc: bool, ws: torch.Tensor, want_row_stats: bool = False):
     """Returns (lse2 [2, n_loc] (row 0 image->text, row 1 text->image; base-2 log-sum-exp),
     scalars [8], packed) — `packed` is the single contiguous buffer [2 * pad + 8] both views live
     in (pad = n_loc rounded up to 4, keeping row 1 16-byte aligned), so that a multi-rank caller
-    can exchange lse and the partial scalars with ONE all-gather."""
+    can exchange lse and the partial scalars with ONE all-gather.  With `want_row_stats` a fourth
+    value follows: [3, 2, n_loc] fp32 per-row terms (loss term, d/ds term, arg-max column as int32
+    bits), strip-major like lse — what the incremental accumulate path sums over row subsets."""
     pad = (n_loc + 3) // 4 * 4
     packed = torch.empty((2 * pad + 8,), dtype=torch.float32, device=ws.device)
     lse = packed[:2 * pad].view(2, pad)[:, :n_loc]
     scalars = packed[2 * pad:]
+    rows = torch.empty((3, 2, n_loc), dtype=torch.float32, device=ws.device) if want_row_stats else None
     with _on_device(ws.device) as stream:
-        check(_lib.load().nans_clip_loss_fwd_finalize(
+        check(_lib.load().nans_clip_loss_fwd_finalize_rows(
             n_loc, total_slots, label_begin, s_dev.data_ptr(),
             NANS_LOSS_WITH_ACC if with_acc else 0, ws.data_ptr(), ws.numel(),
-            lse[0].data_ptr(), lse[1].data_ptr(), scalars.data_ptr(), stream))
+            lse[0].data_ptr(), lse[1].data_ptr(), scalars.data_ptr(), _ptr(rows), stream))
     _count(1)
+    if want_row_stats:
+        return lse, scalars, packed, rows
     return lse, scalars, packed
 
 

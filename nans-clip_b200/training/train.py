@@ -20,6 +20,7 @@ import torch.distributed as dist
 import torch.nn as nn
 import torch.nn.functional as F
 
+from .. import accum
 from ..loss import clip_contrastive_loss
 
 # 16-bit operand type handed to the tensor cores.  fp16 keeps unit-norm features 8x more precisely
@@ -89,12 +90,22 @@ def get_loss(model, images, texts, loss_img, loss_txt, args, accum_image_feature
     if args.aggregate and group is None:
         raise RuntimeError("args.aggregate is set but torch.distributed is not initialised "
                            "(the reference calls dist.get_world_size() here, train.py:54)")
-    total_loss, acc = clip_contrastive_loss(
-        image_features, text_features, logit_scale, group=group,
-        gather_with_grad=bool(args.aggregate and args.gather_with_grad),
-        report_acc=bool(args.report_training_batch_acc), feat_dtype=FEAT_DTYPE,
-        full_image_features=full_image_features, full_text_features=full_text_features,
-        row_begin=row_begin, label_smoothing=smoothing)
+    world = dist.get_world_size(group) if group is not None else 1
+    if (args.accum_freq > 1 and image_features.is_cuda
+            and accum.eligible(accum_image_features, accum_text_features, int(image_features.shape[0]), world,
+                               smoothing)):
+        # only chunk j's rows and columns differ from the cached features: incremental forward (accum.py)
+        total_loss, acc = accum.incremental_accum_loss(
+            image_features, text_features, logit_scale, accum_image_features, accum_text_features, accum_idx,
+            group=group, gather_with_grad=bool(args.aggregate and args.gather_with_grad),
+            report_acc=bool(args.report_training_batch_acc), feat_dtype=FEAT_DTYPE)
+    else:
+        total_loss, acc = clip_contrastive_loss(
+            image_features, text_features, logit_scale, group=group,
+            gather_with_grad=bool(args.aggregate and args.gather_with_grad),
+            report_acc=bool(args.report_training_batch_acc), feat_dtype=FEAT_DTYPE,
+            full_image_features=full_image_features, full_text_features=full_text_features,
+            row_begin=row_begin, label_smoothing=smoothing)
 
     if args.distillation:
         # outside the fused path: plain PyTorch, same gather order as train.py:90-100

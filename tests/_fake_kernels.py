@@ -14,7 +14,7 @@ STATE = {}
 
 def install(K):
     for name in ("l2norm_cast", "fwd_phase_slots", "fwd_workspace", "fwd_phase", "fwd_finalize", "bwd",
-                 "smooth_stats", "smooth_bwd", "topk_ip", "topk_merge"):
+                 "smooth_stats", "smooth_bwd", "clone_workspace", "topk_ip", "topk_merge"):
         setattr(K, name, globals()[name])
 
 
@@ -37,8 +37,17 @@ def fwd_workspace(n_loc, total_slots, device):
     return t
 
 
+def clone_workspace(ws):
+    import copy
+    t = torch.zeros(16, dtype=torch.uint8)
+    src = STATE[ws.data_ptr()]
+    STATE[t.data_ptr()] = {"slots": {k: dict(v) for k, v in src["slots"].items()}, "diag": src["diag"].clone(),
+                           "n": src["n"]}
+    return t
+
+
 def fwd_phase(I_loc, T_loc, T_cols, I_cols, *, col_global_begin, label_begin, s_dev, with_acc, ws, slot_begin,
-              skip_begin=0, skip_count=0, strip=None):
+              skip_begin=0, skip_count=0, strip=None, label_rows=None):
     st = STATE[ws.data_ptr()]
     s = float(s_dev)
     n_loc, ncols = I_loc.shape[0], T_cols.shape[0]
@@ -52,7 +61,8 @@ def fwd_phase(I_loc, T_loc, T_cols, I_cols, *, col_global_begin, label_begin, s_
         entry = st["slots"].setdefault(slot_begin + sl, {})
         for k in strips:
             A, B = ((I_loc, T_cols), (T_loc, I_cols))[k]
-            assert k not in entry, "a slot half was written twice"
+            # (a slot may be overwritten on purpose: the incremental accumulate path replaces one
+            #  column chunk's slots in a cloned workspace)
             cos = A.float() @ B[cols].float().t()
             t = cos * (s * math.log2(math.e))
             m = t.max(dim=1).values
@@ -60,6 +70,9 @@ def fwd_phase(I_loc, T_loc, T_cols, I_cols, *, col_global_begin, label_begin, s_
             bv, bj = cos.max(dim=1)
             entry[k] = (m, e.sum(1), (e * cos).sum(1), bv, cols[bj] + col_global_begin)
             lab = torch.arange(n_loc) + label_begin - col_global_begin
+            if label_rows is not None:
+                in_rows = (torch.arange(n_loc) >= label_rows[0]) & (torch.arange(n_loc) < label_rows[0] + label_rows[1])
+                lab = torch.where(in_rows, lab, torch.full_like(lab, -1))
             pos = torch.full((ncols + 1,), -1, dtype=torch.long)
             pos[cols] = torch.arange(cols.numel())
             where = pos[lab.clamp(0, ncols)]
@@ -79,8 +92,9 @@ def smooth_bwd(dI, dT, I_rows, T_rows, stats, s_dev, grad_out, coef, inv_n):
     dT += a * I_rows - a * inv_n * stats[:D]
 
 
-def fwd_finalize(n_loc, total_slots, label_begin, s_dev, with_acc, ws):
+def fwd_finalize(n_loc, total_slots, label_begin, s_dev, with_acc, ws, want_row_stats=False):
     st = STATE.pop(ws.data_ptr())
+    rows = torch.zeros(3, 2, n_loc)
     assert sorted(st["slots"]) == list(range(total_slots)), "a slot was skipped"
     assert all(sorted(e) == [0, 1] for e in st["slots"].values()), "a slot half was left unwritten"
     s = float(s_dev)
@@ -102,7 +116,11 @@ def fwd_finalize(n_loc, total_slots, label_begin, s_dev, with_acc, ws):
         sc[2 + strip] = ((Wt / L).double() - d.double()).sum()
         if with_acc:
             sc[4 + strip] = (arg == torch.arange(n_loc) + label_begin).sum()
-    return lse, sc, torch.cat([lse.reshape(-1), sc])
+        rows[0, strip] = (lse[strip].double() * math.log(2) - s * d.double()).float()
+        rows[1, strip] = ((Wt / L).double() - d.double()).float()
+        rows[2, strip] = (arg if with_acc else torch.full_like(arg, -1)).to(torch.int32).view(torch.float32)
+    packed = torch.cat([lse.reshape(-1), sc])
+    return (lse, sc, packed, rows) if want_row_stats else (lse, sc, packed)
 
 
 def bwd(I_loc, T_loc, T_all, I_all, *, label_begin, s_dev, lse_all, grad_out, grad_mult, row_begin,

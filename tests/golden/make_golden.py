@@ -12,6 +12,8 @@ at module load, and `Tensor.cuda` -> identity because `get_loss` hard-codes `.cu
   loss_w1_*.npz      get_loss (aggregate=False), loss / acc / autograd gradients
   loss_dist_*.npz    get_loss under torch.distributed gloo, W ranks, both gather modes
   loss_accum_*.npz   get_loss on the gradient-accumulation path (train.py:34-51)
+  loss_accum4_*.npz  the same with 4 chunks of 256 rows and a re-forwarded chunk that differs from its cache
+                     (features stored as their bf16 bit patterns: they are bf16-exact by construction)
   tail_*.npz         CLIP.forward normalise lines + get_similarity (model.py:412-431)
   topk_*.npz         make_topk_predictions.py / _tr.py run as scripts on small JSONL files
   lora_loss_*.npz    train_lora.py `contrastive_loss` (label-smoothed InfoNCE), value + gradients
@@ -168,6 +170,36 @@ def gen_loss_accum():
         print("loss_accum", j, float(total))
 
 
+def gen_loss_accum_big():
+    """accum_freq = 4 with 256-row chunks (what the incremental accumulate path needs) and a
+    re-forwarded chunk that DIFFERS from its cached copy (the reference re-forwards with masking /
+    dropout, train.py:35 vs :210): calls j = 2 then j = 0 of one optimizer step."""
+    from cn_clip.training.train import get_loss
+    A, B, d, ls = 4, 256, 64, 2.9
+    img, txt = synth(A * B, d, 4242, 0.5)
+    cache_i = [img[a * B:(a + 1) * B].clone() for a in range(A)]
+    cache_t = [txt[a * B:(a + 1) * B].clone() for a in range(A)]
+    g = torch.Generator().manual_seed(99)
+    for j in (2, 0):
+        ni = img[j * B:(j + 1) * B] + 0.05 * torch.randn(B, d, generator=g)
+        nt = txt[j * B:(j + 1) * B] + 0.05 * torch.randn(B, d, generator=g)
+        ni = (ni / ni.norm(dim=-1, keepdim=True)).bfloat16().float()
+        nt = (nt / nt.norm(dim=-1, keepdim=True)).bfloat16().float()
+        model = StubModel(ni, nt, ls)
+        args = make_args(accum_freq=A)
+        total, acc = get_loss(model, None, None, nn.CrossEntropyLoss(), nn.CrossEntropyLoss(), args,
+                              cache_i, cache_t, j)
+        total.backward()
+        bits = lambda x: x.bfloat16().view(torch.int16).numpy()   # the features are bf16-exact: store the bit patterns
+        assert all(bool((x.bfloat16().float() == x).all()) for x in (img, txt, ni, nt))
+        np.savez_compressed(HERE / f"loss_accum4_j{j}.npz", img_bf16=bits(img), txt_bf16=bits(txt),
+                            new_img_bf16=bits(ni), new_txt_bf16=bits(nt),
+                            logit_scale_log=ls, A=A, B=B, j=j, s=float(np.exp(ls)), loss=np_(total),
+                            i2t=np_(acc["i2t"]), t2i=np_(acc["t2i"]), dI=np_(model.img.grad), dT=np_(model.txt.grad),
+                            dlogit_scale_log=np_(model.logit_scale.grad))
+        print("loss_accum4", j, float(total))
+
+
 def gen_tail():
     from cn_clip.clip.model import CLIP
     torch.manual_seed(0)
@@ -276,9 +308,13 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "lora":
         gen_lora_loss()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "accum4":
+        gen_loss_accum_big()
+        sys.exit(0)
     gen_lora_loss()
     gen_loss_w1()
     gen_loss_accum()
+    gen_loss_accum_big()
     gen_tail()
     gen_topk()
     gen_loss_dist()

@@ -71,3 +71,69 @@ def test_two_ranks_nccl(name):
         p.join(timeout=60)
     for rank, ok, info in res:
         assert all(ok), f"rank {rank}: {ok} {info}"
+
+
+def _accum_worker(rank, W, port, q):
+    """Incremental accumulate path over NCCL: 4 chunks of 128 rows per rank (W * B = 256), calls
+    j = 1, 3, 0 of one optimizer step; oracle = full loss on the spliced, concatenated batch."""
+    try:
+        sys.path.insert(0, str(ROOT))
+        import torch.distributed as dist
+        os.environ["MASTER_ADDR"] = "127.0.0.1"
+        os.environ["MASTER_PORT"] = str(port)
+        torch.cuda.set_device(rank)
+        dev = torch.device("cuda", rank)
+        dist.init_process_group("nccl", rank=rank, world_size=W, device_id=dev)
+        from nans_clip_b200 import accum
+        from oracle import clip_loss as OL
+        A, B, D, s = 4, 128, 64, 14.2857
+        gen = torch.Generator().manual_seed(17)
+        n_loc = A * B
+        img = torch.nn.functional.normalize(torch.randn(W * n_loc, D, generator=gen), dim=-1).half().float()
+        txt = torch.nn.functional.normalize(img + 0.8 * torch.randn(W * n_loc, D, generator=gen), dim=-1).half().float()
+        mine = slice(rank * n_loc, (rank + 1) * n_loc)
+        cache_i = [img[mine][a * B:(a + 1) * B].to(dev) for a in range(A)]
+        cache_t = [txt[mine][a * B:(a + 1) * B].to(dev) for a in range(A)]
+        ok = [accum.eligible(cache_i, cache_t, B, W, 0.0)]
+        for j in (1, 3, 0):
+            new_i = torch.nn.functional.normalize(img + 0.1 * torch.randn(W * n_loc, D, generator=gen), dim=-1).half().float()
+            new_t = torch.nn.functional.normalize(txt + 0.1 * torch.randn(W * n_loc, D, generator=gen), dim=-1).half().float()
+            cur_i, cur_t = img.clone(), txt.clone()
+            for r in range(W):
+                blk = slice(r * n_loc + j * B, r * n_loc + (j + 1) * B)
+                cur_i[blk], cur_t[blk] = new_i[blk], new_t[blk]
+            want = OL.global_loss_and_grads(cur_i, cur_t, s, torch.float64)
+            blk = slice(rank * n_loc + j * B, rank * n_loc + (j + 1) * B)
+            ci = new_i[blk].to(dev).requires_grad_(True)
+            ct = new_t[blk].to(dev).requires_grad_(True)
+            sc = torch.tensor(s, device=dev, requires_grad=True)
+            loss, acc = accum.incremental_accum_loss(ci, ct, sc, cache_i, cache_t, j, group=dist.group.WORLD,
+                                                     report_acc=True)
+            loss.backward()
+            ok.append(abs(float(loss) - float(want["loss"])) <= 1e-3 * abs(float(want["loss"])))
+            ok.append(abs(float(acc["i2t"]) - float(want["i2t"])) < 1e-6)
+            for got, w in ((ci.grad, want["dI"][blk]), (ct.grad, want["dT"][blk])):
+                ok.append(float((got.cpu().double() - w.double()).norm() / w.double().norm()) < 1e-3)
+            ok.append(abs(float(sc.grad) - float(want["ds"])) <= 1e-3 * abs(float(want["ds"])))
+        q.put((rank, ok, ""))
+        dist.barrier()
+        dist.destroy_process_group()
+    except Exception:
+        import traceback
+        q.put((rank, [False], traceback.format_exc()))
+
+
+def test_incremental_accumulate_two_ranks_nccl():
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_accum_worker, args=(r, 2, 29811, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, ok, info in res:
+        assert all(ok), f"rank {rank}: {ok} {info}"

@@ -285,6 +285,93 @@ def test_accumulate_path_rows(dev, golden_dir):
         assert relerr(ct.grad.cpu(), torch.from_numpy(g["dT"])) < 3e-3
 
 
+def test_incremental_accumulate_path_matches_reference(dev, golden_dir, monkeypatch):
+    """get_loss on the accumulate path with 4 chunks of 256 rows goes through the
+    incremental forward (accum.py): calls j = 2 then j = 0 of ONE optimizer step (same cache lists,
+    re-forwarded chunks that differ from their cached copies) against the reference's own outputs,
+    and against the full recomputation (NANS_ACCUM_INCREMENTAL=0)."""
+    import types
+    import torch.nn as nn
+    from nans_clip_b200 import accum
+    from nans_clip_b200.training.train import get_loss
+
+    def bf(bits):
+        return torch.from_numpy(bits).view(torch.bfloat16).float().to(dev)
+
+    g0 = np.load(golden_dir / "loss_accum4_j2.npz")
+    A, B = int(g0["A"]), int(g0["B"])
+    img, txt = bf(g0["img_bf16"]), bf(g0["txt_bf16"])
+
+    class Stub(nn.Module):
+        def __init__(self, ni, nt, ls):
+            super().__init__()
+            self.img, self.txt = nn.Parameter(ni), nn.Parameter(nt)
+            self.logit_scale = nn.Parameter(torch.tensor(ls, device=dev))
+
+        def forward(self, images, texts, mask_ratio=0):
+            return self.img, self.txt, self.logit_scale.exp()
+
+    args = types.SimpleNamespace(accum_freq=A, mask_ratio=0, distillation=False, aggregate=False,
+                                 gather_with_grad=False, local_device_rank=0, report_training_batch_acc=True)
+    results = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("NANS_ACCUM_INCREMENTAL", mode)
+        cache_i = [img[a * B:(a + 1) * B].clone() for a in range(A)]
+        cache_t = [txt[a * B:(a + 1) * B].clone() for a in range(A)]
+        for j in (2, 0):
+            g = np.load(golden_dir / f"loss_accum4_j{j}.npz")
+            model = Stub(bf(g["new_img_bf16"]), bf(g["new_txt_bf16"]), float(g["logit_scale_log"]))
+            total, acc = get_loss(model, None, None, nn.CrossEntropyLoss(), nn.CrossEntropyLoss(), args,
+                                  cache_i, cache_t, j)
+            total.backward()
+            assert (getattr(cache_i[0], accum._ATTR, None) is not None) == (mode == "1")
+            s = float(g["s"])
+            assert abs(float(total) - float(g["loss"])) <= TOL * float(g["loss"])
+            assert abs(float(acc["i2t"]) - float(g["i2t"])) < 1e-6 and abs(float(acc["t2i"]) - float(g["t2i"])) < 1e-6
+            assert grad_ok(model.img.grad.cpu(), torch.from_numpy(g["dI"]), A * B, s)
+            assert grad_ok(model.txt.grad.cpu(), torch.from_numpy(g["dT"]), A * B, s)
+            assert abs(float(model.logit_scale.grad) - float(g["dlogit_scale_log"])) <= TOL * abs(float(g["dlogit_scale_log"]))
+            results[(mode, j)] = (float(total), model.img.grad.clone())
+    for j in (2, 0):   # same tiles, same operands: the two paths agree far below the tolerance
+        assert abs(results[("1", j)][0] - results[("0", j)][0]) <= 2e-6 * abs(results[("0", j)][0])
+        assert relerr(results[("1", j)][1], results[("0", j)][1]) < 1e-4
+
+
+def test_incremental_accumulate_larger_and_ragged_d(dev):
+    """A = 5 chunks of 512 rows, D = 72, scale 50, calls in arbitrary order incl. a repeated chunk:
+    incremental path against the full path on the spliced block."""
+    from nans_clip_b200 import accum
+    from nans_clip_b200.loss import clip_contrastive_loss
+    A, B, d, s = 5, 512, 72, 50.0
+    I, T = synth(A * B, d, 31, 0.5)
+    I, T = I.to(dev), T.to(dev)
+    cache_i = [I[a * B:(a + 1) * B].clone() for a in range(A)]
+    cache_t = [T[a * B:(a + 1) * B].clone() for a in range(A)]
+    assert accum.eligible(cache_i, cache_t, B, 1, 0.0) and not accum.eligible(cache_i[:3], cache_t[:3], B, 1, 0.0)
+    gen = torch.Generator(device=dev).manual_seed(5)
+    for j in (4, 1, 1, 0):
+        ni = torch.nn.functional.normalize(cache_i[j] + 0.1 * torch.randn(B, d, device=dev, generator=gen), dim=-1)
+        nt = torch.nn.functional.normalize(cache_t[j] + 0.1 * torch.randn(B, d, device=dev, generator=gen), dim=-1)
+        outs = []
+        for inc in (True, False):
+            ci, ct = ni.clone().requires_grad_(True), nt.clone().requires_grad_(True)
+            sc = torch.tensor(s, device=dev, requires_grad=True)
+            if inc:
+                loss, acc = accum.incremental_accum_loss(ci, ct, sc, cache_i, cache_t, j, report_acc=True)
+            else:
+                full_i = torch.cat(cache_i[:j] + [ni] + cache_i[j + 1:])
+                full_t = torch.cat(cache_t[:j] + [nt] + cache_t[j + 1:])
+                loss, acc = clip_contrastive_loss(ci, ct, sc, report_acc=True, full_image_features=full_i,
+                                                  full_text_features=full_t, row_begin=j * B)
+            loss.backward()
+            outs.append((float(loss), ci.grad, ct.grad, float(sc.grad), float(acc["i2t"]), float(acc["t2i"])))
+        a, b = outs
+        assert abs(a[0] - b[0]) <= 2e-6 * abs(b[0]) + 1e-7
+        assert relerr(a[1], b[1]) < 1e-4 and relerr(a[2], b[2]) < 1e-4
+        assert abs(a[3] - b[3]) <= 1e-4 * abs(b[3]) + 1e-8
+        assert a[4] == b[4] and a[5] == b[5]
+
+
 def test_get_loss_dropin_signature_and_values(dev, golden_dir):
     """The drop-in get_loss, called exactly as train.py:192-203 calls the reference's."""
     import types

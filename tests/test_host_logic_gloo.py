@@ -113,6 +113,60 @@ def test_label_smoothing_under_gloo(gwg, port):
         assert all(ok), f"rank {rank}: {ok} {info}"
 
 
+def _accum_worker(rank, W, port, gwg, q):
+    """Incremental accumulate path (accum.py) across ranks: 4 chunks of 128 rows per rank, calls
+    j = 1, 3, 0 of one optimizer step with re-forwarded chunks that differ from the cache; oracle =
+    the full loss on the spliced, concatenated batch."""
+    try:
+        _init(rank, W, port)
+        from nans_clip_b200 import accum
+        from oracle import clip_loss as OL
+        A, B, D, s = 4, 128, 24, 12.0
+        gen = torch.Generator().manual_seed(17)
+        n_loc = A * B
+        img = torch.nn.functional.normalize(torch.randn(W * n_loc, D, generator=gen), dim=-1)
+        txt = torch.nn.functional.normalize(img + 0.8 * torch.randn(W * n_loc, D, generator=gen), dim=-1)
+        mine = slice(rank * n_loc, (rank + 1) * n_loc)
+        cache_i = [img[mine][a * B:(a + 1) * B].clone() for a in range(A)]
+        cache_t = [txt[mine][a * B:(a + 1) * B].clone() for a in range(A)]
+        assert accum.eligible(cache_i, cache_t, B, W, 0.0)
+        ok = []
+        for j in (1, 3, 0):
+            # every rank re-forwards its chunk j: the global batch differs from the cache in W blocks
+            new_i = torch.nn.functional.normalize(img + 0.1 * torch.randn(W * n_loc, D, generator=gen), dim=-1)
+            new_t = torch.nn.functional.normalize(txt + 0.1 * torch.randn(W * n_loc, D, generator=gen), dim=-1)
+            cur_i, cur_t = img.clone(), txt.clone()
+            for r in range(W):
+                blk = slice(r * n_loc + j * B, r * n_loc + (j + 1) * B)
+                cur_i[blk], cur_t[blk] = new_i[blk], new_t[blk]
+            want = OL.global_loss_and_grads(cur_i, cur_t, s, torch.float64)
+            blk = slice(rank * n_loc + j * B, rank * n_loc + (j + 1) * B)
+            ci = new_i[blk].clone().requires_grad_(True)
+            ct = new_t[blk].clone().requires_grad_(True)
+            sc = torch.tensor(s, requires_grad=True)
+            loss, acc = accum.incremental_accum_loss(ci, ct, sc, cache_i, cache_t, j, group=dist.group.WORLD,
+                                                     gather_with_grad=gwg, report_acc=True, feat_dtype=torch.float32)
+            loss.backward()
+            mult = float(W) if gwg else 1.0
+            ok.append(abs(float(loss) - float(want["loss"])) <= 1e-5 * abs(float(want["loss"])))
+            ok.append(abs(float(acc["i2t"]) - float(want["i2t"])) < 1e-6 and abs(float(acc["t2i"]) - float(want["t2i"])) < 1e-6)
+            for got, w in ((ci.grad, want["dI"][blk]), (ct.grad, want["dT"][blk])):
+                ok.append(float((got.double() - mult * w.double()).abs().max()) <= 1e-4 * mult * float(w.abs().max()))
+            ok.append(abs(float(sc.grad) - float(want["ds"])) <= 1e-4 * abs(float(want["ds"])) + 1e-9)
+        q.put((rank, ok, ""))
+        dist.barrier()
+        dist.destroy_process_group()
+    except Exception:
+        import traceback
+        q.put((rank, [False], traceback.format_exc()))
+
+
+@pytest.mark.parametrize("gwg,port", [(False, 29731), (True, 29732)])
+def test_incremental_accumulate_under_gloo(gwg, port):
+    for rank, ok, info in _spawn(_accum_worker, 2, port, gwg):
+        assert all(ok), f"rank {rank}: {ok} {info}"
+
+
 def _strip_split_worker(rank, W, port, gwg, q):
     """n_loc = 256: the tile-aligned path (local block, then one single-strip launch per gathered
     tensor sharing their slots) against the oracle on the concatenated batch."""

@@ -83,6 +83,31 @@ def test_accumulate_path_matches_reference(golden_dir, j):
     assert torch.allclose(ls.grad, _t(g["dlogit_scale_log"]), rtol=1e-5)
 
 
+def _bf16(bits):
+    return torch.from_numpy(bits).view(torch.bfloat16).float()
+
+
+@pytest.mark.parametrize("j", [2, 0])
+def test_accumulate_path_with_a_changed_chunk_matches_reference(golden_dir, j):
+    """4 chunks of 256 rows, the re-forwarded chunk differs from its cached copy (fixtures of the
+    incremental accumulate path)."""
+    g = _load(golden_dir / f"loss_accum4_j{j}.npz")
+    A, B = int(g["A"]), int(g["B"])
+    img, txt = _bf16(g["img_bf16"]), _bf16(g["txt_bf16"])
+    cache_i = [img[a * B:(a + 1) * B] for a in range(A)]
+    cache_t = [txt[a * B:(a + 1) * B] for a in range(A)]
+    ci = _bf16(g["new_img_bf16"]).requires_grad_(True)
+    ct = _bf16(g["new_txt_bf16"]).requires_grad_(True)
+    ls = torch.tensor(float(g["logit_scale_log"]), requires_grad=True)
+    loss, acc = OL.local_loss(OL.accum_splice(cache_i, ci, j), OL.accum_splice(cache_t, ct, j), ls.exp(), True)
+    loss.backward()
+    assert torch.allclose(loss.detach(), _t(g["loss"]), rtol=1e-6)
+    assert torch.allclose(ci.grad, _t(g["dI"]), rtol=1e-5, atol=1e-9)
+    assert torch.allclose(ct.grad, _t(g["dT"]), rtol=1e-5, atol=1e-9)
+    assert torch.allclose(ls.grad, _t(g["dlogit_scale_log"]), rtol=1e-5)
+    assert abs(float(acc["i2t"]) - float(g["i2t"])) < 1e-6
+
+
 @pytest.mark.parametrize("name", ["a", "b", "c"])
 def test_forward_tail_matches_reference(golden_dir, name):
     g = _load(golden_dir / f"tail_{name}.npz")
@@ -183,4 +208,4 @@ def test_lora_label_smoothed_loss_matches_reference(golden_dir, name):
 
 def test_all_fixtures_are_covered(golden_dir):
     names = sorted(p.split("/")[-1] for p in glob.glob(str(golden_dir / "*.npz")))
-    assert len(names) == 22, names
+    assert len(names) == 24, names
