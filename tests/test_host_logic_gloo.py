@@ -218,7 +218,7 @@ def _topk_worker(rank, W, port, q):
         lo, hi = G * rank // W, G * (rank + 1) // W
 
         class FakeShard(retrieval.GalleryShard):
-            def __init__(self, gallery, device, feat_dtype, index_offset):
+            def __init__(self, gallery, device, feat_dtype, index_offset, gallery16=None):
                 self.g32 = gallery.float()
                 self.g16 = gallery.float()
                 self.feat_dtype = torch.float32
