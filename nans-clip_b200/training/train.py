@@ -78,11 +78,6 @@ def get_loss(model, images, texts, loss_img, loss_txt, args, accum_image_feature
             teacher_chunk = _teacher_features(teacher_model, images)
             teacher_image_features = torch.cat(teacher_accum_image_features[:accum_idx] + [teacher_chunk]
                                                + teacher_accum_image_features[accum_idx + 1:])
-        # the block the loss sees: chunk j spliced between the cached (no-grad) chunks
-        full_image_features = torch.cat(accum_image_features[:accum_idx] + [image_features.detach()]
-                                        + accum_image_features[accum_idx + 1:])
-        full_text_features = torch.cat(accum_text_features[:accum_idx] + [text_features.detach()]
-                                       + accum_text_features[accum_idx + 1:])
         row_begin = sum(int(f.shape[0]) for f in accum_image_features[:accum_idx])
     logit_scale = logit_scale.mean()
 
@@ -91,9 +86,16 @@ def get_loss(model, images, texts, loss_img, loss_txt, args, accum_image_feature
         raise RuntimeError("args.aggregate is set but torch.distributed is not initialised "
                            "(the reference calls dist.get_world_size() here, train.py:54)")
     world = dist.get_world_size(group) if group is not None else 1
-    if (args.accum_freq > 1 and image_features.is_cuda
-            and accum.eligible(accum_image_features, accum_text_features, int(image_features.shape[0]), world,
-                               smoothing)):
+    incremental = (args.accum_freq > 1 and image_features.is_cuda
+                   and accum.eligible(accum_image_features, accum_text_features, int(image_features.shape[0]),
+                                      world, smoothing))
+    if args.accum_freq > 1 and (not incremental or args.distillation):
+        # the block the loss sees: chunk j spliced between the cached (no-grad) chunks (train.py:48-51)
+        full_image_features = torch.cat(accum_image_features[:accum_idx] + [image_features.detach()]
+                                        + accum_image_features[accum_idx + 1:])
+        full_text_features = torch.cat(accum_text_features[:accum_idx] + [text_features.detach()]
+                                       + accum_text_features[accum_idx + 1:])
+    if incremental:
         # only chunk j's rows and columns differ from the cached features: incremental forward (accum.py)
         total_loss, acc = accum.incremental_accum_loss(
             image_features, text_features, logit_scale, accum_image_features, accum_text_features, accum_idx,
