@@ -197,6 +197,12 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1 to every rank; the reference arm is rank 0 alone on the host
+    # cores, so it takes all of them (what a plain `python bench.py --impl reference` gets by default)
+    try:
+        torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+    except (AttributeError, OSError):
+        torch.set_num_threads(max(1, os.cpu_count() or 1))
     if args.workload == "retrieval":
         base = cpu_topk_baseline()
         metric, cfg = "retrieval_queries_per_s", {"workload": f"top-{RET_K} retrieval Q={RET_Q} G={RET_G} D={D}"}
