@@ -183,6 +183,17 @@ int nans_clip_loss_fwd(const void* I_loc, const void* T_loc, int64_t ld_loc, con
  */
 size_t nans_clip_loss_bwd_workspace_bytes(int64_t grad_row_count, int64_t N, int64_t D);
 
+/* The launch schedule nans_clip_loss_bwd would use for (gradient rows, N, D) on the current device
+ * (148 SMs are assumed when there is none): diagnostics and the CPU test-suite.  Host only, no launch.
+ * out[0] kernel (0 single CTA, 1 wide pairs, 2 narrow pairs, 3 narrow pairs persistent), [1] column
+ * tile width, [2] passes over the logits, [3] A resident, [4] row blocks per strip, [5] column tiles,
+ * [6] ring stages, [7] dynamic shared memory bytes, [8] grid (CTAs), [9] uniform column splits,
+ * [10] units run unsplit, [11] column splits of the remaining units, [12] persistent: tiles a unit's
+ * own pair sweeps (0 = equal ranges), [13] persistent: units, [14] persistent: CTA pairs,
+ * [15] outputs zeroed first (0 none, 1 rows of the split units, 2 all). */
+#define NANS_BWD_PLAN_FIELDS 16
+int nans_clip_loss_bwd_plan(int64_t grad_row_count, int64_t N, int64_t D, int64_t* out, int n_out);
+
 int nans_clip_loss_bwd(const void* I_loc, const void* T_loc, int64_t ld_loc, const void* T_all,
                        const void* I_all, int64_t ld_all, int feat_dtype, int64_t n_loc,
                        int64_t N, int64_t D, int64_t label_begin, const float* s_dev,

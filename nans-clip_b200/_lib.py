@@ -55,6 +55,7 @@ _SIGNATURES = {
                                    c_int64, c_int64, c_int64, c_int64, c_void_p, c_int, c_void_p,
                                    c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "nans_clip_loss_bwd_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),
+    "nans_clip_loss_bwd_plan": (c_int, [c_int64, c_int64, c_int64, c_void_p, c_int]),
     "nans_clip_loss_bwd": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int,
                                    c_int64, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p,
                                    c_void_p, c_float, c_int64, c_int64, c_void_p, c_void_p, c_int,

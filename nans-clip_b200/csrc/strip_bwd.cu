@@ -141,47 +141,25 @@ int choose_bwd_nsplit(int64_t rows, int64_t N, int npass, int rows_per_unit, int
   return best;
 }
 
-}  // namespace
-}  // namespace nans
+// ---- which kernel, which grid: everything that depends only on (gradient rows, N, D) --------------
+enum BwdKind { BWD_1CTA = 0, BWD_WIDE_PAIR = 1, BWD_NARROW = 2, BWD_NARROW_PERSISTENT = 3 };
 
-using namespace nans;
+struct BwdSchedule {
+  int kind;
+  int kchunks, npass;          // 64-feature chunks; passes over the logits (feature slices of dA)
+  int tile_cols;               // column tile width
+  bool a_resident;
+  int nrb, ntiles, nr;         // row blocks per strip, column tiles, ring stages
+  int nsplit;                  // uniform column splits (wide kernels); 2 = "outputs are accumulated" for persistent
+  NpTail tail;                 // narrow: whole-wave units + column-split partial wave
+  int npp_t1, npp_units, npairs;  // persistent narrow kernel
+  size_t smem_bytes;
+  unsigned grid;
+  bool zero_all, zero_tail;    // which output rows must be zeroed before the launch
+};
 
-extern "C" size_t nans_clip_loss_bwd_workspace_bytes(int64_t grad_row_count, int64_t N, int64_t D) {
-  (void)N;
-  if (grad_row_count <= 0 || D <= 0) return 512;
-  return 2 * align_up(static_cast<size_t>(grad_row_count) * D * 4, 256) + 512;
-}
-
-extern "C" int nans_clip_loss_bwd(const void* I_loc, const void* T_loc, int64_t ld_loc,
-                                  const void* T_all, const void* I_all, int64_t ld_all,
-                                  int feat_dtype, int64_t n_loc, int64_t N, int64_t D,
-                                  int64_t label_begin, const float* s_dev, const float* lse_img_all,
-                                  const float* lse_txt_all, const float* grad_out_dev,
-                                  float grad_mult, int64_t grad_row_begin, int64_t grad_row_count,
-                                  void* dI_loc, void* dT_loc, int out_dtype, void* ws,
-                                  size_t ws_bytes, void* stream) {
-  int rc = check_device();
-  if (rc != NANS_OK) return rc;
-  NANS_REQUIRE(feat_dtype == NANS_F16 || feat_dtype == NANS_BF16,
-               "loss_bwd: feat_dtype must be NANS_F16 or NANS_BF16");
-  NANS_REQUIRE(out_dtype == NANS_F32 || out_dtype == NANS_F16 || out_dtype == NANS_BF16,
-               "loss_bwd: bad out_dtype");
-  NANS_REQUIRE(n_loc > 0 && N > 0 && D > 0 && D % 8 == 0, "loss_bwd: bad sizes (D must be a multiple of 8)");
-  NANS_REQUIRE(n_loc < (1ll << 30) && N < (1ll << 30) && D <= 8192, "loss_bwd: size too large");
-  NANS_REQUIRE(grad_row_begin >= 0 && grad_row_count >= 0 && grad_row_begin + grad_row_count <= n_loc,
-               "loss_bwd: gradient rows [%lld, +%lld) outside the local block of %lld rows",
-               (long long)grad_row_begin, (long long)grad_row_count, (long long)n_loc);
-  NANS_REQUIRE(label_begin >= 0 && label_begin + n_loc <= N, "loss_bwd: labels outside [0, N)");
-  if (grad_row_count == 0) return NANS_OK;
-  NANS_REQUIRE(I_loc && T_loc && T_all && I_all && s_dev && lse_img_all && lse_txt_all &&
-                   grad_out_dev && dI_loc && dT_loc,
-               "loss_bwd: null pointer");
-  NANS_REQUIRE(ld_loc >= D && ld_all >= D, "loss_bwd: leading dimension smaller than D");
-  NANS_REQUIRE((reinterpret_cast<uintptr_t>(lse_img_all) & 15) == 0 &&
-                   (reinterpret_cast<uintptr_t>(lse_txt_all) & 15) == 0,
-               "loss_bwd: lse arrays must be 16-byte aligned");
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-
+BwdSchedule plan_bwd_schedule(int64_t grad_row_count, int64_t N, int64_t D) {
+  BwdSchedule sc{};
   const int kchunks = static_cast<int>(ceil_div(D, BK));
   const int npass = static_cast<int>(ceil_div(kchunks, SLICE / BK));
   // CTA pairs (cta_group::2) by default; NANS_BWD_1CTA=1 selects the single-CTA kernel
@@ -245,6 +223,96 @@ extern "C" int nans_clip_loss_bwd(const void* I_loc, const void* T_loc, int64_t 
                      : use_np   ? 1  /* per-unit: see plan_np_tail */
                      : use_pair ? choose_bwd_nsplit(grad_row_count, N, npass, 2 * BM, sm_count() / 2)
                                 : choose_bwd_nsplit(grad_row_count, N, npass, BM, sm_count());
+  sc.kchunks = kchunks;
+  sc.npp_t1 = npp_t1;
+  sc.npp_units = npp_units;
+  sc.tail = tail;
+  sc.nsplit = nsplit;
+  sc.kind = use_npp ? BWD_NARROW_PERSISTENT : use_np ? BWD_NARROW : use_pair ? BWD_WIDE_PAIR : BWD_1CTA;
+  sc.npass = (use_np || use_npp) ? np_npass : npass;
+  sc.tile_cols = use_np ? np_tk : KT;
+  sc.a_resident = use_np ? np_ares : (use_pair ? pplan.a_resident : plan.a_resident);
+  sc.nrb = static_cast<int>(ceil_div(grad_row_count, use_np ? 2 * NP_ROWS : (use_pair ? 2 * BM : BM)));
+  sc.ntiles = static_cast<int>(ceil_div(N, sc.tile_cols));
+  sc.nr = use_np ? nplan.nr : (use_pair ? pplan.nr : plan.nr);
+  sc.smem_bytes = use_np ? nplan.bytes : (use_pair ? pplan.bytes : plan.bytes);
+  sc.npairs = 0;
+  if (use_npp) {
+    if (npp_t1 > 0) {
+      sc.npairs = sm_count() / 2;  // npp_units main pairs + the helpers
+    } else {
+      // equal ranges: at least ~4 tiles per pair, at most one pair per two SMs
+      const long long total = 2ll * sc.nrb * sc.ntiles;
+      sc.npairs = static_cast<int>(std::min<long long>(sm_count() / 2, std::max<long long>(1, total / 4)));
+    }
+    sc.grid = static_cast<unsigned>(2 * sc.npairs);
+  } else if (use_np) {
+    sc.grid = static_cast<unsigned>(2 * (tail.n_full + (np_units - tail.n_full) * tail.ns_tail));
+  } else {
+    sc.grid = static_cast<unsigned>((use_pair ? 2 : 1) * 2 * sc.nrb * sc.npass * sc.nsplit);
+  }
+  sc.zero_all = nsplit > 1 || (sc.kind == BWD_NARROW && tail.ns_tail > 1 && np_npass > 1);
+  sc.zero_tail = !sc.zero_all && sc.kind == BWD_NARROW && tail.ns_tail > 1;
+  return sc;
+}
+
+}  // namespace
+}  // namespace nans
+
+using namespace nans;
+
+extern "C" size_t nans_clip_loss_bwd_workspace_bytes(int64_t grad_row_count, int64_t N, int64_t D) {
+  (void)N;
+  if (grad_row_count <= 0 || D <= 0) return 512;
+  return 2 * align_up(static_cast<size_t>(grad_row_count) * D * 4, 256) + 512;
+}
+
+extern "C" int nans_clip_loss_bwd_plan(int64_t grad_row_count, int64_t N, int64_t D, int64_t* out, int n_out) {
+  if (grad_row_count <= 0 || N <= 0 || D <= 0 || D % 8 != 0 || out == nullptr || n_out < NANS_BWD_PLAN_FIELDS) {
+    set_error("loss_bwd_plan: bad arguments");
+    return NANS_ERR_ARG;
+  }
+  const BwdSchedule sc = plan_bwd_schedule(grad_row_count, N, D);
+  const int64_t v[NANS_BWD_PLAN_FIELDS] = {
+      sc.kind, sc.tile_cols, sc.npass, sc.a_resident ? 1 : 0, sc.nrb, sc.ntiles, sc.nr,
+      static_cast<int64_t>(sc.smem_bytes), static_cast<int64_t>(sc.grid), sc.nsplit, sc.tail.n_full,
+      sc.tail.ns_tail, sc.npp_t1, sc.npp_units, sc.npairs, sc.zero_all ? 2 : (sc.zero_tail ? 1 : 0)};
+  for (int i = 0; i < NANS_BWD_PLAN_FIELDS; ++i) out[i] = v[i];
+  return NANS_OK;
+}
+
+extern "C" int nans_clip_loss_bwd(const void* I_loc, const void* T_loc, int64_t ld_loc,
+                                  const void* T_all, const void* I_all, int64_t ld_all,
+                                  int feat_dtype, int64_t n_loc, int64_t N, int64_t D,
+                                  int64_t label_begin, const float* s_dev, const float* lse_img_all,
+                                  const float* lse_txt_all, const float* grad_out_dev,
+                                  float grad_mult, int64_t grad_row_begin, int64_t grad_row_count,
+                                  void* dI_loc, void* dT_loc, int out_dtype, void* ws,
+                                  size_t ws_bytes, void* stream) {
+  int rc = check_device();
+  if (rc != NANS_OK) return rc;
+  NANS_REQUIRE(feat_dtype == NANS_F16 || feat_dtype == NANS_BF16,
+               "loss_bwd: feat_dtype must be NANS_F16 or NANS_BF16");
+  NANS_REQUIRE(out_dtype == NANS_F32 || out_dtype == NANS_F16 || out_dtype == NANS_BF16,
+               "loss_bwd: bad out_dtype");
+  NANS_REQUIRE(n_loc > 0 && N > 0 && D > 0 && D % 8 == 0, "loss_bwd: bad sizes (D must be a multiple of 8)");
+  NANS_REQUIRE(n_loc < (1ll << 30) && N < (1ll << 30) && D <= 8192, "loss_bwd: size too large");
+  NANS_REQUIRE(grad_row_begin >= 0 && grad_row_count >= 0 && grad_row_begin + grad_row_count <= n_loc,
+               "loss_bwd: gradient rows [%lld, +%lld) outside the local block of %lld rows",
+               (long long)grad_row_begin, (long long)grad_row_count, (long long)n_loc);
+  NANS_REQUIRE(label_begin >= 0 && label_begin + n_loc <= N, "loss_bwd: labels outside [0, N)");
+  if (grad_row_count == 0) return NANS_OK;
+  NANS_REQUIRE(I_loc && T_loc && T_all && I_all && s_dev && lse_img_all && lse_txt_all &&
+                   grad_out_dev && dI_loc && dT_loc,
+               "loss_bwd: null pointer");
+  NANS_REQUIRE(ld_loc >= D && ld_all >= D, "loss_bwd: leading dimension smaller than D");
+  NANS_REQUIRE((reinterpret_cast<uintptr_t>(lse_img_all) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(lse_txt_all) & 15) == 0,
+               "loss_bwd: lse arrays must be 16-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+
+  const BwdSchedule sc = plan_bwd_schedule(grad_row_count, N, D);
+  const int kchunks = sc.kchunks;
   const size_t out_bytes = static_cast<size_t>(grad_row_count) * D * 4;
   // workspace: [0,256) lse min/max slots, then (16-bit outputs only) the two fp32 gradient buffers
   if (ws == nullptr || ws_bytes < 512) {
@@ -270,17 +338,14 @@ extern "C" int nans_clip_loss_bwd(const void* I_loc, const void* T_loc, int64_t 
     out32[0] = reinterpret_cast<float*>(static_cast<uint8_t*>(ws) + 256);
     out32[1] = reinterpret_cast<float*>(static_cast<uint8_t*>(ws) + 256 + align_up(out_bytes, 256));
   }
-  if (nsplit > 1) {
+  if (sc.zero_all) {
     NANS_CUDA_OK(cudaMemsetAsync(out32[0], 0, out_bytes, st));
     NANS_CUDA_OK(cudaMemsetAsync(out32[1], 0, out_bytes, st));
-  } else if (use_np && !use_npp && tail.ns_tail > 1 && np_npass > 1) {
-    NANS_CUDA_OK(cudaMemsetAsync(out32[0], 0, out_bytes, st));
-    NANS_CUDA_OK(cudaMemsetAsync(out32[1], 0, out_bytes, st));
-  } else if (use_np && !use_npp && tail.ns_tail > 1) {
-    // only the rows of the column-split tail units are accumulated
-    const int64_t nrb_np = np_units / 2;
+  } else if (sc.zero_tail) {
+    // only the rows of the column-split tail units are accumulated (single pass: unit = (strip, row block))
+    const int64_t nrb_np = sc.nrb;
     for (int strip = 0; strip < 2; ++strip) {
-      const int64_t u0 = std::max<int64_t>(tail.n_full, strip * nrb_np), u1 = (strip + 1) * nrb_np;
+      const int64_t u0 = std::max<int64_t>(sc.tail.n_full, strip * nrb_np), u1 = (strip + 1) * nrb_np;
       if (u0 >= u1) continue;
       const int64_t r0 = (u0 - strip * nrb_np) * 2 * NP_ROWS;
       const int64_t r1 = std::min<int64_t>(grad_row_count, (u1 - strip * nrb_np) * 2 * NP_ROWS);
@@ -305,11 +370,11 @@ extern "C" int nans_clip_loss_bwd(const void* I_loc, const void* T_loc, int64_t 
   p.ncols = static_cast<int>(N);
   p.D = static_cast<int>(D);
   p.kchunks = kchunks;
-  p.nrb = static_cast<int>(ceil_div(grad_row_count, use_np ? 2 * NP_ROWS : (use_pair ? 2 * BM : BM)));
-  p.npass = npass;
-  p.nsplit = nsplit;
-  p.ntiles = static_cast<int>(ceil_div(N, use_np ? np_tk : KT));
-  p.nr = use_np ? nplan.nr : (use_pair ? pplan.nr : plan.nr);
+  p.nrb = sc.nrb;
+  p.npass = sc.npass;
+  p.nsplit = sc.nsplit;
+  p.ntiles = sc.ntiles;
+  p.nr = sc.nr;
   p.idesc1_fmt = static_cast<uint32_t>(idesc_fmt(feat_dtype));
   // tcgen05.mma kind::f16 wants A and B in the same 16-bit format (a mixed f16 x bf16 descriptor
   // faults as an illegal instruction on sm_100a), so G is written in the features' format.
@@ -328,58 +393,46 @@ extern "C" int nans_clip_loss_bwd(const void* I_loc, const void* T_loc, int64_t 
   p.lse_col[1] = lse_img_all;
   p.out[0] = out32[0];
   p.out[1] = out32[1];
-  p.accumulate = nsplit > 1 ? 1 : 0;
+  p.accumulate = sc.nsplit > 1 ? 1 : 0;
   p.lse_minmax = minmax;
   {
     const char* e = getenv("NANS_BWD_DEBUG");
     p.debug = e ? atoi(e) : 0;
   }
 
-  if (use_npp) {
-    p.total_tiles = 2ll * p.nrb * p.ntiles;
-    p.npp_t1 = npp_t1;
-    p.npp_units = npp_units;
-    if (npp_t1 > 0) {
-      p.npairs = sm_count() / 2;  // npp_units main pairs + the helpers
-    } else {
-      // at least ~4 tiles per pair, at most one pair per two SMs
-      const long long want = std::max<long long>(1, p.total_tiles / 4);
-      p.npairs = static_cast<int>(std::min<long long>(sm_count() / 2, want));
-    }
+  const size_t smem = sc.smem_bytes;
+  p.n_full = sc.tail.n_full;
+  p.ns_tail = sc.tail.ns_tail;
+  p.total_tiles = 2ll * sc.nrb * sc.ntiles;
+  p.npp_t1 = sc.npp_t1;
+  p.npp_units = sc.npp_units;
+  p.npairs = sc.npairs;
+  if (sc.kind == BWD_NARROW_PERSISTENT) {
     NANS_CUDA_OK(cudaFuncSetAttribute(clip_bwd_npp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      static_cast<int>(nplan.bytes)));
-    clip_bwd_npp_kernel<<<static_cast<unsigned>(2 * p.npairs), NUM_THREADS, nplan.bytes, st>>>(tmAn0, tmB0, tmAn1,
-                                                                                            tmB1, p);
-  } else if (use_np) {
-    p.n_full = tail.n_full;
-    p.ns_tail = tail.ns_tail;
-    const unsigned grid = static_cast<unsigned>(2 * (tail.n_full + (np_units - tail.n_full) * tail.ns_tail));
-    p.npass = np_npass;
-    if (np_tk == NP_KT && !np_ares) {
+                                      static_cast<int>(smem)));
+    clip_bwd_npp_kernel<<<sc.grid, NUM_THREADS, smem, st>>>(tmAn0, tmB0, tmAn1, tmB1, p);
+  } else if (sc.kind == BWD_NARROW) {
+    if (sc.tile_cols == NP_KT && !sc.a_resident) {
       NANS_CUDA_OK(cudaFuncSetAttribute(clip_bwd_np_kernel<NP_KT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        static_cast<int>(nplan.bytes)));
-      clip_bwd_np_kernel<NP_KT, false><<<grid, NUM_THREADS, nplan.bytes, st>>>(tmAn0, tmB0, tmB0, tmAn1, tmB1, tmB1, p);
-    } else if (np_tk == NP_KT) {
+                                        static_cast<int>(smem)));
+      clip_bwd_np_kernel<NP_KT, false><<<sc.grid, NUM_THREADS, smem, st>>>(tmAn0, tmB0, tmB0, tmAn1, tmB1, tmB1, p);
+    } else if (sc.tile_cols == NP_KT) {
       NANS_CUDA_OK(cudaFuncSetAttribute(clip_bwd_np_kernel<NP_KT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        static_cast<int>(nplan.bytes)));
-      clip_bwd_np_kernel<NP_KT, true><<<grid, NUM_THREADS, nplan.bytes, st>>>(tmAn0, tmB0, tmB0, tmAn1, tmB1, tmB1, p);
+                                        static_cast<int>(smem)));
+      clip_bwd_np_kernel<NP_KT, true><<<sc.grid, NUM_THREADS, smem, st>>>(tmAn0, tmB0, tmB0, tmAn1, tmB1, tmB1, p);
     } else {
       NANS_CUDA_OK(cudaFuncSetAttribute(clip_bwd_np_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        static_cast<int>(nplan.bytes)));
-      clip_bwd_np_kernel<128, true><<<grid, NUM_THREADS, nplan.bytes, st>>>(tmAn0, tmBk0, tmB0, tmAn1, tmBk1, tmB1, p);
+                                        static_cast<int>(smem)));
+      clip_bwd_np_kernel<128, true><<<sc.grid, NUM_THREADS, smem, st>>>(tmAn0, tmBk0, tmB0, tmAn1, tmBk1, tmB1, p);
     }
-  } else if (use_pair) {
-    auto kern = pplan.a_resident ? clip_bwd_pair_kernel<true> : clip_bwd_pair_kernel<false>;
-    NANS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      static_cast<int>(pplan.bytes)));
-    const unsigned grid = static_cast<unsigned>(2 * 2 * p.nrb * p.npass * p.nsplit);  // 2 CTAs per unit
-    kern<<<grid, NUM_THREADS, pplan.bytes, st>>>(tmA0, tmBk0, tmB0, tmA1, tmBk1, tmB1, p);
+  } else if (sc.kind == BWD_WIDE_PAIR) {
+    auto kern = sc.a_resident ? clip_bwd_pair_kernel<true> : clip_bwd_pair_kernel<false>;
+    NANS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    kern<<<sc.grid, NUM_THREADS, smem, st>>>(tmA0, tmBk0, tmB0, tmA1, tmBk1, tmB1, p);
   } else {
-    auto kern = plan.a_resident ? clip_bwd_kernel<true> : clip_bwd_kernel<false>;
-    NANS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      static_cast<int>(plan.bytes)));
-    const unsigned grid = static_cast<unsigned>(2 * p.nrb * p.npass * p.nsplit);
-    kern<<<grid, NUM_THREADS, plan.bytes, st>>>(tmA0, tmB0, tmA1, tmB1, p);
+    auto kern = sc.a_resident ? clip_bwd_kernel<true> : clip_bwd_kernel<false>;
+    NANS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    kern<<<sc.grid, NUM_THREADS, smem, st>>>(tmA0, tmB0, tmA1, tmB1, p);
   }
   NANS_CUDA_OK(cudaGetLastError());
 
