@@ -1,0 +1,38 @@
+"""bench.py's reference arm runs without a GPU: check the JSON-line contract it prints (one line on
+stdout, the keys the driver reads) and that ranks other than 0 stay silent."""
+import json
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def _run(extra_env, *args):
+    env = dict(os.environ)
+    env.update(extra_env)
+    r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                        *args], capture_output=True, text=True, env=env, timeout=600, cwd=str(ROOT))
+    assert r.returncode == 0, r.stderr[-2000:]
+    return r.stdout
+
+
+def test_reference_arm_prints_one_contract_line():
+    out = _run({"OMP_NUM_THREADS": "1"})          # torchrun's default: the arm must still use the host cores
+    lines = [l for l in out.splitlines() if l.strip()]
+    assert len(lines) == 1, out
+    d = json.loads(lines[0])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+                "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in d, key
+    assert d["impl"] == "reference" and d["metric"] == "contrastive_fwd_bwd_pairs_per_s" and d["unit"] == "pairs/s"
+    assert d["vs_baseline"] is None and d["higher_is_better"] is True and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0))
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    assert "workload" in d["config"]
+
+
+def test_reference_arm_other_ranks_are_silent():
+    assert _run({"RANK": "3", "WORLD_SIZE": "8", "LOCAL_RANK": "3"}, "--gpus", "8").strip() == ""
