@@ -202,6 +202,28 @@ int nans_clip_loss_bwd(const void* I_loc, const void* T_loc, int64_t ld_loc, con
                        int64_t grad_row_count, void* dI_loc, void* dT_loc, int out_dtype,
                        void* ws, size_t ws_bytes, void* stream);
 
+/* nans_clip_loss_bwd with the lse min / max supplied by nans_clip_loss_exchange_finish (saves the
+ * backward's own min/max launch); lse_minmax = NULL behaves exactly like nans_clip_loss_bwd. */
+int nans_clip_loss_bwd_minmax(const void* I_loc, const void* T_loc, int64_t ld_loc, const void* T_all,
+                              const void* I_all, int64_t ld_all, int feat_dtype, int64_t n_loc,
+                              int64_t N, int64_t D, int64_t label_begin, const float* s_dev,
+                              const float* lse_img_all, const float* lse_txt_all, const int* lse_minmax,
+                              const float* grad_out_dev, float grad_mult, int64_t grad_row_begin,
+                              int64_t grad_row_count, void* dI_loc, void* dT_loc, int out_dtype,
+                              void* ws, size_t ws_bytes, void* stream);
+
+/* After the cross-rank exchange of the forward (one all-gather of, per rank, [lse_img (pad floats) |
+ * lse_txt (pad) | scalars[8]] = the `packed` layout nans_clip_loss_fwd_finalize's outputs have when
+ * lse_txt_loc = lse_img_loc + pad and scalars = lse_img_loc + 2 pad): ONE launch that
+ *   - writes the rank-major table lse_all[2][ld] (row 0 image->text, row 1 text->image; ld >= world * n_loc)
+ *     the backward reads,
+ *   - reduces the partial scalars over the ranks: out[0] = loss (train.py:112-115), out[1] = d loss / d s,
+ *     out[2], out[3] = the two accuracies (train.py:117-121),
+ *   - writes lse_minmax[2] for nans_clip_loss_bwd_minmax.
+ * Replaces the host-side permute / sum / scale ops and the backward's min/max launch. */
+int nans_clip_loss_exchange_finish(const float* gathered, int64_t world, int64_t n_loc, int64_t pad,
+                                   float* lse_all, int64_t ld, float* out, int* lse_minmax, void* stream);
+
 /* ---- (3b) label-smoothed variant ---------------------------------------------------------- */
 /*
  * Replaces the fork's train_lora.py:95-110 (`contrastive_loss`: F.cross_entropy(logits, arange,

@@ -60,6 +60,12 @@ _SIGNATURES = {
                                    c_int64, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p,
                                    c_void_p, c_float, c_int64, c_int64, c_void_p, c_void_p, c_int,
                                    c_void_p, c_size_t, c_void_p]),
+    "nans_clip_loss_bwd_minmax": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int,
+                                          c_int64, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p,
+                                          c_void_p, c_void_p, c_float, c_int64, c_int64, c_void_p, c_void_p, c_int,
+                                          c_void_p, c_size_t, c_void_p]),
+    "nans_clip_loss_exchange_finish": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_void_p,
+                                               c_void_p, c_void_p]),
     "nans_label_smooth_stats": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p]),
     "nans_label_smooth_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64,
                                       c_void_p, c_void_p, c_void_p, c_float, c_float, c_void_p]),

@@ -289,6 +289,19 @@ extern "C" int nans_clip_loss_bwd(const void* I_loc, const void* T_loc, int64_t 
                                   float grad_mult, int64_t grad_row_begin, int64_t grad_row_count,
                                   void* dI_loc, void* dT_loc, int out_dtype, void* ws,
                                   size_t ws_bytes, void* stream) {
+  return nans_clip_loss_bwd_minmax(I_loc, T_loc, ld_loc, T_all, I_all, ld_all, feat_dtype, n_loc, N, D, label_begin,
+                                   s_dev, lse_img_all, lse_txt_all, nullptr, grad_out_dev, grad_mult, grad_row_begin,
+                                   grad_row_count, dI_loc, dT_loc, out_dtype, ws, ws_bytes, stream);
+}
+
+extern "C" int nans_clip_loss_bwd_minmax(const void* I_loc, const void* T_loc, int64_t ld_loc,
+                                         const void* T_all, const void* I_all, int64_t ld_all,
+                                         int feat_dtype, int64_t n_loc, int64_t N, int64_t D,
+                                         int64_t label_begin, const float* s_dev, const float* lse_img_all,
+                                         const float* lse_txt_all, const int* lse_minmax,
+                                         const float* grad_out_dev, float grad_mult, int64_t grad_row_begin,
+                                         int64_t grad_row_count, void* dI_loc, void* dT_loc, int out_dtype,
+                                         void* ws, size_t ws_bytes, void* stream) {
   int rc = check_device();
   if (rc != NANS_OK) return rc;
   NANS_REQUIRE(feat_dtype == NANS_F16 || feat_dtype == NANS_BF16,
@@ -320,9 +333,13 @@ extern "C" int nans_clip_loss_bwd(const void* I_loc, const void* T_loc, int64_t 
     return NANS_ERR_WORKSPACE;
   }
   NANS_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 15) == 0, "loss_bwd: workspace must be 16-byte aligned");
-  int* minmax = static_cast<int*>(ws);
-  lse_minmax_kernel<<<1, 1024, 0, st>>>(lse_img_all, lse_txt_all, static_cast<int>(N), minmax);
-  NANS_CUDA_OK(cudaGetLastError());
+  const int* minmax = lse_minmax;
+  if (minmax == nullptr) {  // not supplied by nans_clip_loss_exchange_finish: one small launch
+    int* mm = static_cast<int*>(ws);
+    lse_minmax_kernel<<<1, 1024, 0, st>>>(lse_img_all, lse_txt_all, static_cast<int>(N), mm);
+    NANS_CUDA_OK(cudaGetLastError());
+    minmax = mm;
+  }
   float* out32[2];
   if (out_dtype == NANS_F32) {
     NANS_REQUIRE((reinterpret_cast<uintptr_t>(dI_loc) & 15) == 0 && (reinterpret_cast<uintptr_t>(dT_loc) & 15) == 0,

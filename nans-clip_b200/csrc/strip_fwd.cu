@@ -305,6 +305,69 @@ __global__ void __launch_bounds__(256) clip_fwd_finalize_kernel(const FinParams 
   }
 }
 
+// ---- after the cross-rank exchange ----------------------------------------------------------------
+// One launch instead of a permute copy, a sum, three scalar ops and the backward's lse min/max:
+// `gathered` holds, per rank, [lse_img (pad) | lse_txt (pad) | 8 partial scalars].  Writes the
+// rank-major [2][N] lse table the backward reads, the reduced results
+//   out[0] loss = (S0 + S1) / 2N   out[1] dloss/ds = (S2 + S3) / 2N   out[2], out[3] accuracies = S4/N, S5/N
+// and the order-preserving int encodings of min / max over all lse values (kernel (3)'s one-exp form).
+// A single block: 2N floats are at most a few hundred KB, the loads are independent.
+__global__ void __launch_bounds__(1024) clip_exchange_finish_kernel(const float* __restrict__ gathered, int W,
+                                                                    int n_loc, int pad, float* __restrict__ lse_all,
+                                                                    long long ld, float* __restrict__ out,
+                                                                    int* __restrict__ minmax) {
+  __shared__ float slo[32], shi[32];
+  const long long L = 2ll * pad + 8;
+  const int total = W * n_loc;
+  float lo = INFINITY, hi = -INFINITY;
+#pragma unroll
+  for (int strip = 0; strip < 2; ++strip) {
+#pragma unroll 8
+    for (int idx = threadIdx.x; idx < total; idx += 1024) {
+      const int rank = idx / n_loc;
+      const int row = idx - rank * n_loc;
+      const float v = __ldg(gathered + rank * L + static_cast<long long>(strip) * pad + row);
+      lse_all[strip * ld + idx] = v;
+      lo = fminf(lo, v);
+      hi = fmaxf(hi, v);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    slo[threadIdx.x >> 5] = lo;
+    shi[threadIdx.x >> 5] = hi;
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    lo = slo[threadIdx.x];
+    hi = shi[threadIdx.x];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+      hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    // lanes 0..5: sum of partial scalar k over the ranks, in rank order (deterministic)
+    float sum = 0.f;
+    if (threadIdx.x < 6)
+      for (int r = 0; r < W; ++r) sum += __ldg(gathered + r * L + 2ll * pad + threadIdx.x);
+    const float s01 = sum + __shfl_down_sync(0xffffffffu, sum, 1);  // lanes 0, 2: S0+S1, S2+S3
+    const float n = static_cast<float>(total);
+    if (threadIdx.x == 0) {
+      out[0] = s01 / (2.0f * n);
+      const int il = __float_as_int(lo), ih = __float_as_int(hi);
+      minmax[0] = il >= 0 ? il : il ^ 0x7fffffff;
+      minmax[1] = ih >= 0 ? ih : ih ^ 0x7fffffff;
+    }
+    if (threadIdx.x == 2) out[1] = s01 / (2.0f * n);
+    if (threadIdx.x == 4) out[2] = sum / n;
+    if (threadIdx.x == 5) out[3] = sum / n;
+  }
+}
+
 // ---- workspace layout ------------------------------------------------------------------------
 // [diag 2*n_loc][block partials][counter][slot 0][slot 1]...   slot = {m, l, w, bv, bi} x 2*n_loc
 // Slot addresses do not depend on how many slots follow, so phases need not know the total.
@@ -557,4 +620,19 @@ extern "C" int nans_clip_loss_fwd(const void* I_loc, const void* T_loc, int64_t 
   const int64_t slots = nans_clip_loss_fwd_phase_slots(n_loc, N, D);
   return nans_clip_loss_fwd_finalize(n_loc, slots, label_begin, s_dev, flags, ws, ws_bytes,
                                      lse_img_loc, lse_txt_loc, scalars, stream);
+}
+
+extern "C" int nans_clip_loss_exchange_finish(const float* gathered, int64_t world, int64_t n_loc, int64_t pad,
+                                              float* lse_all, int64_t ld, float* out, int* lse_minmax,
+                                              void* stream) {
+  int rc = check_device();
+  if (rc != NANS_OK) return rc;
+  NANS_REQUIRE(world > 0 && n_loc > 0 && pad >= n_loc && ld >= world * n_loc && world * n_loc < (1ll << 30),
+               "loss_exchange_finish: bad sizes");
+  NANS_REQUIRE(gathered && lse_all && out && lse_minmax, "loss_exchange_finish: null pointer");
+  clip_exchange_finish_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(
+      gathered, static_cast<int>(world), static_cast<int>(n_loc), static_cast<int>(pad), lse_all,
+      static_cast<long long>(ld), out, lse_minmax);
+  NANS_CUDA_OK(cudaGetLastError());
+  return NANS_OK;
 }

@@ -181,13 +181,35 @@ def fwd_finalize(n_loc: int, total_slots: int, label_begin: int, s_dev: torch.Te
     return lse, scalars, packed
 
 
+def exchange_finish(gathered: torch.Tensor, n_loc: int):
+    """`gathered` [W, 2 * pad + 8]: every rank's `packed` buffer of fwd_finalize, all-gathered.
+    Returns (lse_all [2, N] rank-major, out [4] = loss, d loss / d s, acc i2t, acc t2i,
+    lse_minmax int32 [2] for bwd) from one launch."""
+    _require_cuda(gathered)
+    W, L = gathered.shape
+    pad = (L - 8) // 2
+    N = W * n_loc
+    ld = (N + 3) // 4 * 4
+    dev = gathered.device
+    assert gathered.dtype == torch.float32 and gathered.is_contiguous() and pad >= n_loc
+    lse_all = torch.empty((2, ld), dtype=torch.float32, device=dev)[:, :N]
+    out = torch.empty((4,), dtype=torch.float32, device=dev)
+    mm = torch.empty((2,), dtype=torch.int32, device=dev)
+    with _on_device(dev) as stream:
+        check(_lib.load().nans_clip_loss_exchange_finish(gathered.data_ptr(), W, n_loc, pad, lse_all.data_ptr(), ld,
+                                                         out.data_ptr(), mm.data_ptr(), stream))
+    _count(1)
+    return lse_all, out, mm
+
+
 # --------------------------------------------------------------------------------------------
 # (3) fused backward
 # --------------------------------------------------------------------------------------------
 def bwd(I_loc, T_loc, T_all, I_all, *, label_begin: int, s_dev: torch.Tensor,
         lse_all: torch.Tensor, grad_out: torch.Tensor, grad_mult: float, row_begin: int,
-        row_count: int, out_dtype: torch.dtype):
-    """lse_all: [2, N] fp32 (image->text, text->image) in global row order.  Returns (dI, dT)."""
+        row_count: int, out_dtype: torch.dtype, lse_minmax: torch.Tensor | None = None):
+    """lse_all: [2, N] fp32 (image->text, text->image) in global row order.  Returns (dI, dT).
+    `lse_minmax`: the int32 [2] of exchange_finish (else the backward computes it itself)."""
     _require_cuda(I_loc, T_loc, T_all, I_all, s_dev, lse_all, grad_out)
     n_loc, D = I_loc.shape
     N = T_all.shape[0]
@@ -205,13 +227,13 @@ def bwd(I_loc, T_loc, T_all, I_all, *, label_begin: int, s_dev: torch.Tensor,
         lse_all = buf
     assert grad_out.dtype == torch.float32 and grad_out.numel() == 1
     with _on_device(dev) as stream:
-        check(lib.nans_clip_loss_bwd(
+        check(lib.nans_clip_loss_bwd_minmax(
             I_loc.data_ptr(), T_loc.data_ptr(), I_loc.stride(0), T_all.data_ptr(),
             I_all.data_ptr(), T_all.stride(0), dtype_code(I_loc.dtype), n_loc, N, D, label_begin,
-            s_dev.data_ptr(), lse_all[0].data_ptr(), lse_all[1].data_ptr(), grad_out.data_ptr(),
+            s_dev.data_ptr(), lse_all[0].data_ptr(), lse_all[1].data_ptr(), _ptr(lse_minmax), grad_out.data_ptr(),
             float(grad_mult), row_begin, row_count, dI.data_ptr(), dT.data_ptr(),
             dtype_code(out_dtype), ws.data_ptr(), ws.numel(), stream))
-    _count(2 if out_dtype == torch.float32 else 4)  # lse min/max + backward (+ 2 casts)
+    _count((1 if lse_minmax is not None else 2) + (0 if out_dtype == torch.float32 else 2))  # [lse min/max +] backward (+ 2 casts)
     return dI, dT
 
 

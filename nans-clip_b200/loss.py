@@ -132,22 +132,22 @@ class _ClipLossFn(torch.autograd.Function):
         lse, scalars, packed = K.fwd_finalize(n_loc, slot, label_begin, s_dev, cfg.report_acc, ws)
 
         # ---- one small exchange: per-row lse (for the backward) and the 8 partial scalars -------
+        lse_minmax = None
         if W > 1:
             L = packed.numel()
-            pad = (L - 8) // 2
             gathered = torch.empty((W, L), dtype=torch.float32, device=dev)
             dist.all_gather_into_tensor(gathered.view(-1), packed, group=cfg.group)
-            lse_all = gathered[:, :2 * pad].view(W, 2, pad)[:, :, :n_loc].permute(1, 0, 2).reshape(2, N)
-            scalars = gathered[:, 2 * pad:].sum(dim=0)   # == all_reduce(SUM) of the partial sums
+            # one launch: rank-major lse table, the scalars summed over ranks and scaled
+            # (loss = (sum_i + sum_j) / 2N, train.py:112-115; acc = hits / N), lse min/max for the backward
+            lse_all, res, lse_minmax = K.exchange_finish(gathered, n_loc)
+            loss, dscale, acc_i2t, acc_t2i = res[0], res[1], res[2], res[3]
         else:
             lse_all = lse
-
-        # loss = (sum_i + sum_j) / 2N (train.py:112-115); d loss / d s likewise; acc = hits / N
-        red = scalars * _scalar_coefs(N, dev)
-        loss = red[0] + red[1]
-        dscale = red[2] + red[3]
-        acc_i2t = red[4]
-        acc_t2i = red[5]
+            red = scalars * _scalar_coefs(N, dev)
+            loss = red[0] + red[1]
+            dscale = red[2] + red[3]
+            acc_i2t = red[4]
+            acc_t2i = red[5]
 
         # ---- label smoothing: the plain loss plus O(N D) terms (csrc/smooth.cu) ------------------
         stats = I32 = T32 = None
@@ -162,7 +162,7 @@ class _ClipLossFn(torch.autograd.Function):
             loss = loss + s_dev[0] * corr
             dscale = dscale + corr
 
-        ctx.save_for_backward(I16, T16, I_all, T_all, s_dev, lse_all, dscale, stats, I32, T32)
+        ctx.save_for_backward(I16, T16, I_all, T_all, s_dev, lse_all, dscale, stats, I32, T32, lse_minmax)
         ctx.cfg = cfg
         ctx.meta = (W, label_begin, int(row_begin), chunk_img.shape[0], chunk_img.dtype,
                     chunk_txt.dtype)
@@ -171,7 +171,7 @@ class _ClipLossFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_loss, _g1, _g2):
-        I16, T16, I_all, T_all, s_dev, lse_all, dscale, stats, I32, T32 = ctx.saved_tensors
+        I16, T16, I_all, T_all, s_dev, lse_all, dscale, stats, I32, T32, lse_minmax = ctx.saved_tensors
         W, label_begin, row_begin, rows, dt_i, dt_t = ctx.meta
         cfg = ctx.cfg
         need_feat = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
@@ -182,7 +182,7 @@ class _ClipLossFn(torch.autograd.Function):
             mult = float(W) if cfg.gather_with_grad else 1.0
             dI, dT = K.bwd(I16, T16, T_all, I_all, label_begin=label_begin, s_dev=s_dev,
                            lse_all=lse_all, grad_out=g, grad_mult=mult,
-                           row_begin=row_begin, row_count=rows, out_dtype=out_dt)
+                           row_begin=row_begin, row_count=rows, out_dtype=out_dt, lse_minmax=lse_minmax)
             if stats is not None:
                 N = T_all.shape[0]
                 K.smooth_bwd(dI, dT, I32[row_begin:row_begin + rows], T32[row_begin:row_begin + rows], stats,

@@ -14,7 +14,7 @@ STATE = {}
 
 def install(K):
     for name in ("l2norm_cast", "fwd_phase_slots", "fwd_workspace", "fwd_phase", "fwd_finalize", "bwd",
-                 "smooth_stats", "smooth_bwd", "clone_workspace", "topk_ip", "topk_merge"):
+                 "smooth_stats", "smooth_bwd", "clone_workspace", "exchange_finish", "topk_ip", "topk_merge"):
         setattr(K, name, globals()[name])
 
 
@@ -123,8 +123,18 @@ def fwd_finalize(n_loc, total_slots, label_begin, s_dev, with_acc, ws, want_row_
     return (lse, sc, packed, rows) if want_row_stats else (lse, sc, packed)
 
 
+def exchange_finish(gathered, n_loc):
+    W, L = gathered.shape
+    pad = (L - 8) // 2
+    N = W * n_loc
+    lse_all = gathered[:, :2 * pad].view(W, 2, pad)[:, :, :n_loc].permute(1, 0, 2).reshape(2, N).clone()
+    sc = gathered[:, 2 * pad:].sum(0)
+    out = torch.stack([(sc[0] + sc[1]) / (2 * N), (sc[2] + sc[3]) / (2 * N), sc[4] / N, sc[5] / N])
+    return lse_all, out, torch.zeros(2, dtype=torch.int32)
+
+
 def bwd(I_loc, T_loc, T_all, I_all, *, label_begin, s_dev, lse_all, grad_out, grad_mult, row_begin,
-        row_count, out_dtype):
+        row_count, out_dtype, lse_minmax=None):
     s = float(s_dev)
     N = T_all.shape[0]
     rows = slice(row_begin, row_begin + row_count)

@@ -267,6 +267,48 @@ def test_rank_strip_with_skipped_local_tiles(dev, W, rank, split_strips):
     assert abs(float(sc[0]) - want0) <= 1e-3 * abs(want0) + 1e-3
 
 
+@pytest.mark.parametrize("W,n_loc", [(2, 200), (8, 4096), (3, 1001), (1, 37)])
+def test_exchange_finish_kernel(dev, W, n_loc):
+    """The post-exchange launch (rank-major lse table, reduced scalars, lse min/max) against the
+    host ops it replaces, and the backward with the supplied min/max against its own."""
+    from nans_clip_b200 import kernels as K
+    pad = (n_loc + 3) // 4 * 4
+    g = torch.Generator(device=dev).manual_seed(W * 1000 + n_loc)
+    gathered = torch.randn(W, 2 * pad + 8, device=dev, generator=g) * 7 + 3
+    lse_all, out, mm = K.exchange_finish(gathered, n_loc)
+    N = W * n_loc
+    want = gathered[:, :2 * pad].view(W, 2, pad)[:, :, :n_loc].permute(1, 0, 2).reshape(2, N)
+    assert torch.equal(lse_all, want)
+    sc = gathered[:, 2 * pad:].double().sum(0)
+    ref = torch.stack([(sc[0] + sc[1]) / (2 * N), (sc[2] + sc[3]) / (2 * N), sc[4] / N, sc[5] / N])
+    assert torch.allclose(out.double(), ref, rtol=1e-5, atol=1e-6)
+
+    def dec(i):   # order-preserving int encoding of a float
+        i = int(i)
+        return torch.tensor(i if i >= 0 else i ^ 0x7fffffff, dtype=torch.int32).view(torch.float32)
+    assert float(dec(mm[0])) == float(want.min()) and float(dec(mm[1])) == float(want.max())
+
+
+def test_backward_with_supplied_lse_minmax(dev):
+    from nans_clip_b200 import kernels as K
+    from oracle import clip_loss as OL
+    n, d, s = 600, 128, 20.0
+    I, T = synth(n, d, 9, 0.5)
+    glob = OL.global_loss_and_grads(I, T, s)
+    I16, T16 = I.half().to(dev), T.half().to(dev)
+    lse = (torch.stack([glob["lse_img"], glob["lse_txt"]]) / math.log(2.0)).to(dev)
+    pad = (n + 3) // 4 * 4
+    packed = torch.zeros(1, 2 * pad + 8, device=dev)
+    packed[0, :n], packed[0, pad:pad + n] = lse[0], lse[1]
+    lse_all, _, mm = K.exchange_finish(packed, n)
+    kw = dict(label_begin=0, s_dev=torch.tensor([s], device=dev), grad_out=torch.ones(1, device=dev),
+              grad_mult=1.0, row_begin=0, row_count=n, out_dtype=torch.float32)
+    a = K.bwd(I16, T16, T16, I16, lse_all=lse_all, lse_minmax=mm, **kw)
+    b = K.bwd(I16, T16, T16, I16, lse_all=lse_all, **kw)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    assert grad_ok(a[0].cpu(), glob["dI"], n, s)
+
+
 def test_accumulate_path_rows(dev, golden_dir):
     """Gradient only for chunk j's rows (train.py:48-51), against the reference's own output."""
     from nans_clip_b200.loss import clip_contrastive_loss
