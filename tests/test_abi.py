@@ -66,3 +66,23 @@ def test_product_path_refuses_cpu_tensors():
     from nans_clip_b200.retrieval import GalleryShard
     with pytest.raises(Exception):
         GalleryShard(x).search(x, 5)
+
+
+def test_forward_slot_and_workspace_queries_are_consistent():
+    """Host-only planning queries of the forward: 1 <= slots <= min(column tiles, 32) for two-strip and
+    single-strip launches alike, the two single-strip flags agree, workspace grows with slots."""
+    lib = _lib.load()
+    for n_loc in (1, 100, 256, 4096, 32768):
+        for ncols in (1, 255, 256, 4096, 28672, 32768, 1000000):
+            both = lib.nans_clip_loss_fwd_phase_slots(n_loc, ncols, 512)
+            one = lib.nans_clip_loss_fwd_phase_slots_flags(n_loc, ncols, 512, 2)
+            assert one == lib.nans_clip_loss_fwd_phase_slots_flags(n_loc, ncols, 512, 4)
+            assert both == lib.nans_clip_loss_fwd_phase_slots_flags(n_loc, ncols, 512, 0)
+            tiles = -(-ncols // 256)
+            assert 1 <= both <= max(1, min(tiles, 32)) and 1 <= one <= max(1, min(tiles, 32))
+            w1 = lib.nans_clip_loss_fwd_workspace_bytes(n_loc, both)
+            w2 = lib.nans_clip_loss_fwd_workspace_bytes(n_loc, both + one)
+            assert w2 > w1 >= 2 * n_loc * 4 * 5 * both
+    assert lib.nans_clip_loss_fwd_phase_slots(0, 10, 512) == 0
+    assert lib.nans_clip_loss_bwd_workspace_bytes(4096, 32768, 512) >= 2 * 4096 * 512 * 4
+    assert lib.nans_topk_ip_workspace_bytes(30000, 1000000, 512, 16) > 0
