@@ -246,6 +246,20 @@ int nans_label_smooth_bwd(float* dI, float* dT, const float* I_rows, const float
                           int64_t rows, int64_t D, const float* stats, const float* s_dev,
                           const float* grad_out_dev, float coef, float inv_n, void* stream);
 
+/* ---- feature files (host only; no GPU) ----------------------------------------------------- */
+/*
+ * Parse the reference's JSONL feature files ({"image_id": int, "feature": [floats]} per line,
+ * cn_clip/eval/extract_features.py:179-181, read back by make_topk_predictions.py:57-65 with json.loads)
+ * into ids[rows] and feats[rows, D] float32, bit-identical to json.loads + np.float32 (correctly rounded
+ * std::from_chars to double, then the float cast), lines parsed in parallel.
+ *   nans_jsonl_scan : rows = non-blank lines, D = length of the first line's feature list
+ *   nans_jsonl_parse: fills the arrays; fails on a malformed line or a different feature length
+ *                     (callers fall back to a general JSON parser).  n_threads <= 0: all cores.
+ */
+int nans_jsonl_scan(const char* buf, int64_t len, const char* id_key, int64_t* rows, int64_t* D);
+int nans_jsonl_parse(const char* buf, int64_t len, const char* id_key, int64_t rows, int64_t D,
+                     int64_t* ids, float* feats, int n_threads);
+
 /* ---- (4) top-k inner-product retrieval ---------------------------------------------------- */
 /*
  * Replaces cn_clip/eval/make_topk_predictions.py:71-85 (and _tr.py): for each query the k gallery

@@ -206,9 +206,8 @@ class FeatureWriter:
         self.close()
 
 
-def load_jsonl_features(path: str, id_key: str):
-    """{"<id_key>": int, "feature": [floats]} per line -> (ids list, float32 [n, D] array);
-    the parsing of make_topk_predictions.py:57-65."""
+def _load_jsonl_python(path: str, id_key: str):
+    """The reference's own parse (make_topk_predictions.py:57-65): json.loads per line."""
     ids, feats = [], []
     with open(path, "r") as fin:
         for line in fin:
@@ -222,6 +221,38 @@ def load_jsonl_features(path: str, id_key: str):
     if arr.ndim != 2:
         arr = arr.reshape(len(ids), -1)
     return ids, arr
+
+
+def _load_jsonl_native(path: str, id_key: str, n_threads: int = 0):
+    """The same parse in C++ (csrc/jsonl.cu: correctly rounded std::from_chars, lines in parallel):
+    bit-identical arrays, ~10x faster per core.  Raises on anything but {"<id_key>": int, "feature": [...]}."""
+    import ctypes
+    from .. import _lib
+    lib = _lib.load()
+    size = os.path.getsize(path)
+    if size == 0:
+        return [], np.zeros((0, 0), dtype=np.float32)
+    buf = np.memmap(path, dtype=np.uint8, mode="r")
+    rows, D = ctypes.c_int64(0), ctypes.c_int64(0)
+    key = id_key.encode("utf-8")
+    _lib.check(lib.nans_jsonl_scan(buf.ctypes.data, size, key, ctypes.byref(rows), ctypes.byref(D)))
+    ids = np.empty((rows.value,), dtype=np.int64)
+    feats = np.empty((rows.value, D.value), dtype=np.float32)
+    _lib.check(lib.nans_jsonl_parse(buf.ctypes.data, size, key, rows.value, D.value, ids.ctypes.data,
+                                    feats.ctypes.data, int(n_threads)))
+    return ids.tolist(), feats
+
+
+def load_jsonl_features(path: str, id_key: str):
+    """{"<id_key>": int, "feature": [floats]} per line -> (ids list, float32 [n, D] array); the
+    parsing of make_topk_predictions.py:57-65.  Native parser first; anything it does not accept
+    (non-integer ids, ragged rows, other JSON) goes through json.loads exactly like the reference."""
+    if os.environ.get("NANS_JSONL_PYTHON", "0") != "1":
+        try:
+            return _load_jsonl_native(path, id_key)
+        except Exception:
+            pass
+    return _load_jsonl_python(path, id_key)
 
 
 def load_features(path: str, id_key: str):

@@ -85,3 +85,62 @@ def test_shard_slices_are_rank_shards(tmp_path):
     assert np.array_equal(np.concatenate(parts), f32)
     assert np.array_equal(np.concatenate([np.asarray(a16[101 * r // W:101 * (r + 1) // W]) for r in range(W)]).view(np.float16),
                           f32.astype(np.float16))
+
+
+# ---- native JSONL parser (csrc/jsonl.cu) ----------------------------------------------------------
+def _write(path, lines):
+    with open(path, "w", newline="") as f:
+        f.write("".join(lines))
+
+
+def test_native_jsonl_parser_is_bit_identical_to_json_loads(tmp_path):
+    rng = np.random.default_rng(3)
+    n, d = 500, 96
+    f32 = (rng.standard_normal((n, d)) * np.exp(rng.uniform(-12, 3, (n, 1)))).astype(np.float32)
+    ids = rng.integers(-5, 2 ** 40, n)
+    p = tmp_path / "f.jsonl"
+    _write(p, [json.dumps({"image_id": int(i), "feature": r.tolist()}) + "\n" for i, r in zip(ids, f32)])
+    a_ids, a = fio._load_jsonl_python(str(p), "image_id")
+    for threads in (1, 3, 0):
+        b_ids, b = fio._load_jsonl_native(str(p), "image_id", threads)
+        assert a_ids == b_ids and b.dtype == np.float32 and np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    c_ids, c = fio.load_jsonl_features(str(p), "image_id")
+    assert c_ids == a_ids and np.array_equal(c, a)
+
+
+def test_native_jsonl_parser_formats(tmp_path):
+    """Exponents, integers, negative zero, doubles that round to float32, key order, blank lines,
+    CRLF, extra keys, missing final newline."""
+    lines = ['{"text_id": 7, "feature": [1, -0.0, 2.5e-05, 1E+2, 0.1, 16777217, 3.4028234663852886e+38]}\n',
+             '\n',
+             '{"feature": [ 0.30000000000000004 ,1e-46, -1.5,4,5 ,6, 1.0000000596046448], "text_id":8 }\r\n',
+             '   \n',
+             '{"extra": "x\\"y", "text_id": 9, "feature": [0,0,0,0,0,0,0], "more": [1, 2]}']
+    p = tmp_path / "g.jsonl"
+    _write(p, lines)
+    a_ids, a = fio._load_jsonl_python(str(p), "text_id")
+    b_ids, b = fio._load_jsonl_native(str(p), "text_id")
+    assert a_ids == b_ids == [7, 8, 9]
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))      # incl. the sign of -0.0
+
+
+def test_native_jsonl_parser_falls_back(tmp_path):
+    """What the native parser refuses still loads through json.loads, like the reference would."""
+    p = tmp_path / "s.jsonl"
+    _write(p, ['{"image_id": "a7", "feature": [1.0, 2.0]}\n', '{"image_id": "b8", "feature": [3.0, 4.0]}\n'])
+    with pytest.raises(Exception):
+        fio._load_jsonl_native(str(p), "image_id")
+    ids, f = fio.load_jsonl_features(str(p), "image_id")
+    assert ids == ["a7", "b8"] and np.array_equal(f, np.array([[1, 2], [3, 4]], dtype=np.float32))
+    r = tmp_path / "r.jsonl"                                        # ragged rows
+    _write(r, ['{"image_id": 1, "feature": [1.0, 2.0]}\n', '{"image_id": 2, "feature": [3.0]}\n'])
+    with pytest.raises(Exception):
+        fio._load_jsonl_native(str(r), "image_id")
+    t = tmp_path / "t.jsonl"                                        # truncated last line
+    _write(t, ['{"image_id": 1, "feature": [1.0, 2.0]}\n', '{"image_id": 2, "feature": [3.0, 4'])
+    with pytest.raises(Exception):
+        fio._load_jsonl_native(str(t), "image_id")
+    e = tmp_path / "e.jsonl"
+    _write(e, [])
+    ids, f = fio.load_jsonl_features(str(e), "image_id")
+    assert ids == [] and f.shape[0] == 0
