@@ -46,8 +46,23 @@ def _stale(target: Path, deps: list[Path]) -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> Path:
-    nvcc = _nvcc()
+    """Serialised across processes (every rank of a torchrun job may get here at once on a fresh
+    checkout): an exclusive flock on lib/.build.lock is held for the whole build, objects and the
+    library are written under temporary names and renamed into place, so a concurrent reader never
+    maps a half-written file."""
+    import fcntl
+
     OBJDIR.mkdir(parents=True, exist_ok=True)
+    with open(LIBDIR / ".build.lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            return _build_locked(force, verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(force: bool, verbose: bool) -> Path:
+    nvcc = _nvcc()
     headers = sorted(CSRC.glob("*.cuh")) + sorted(INCLUDE.glob("*.h")) + [Path(__file__)]
     jobs = []
     objs = []
@@ -60,12 +75,15 @@ def build(force: bool = False, verbose: bool = False) -> Path:
 
     def compile_one(job):
         src, obj = job
-        cmd = [nvcc, *NVCC_FLAGS, "-I", str(INCLUDE), "-c", str(src), "-o", str(obj)]
+        tmp = obj.with_suffix(f".{os.getpid()}.tmp.o")
+        cmd = [nvcc, *NVCC_FLAGS, "-I", str(INCLUDE), "-c", str(src), "-o", str(tmp)]
         r = subprocess.run(cmd, capture_output=True, text=True)
-        log = OBJDIR / (src.stem + ".ptxas.log")
+        log = OBJDIR / (src.stem + ".ptxas.log")   # untracked (registers / spills of the last build)
         log.write_text(r.stdout + r.stderr)
         if r.returncode != 0:
+            tmp.unlink(missing_ok=True)
             raise RuntimeError(f"nvcc failed for {src.name}:\n{r.stdout}\n{r.stderr}")
+        os.replace(tmp, obj)
         if verbose:
             print(r.stderr)
         return obj
@@ -74,10 +92,13 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as ex:
             list(ex.map(compile_one, jobs))
     if jobs or force or _stale(LIB, objs):
-        cmd = [nvcc, "-shared", "-o", str(LIB), *map(str, objs), "-cudart", "static"]
+        tmp = LIB.with_name(f".{LIB.name}.{os.getpid()}.tmp")
+        cmd = [nvcc, "-shared", "-o", str(tmp), *map(str, objs), "-cudart", "static"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
+            tmp.unlink(missing_ok=True)
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+        os.replace(tmp, LIB)
     return LIB
 
 
