@@ -36,14 +36,39 @@ const char* find_key(const char* p, const char* e, const char* key, size_t klen)
   return nullptr;
 }
 
-// 0 ok, else a small positive code; *nvals = numbers found in the feature list
+// A JSON number as json.loads accepts it: -?(0|[1-9][0-9]*)(\.[0-9]+)?([eE][+-]?[0-9]+)?.  from_chars is more
+// liberal (nan, inf, infinity in any case, "012", ".5", "5."): those tokens are refused here so that the
+// caller falls back to json.loads, which either parses them its own way (NaN, Infinity) or raises as the
+// reference would.
+inline bool json_number_start(const char* p, const char* e) {
+  if (p < e && *p == '-') ++p;
+  if (p >= e || *p < '0' || *p > '9') return false;
+  if (*p == '0' && p + 1 < e && p[1] >= '0' && p[1] <= '9') return false;
+  return true;
+}
+inline bool json_number_tail_ok(const char* b, const char* e) {  // [b, e) = the token from_chars consumed
+  for (const char* q = b; q < e; ++q)
+    if (*q == '.' && (q + 1 >= e || q[1] < '0' || q[1] > '9')) return false;
+  return true;
+}
+
+// 0 ok, else a small positive code; *nvals = numbers found in the feature list.  Accepts exactly the
+// shape extract_features.py writes — {"<id_key>": int, "feature": [numbers]} — and refuses everything
+// else (non-integer ids, non-JSON number tokens, trailing text) so that the json.loads fallback decides.
 int parse_line(const char* p, const char* e, const char* id_key, size_t id_klen, int64_t* id, float* feat,
                int64_t cap, int64_t* nvals) {
+  if (p >= e || *p != '{') return 9;
   const char* v = find_key(p, e, id_key, id_klen);
   if (!v) return 1;
   v = skip_ws(v, e);
+  if (!json_number_start(v, e)) return 2;
   auto ri = std::from_chars(v, e, *id);
   if (ri.ec != std::errc()) return 2;
+  {
+    // an integer token must end here: 12.5, 12.0 or 1e3 are floats for json.loads, not the int 12 / 1
+    const char* a = skip_ws(ri.ptr, e);
+    if (a >= e || (*a != ',' && *a != '}')) return 10;
+  }
   const char* f = find_key(p, e, "feature", 7);
   if (!f) return 3;
   f = skip_ws(f, e);
@@ -51,15 +76,22 @@ int parse_line(const char* p, const char* e, const char* id_key, size_t id_klen,
   ++f;
   int64_t n = 0;
   f = skip_ws(f, e);
+  auto closes = [&](const char* q) {  // after ']': either more members (',') or '}' and nothing else
+    q = skip_ws(q + 1, e);
+    if (q >= e) return false;
+    if (*q == ',') return true;
+    return *q == '}' && skip_ws(q + 1, e) == e;
+  };
   if (f < e && *f == ']') {
     *nvals = 0;
-    return 0;
+    return closes(f) ? 0 : 11;
   }
   for (;;) {
     f = skip_ws(f, e);
+    if (!json_number_start(f, e)) return 5;
     double d;
     auto rf = std::from_chars(f, e, d);  // JSON numbers are a subset of what from_chars accepts
-    if (rf.ec != std::errc()) return 5;
+    if (rf.ec != std::errc() || !json_number_tail_ok(f, rf.ptr)) return 5;
     if (n < cap) feat[n] = static_cast<float>(d);
     ++n;
     f = skip_ws(rf.ptr, e);
@@ -71,6 +103,7 @@ int parse_line(const char* p, const char* e, const char* id_key, size_t id_klen,
     if (*f == ']') break;
     return 7;
   }
+  if (!closes(f)) return 11;
   *nvals = n;
   return 0;
 }

@@ -401,8 +401,29 @@ __global__ void __launch_bounds__(FIN_WARPS * 32) topk_finalize_kernel(const Fin
       }
     }
   }
-  // pad when the shard has fewer than k rows
+  // A query can end up with fewer candidates than min(G, k): NaN scores (a zero-norm row normalised to
+  // NaN by extract_features.py) never pass `v > threshold`.  The reference always emits k valid ids
+  // (make_topk_predictions.py:84-85; for an all-NaN row its stable sort leaves gallery order), so the
+  // open ranks are filled with the lowest gallery rows not selected yet, score -inf — never left
+  // unwritten (the outputs are torch.empty) and never -1 while the shard still has rows.
+  __syncwarp();
+  int nsel = 0;
+  for (int d = 0; d < p.kc; ++d) nsel += sel_i[w][d] >= 0 ? 1 : 0;
   const int nvalid = p.G < p.k ? p.G : p.k;
+  if (nsel < nvalid && lane == 0) {
+    int cand = 0;
+    for (int r = nsel; r < nvalid; ++r) {
+      for (;; ++cand) {
+        bool used = false;
+        for (int d = 0; d < p.kc; ++d) used |= sel_i[w][d] == cand;
+        if (!used) break;
+      }
+      p.out_scores[static_cast<long long>(q) * p.k + r] = -INFINITY;
+      p.out_index[static_cast<long long>(q) * p.k + r] = p.index_offset + cand;
+      ++cand;
+    }
+  }
+  // pad when the shard has fewer than k rows
   if (lane >= nvalid && lane < p.k) {
     p.out_scores[static_cast<long long>(q) * p.k + lane] = -INFINITY;
     p.out_index[static_cast<long long>(q) * p.k + lane] = -1;

@@ -11,6 +11,7 @@ at module load, and `Tensor.cuda` -> identity because `get_loss` hard-codes `.cu
 
   loss_w1_*.npz      get_loss (aggregate=False), loss / acc / autograd gradients
   loss_dist_*.npz    get_loss under torch.distributed gloo, W ranks, both gather modes
+  loss_kd_*.npz      get_loss with args.distillation under gloo (W = 2, both gather modes) and local
   loss_accum_*.npz   get_loss on the gradient-accumulation path (train.py:34-51)
   loss_accum4_*.npz  the same with 4 chunks of 256 rows and a re-forwarded chunk that differs from its cache
                      (features stored as their bf16 bit patterns: they are bf16-exact by construction)
@@ -122,6 +123,64 @@ def _dist_worker(rank, W, port, gather_with_grad, n_loc, d, seed, corr, ls, out)
              np_(model.txt.grad), np_(model.logit_scale.grad)))
     dist.barrier()
     dist.destroy_process_group()
+
+
+class StubTeacher(nn.Module):
+    """teacher_model.module.get_feature(images) (train.py:25-32): fixed features of another width."""
+
+    def __init__(self, feat):
+        super().__init__()
+        self.module = self
+        self.feat = feat
+
+    def get_feature(self, images):
+        return self.feat
+
+
+def _kd_worker(rank, W, port, gather_with_grad, n_loc, d, dt, seed, ls, out):
+    install_shims()
+    from cn_clip.training.train import get_loss
+    if W > 1:
+        os.environ["MASTER_ADDR"] = "127.0.0.1"
+        os.environ["MASTER_PORT"] = str(port)
+        dist.init_process_group("gloo", rank=rank, world_size=W)
+    img, txt = synth(W * n_loc, d, seed, 0.5)
+    teacher = torch.randn(W * n_loc, dt, generator=torch.Generator().manual_seed(seed + 7))
+    sl = slice(rank * n_loc, (rank + 1) * n_loc)
+    model = StubModel(img[sl], txt[sl], ls)
+    args = make_args(aggregate=W > 1, gather_with_grad=gather_with_grad, distillation=True, kd_loss_weight=0.5)
+    total, acc = get_loss(model, None, None, nn.CrossEntropyLoss(), nn.CrossEntropyLoss(), args,
+                          teacher_model=StubTeacher(teacher[sl]))
+    total.backward()
+    out.put((rank, np_(total), np_(model.img.grad), np_(model.txt.grad), np_(model.logit_scale.grad)))
+    if W > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def gen_loss_kd():
+    """The knowledge-distillation branch (train.py:25-32, 62-63, 90-100, 106-107, 123-124), including the
+    reference's pairing of a rank-ordered student gather with a local-first teacher gather under
+    gather_with_grad."""
+    port = 29641
+    for name, W, gwg in [("w1", 1, False), ("w2", 2, False), ("w2g", 2, True)]:
+        n_loc, d, dt, seed, ls = 24, 64, 96, 777, 2.6593
+        ctx = mp.get_context("spawn")
+        q = ctx.Queue()
+        procs = [ctx.Process(target=_kd_worker, args=(r, W, port, gwg, n_loc, d, dt, seed, ls, q)) for r in range(W)]
+        port += 1
+        for p in procs:
+            p.start()
+        res = sorted([q.get(timeout=300) for _ in range(W)], key=lambda x: x[0])
+        for p in procs:
+            p.join()
+        img, txt = synth(W * n_loc, d, seed, 0.5)
+        teacher = torch.randn(W * n_loc, dt, generator=torch.Generator().manual_seed(seed + 7))
+        np.savez(HERE / f"loss_kd_{name}.npz", img=np_(img), txt=np_(txt), teacher=np_(teacher), logit_scale_log=ls,
+                 W=W, n_loc=n_loc, gather_with_grad=gwg, kd_loss_weight=0.5,
+                 loss=np.stack([r[1] for r in res]), dI=np.stack([r[2] for r in res]),
+                 dT=np.stack([r[3] for r in res]), dlogit_scale_log=np.stack([r[4] for r in res]))
+        print("loss_kd", name, [float(r[1]) for r in res])
 
 
 def gen_loss_dist():
@@ -308,6 +367,9 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "lora":
         gen_lora_loss()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "kd":
+        gen_loss_kd()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "accum4":
         gen_loss_accum_big()
         sys.exit(0)
@@ -318,4 +380,5 @@ if __name__ == "__main__":
     gen_tail()
     gen_topk()
     gen_loss_dist()
+    gen_loss_kd()
     print("golden fixtures written to", HERE)

@@ -140,6 +140,25 @@ def test_native_jsonl_parser_falls_back(tmp_path):
     _write(t, ['{"image_id": 1, "feature": [1.0, 2.0]}\n', '{"image_id": 2, "feature": [3.0, 4'])
     with pytest.raises(Exception):
         fio._load_jsonl_native(str(t), "image_id")
+    # tokens from_chars would take but json.loads reads differently (or refuses): the native parser must
+    # refuse them so that the fallback decides
+    for k, bad in enumerate(['{"image_id": 12.5, "feature": [1.0]}\n', '{"image_id": 1e3, "feature": [1.0]}\n',
+                             '{"image_id": 1, "feature": [nan]}\n', '{"image_id": 1, "feature": [inf]}\n',
+                             '{"image_id": 1, "feature": [012]}\n', '{"image_id": 1, "feature": [.5]}\n',
+                             '{"image_id": 1, "feature": [5.]}\n', '{"image_id": 1, "feature": [1.0]} trailing\n',
+                             '{"image_id": 1, "feature": [1.0]\n', '"image_id": 1, "feature": [1.0]}\n']):
+        b = tmp_path / f"bad{k}.jsonl"
+        _write(b, [bad])
+        with pytest.raises(Exception):
+            fio._load_jsonl_native(str(b), "image_id")
+    nn = tmp_path / "nan.jsonl"                                     # json.loads' own NaN / Infinity spelling
+    _write(nn, ['{"image_id": 1, "feature": [NaN, -Infinity]}\n'])
+    ids, f = fio.load_jsonl_features(str(nn), "image_id")
+    assert ids == [1] and np.isnan(f[0, 0]) and f[0, 1] == -np.inf
+    fl = tmp_path / "fl.jsonl"                                      # a float id stays a float, as json.loads has it
+    _write(fl, ['{"image_id": 12.5, "feature": [1.0]}\n'])
+    ids, f = fio.load_jsonl_features(str(fl), "image_id")
+    assert ids == [12.5]
     e = tmp_path / "e.jsonl"
     _write(e, [])
     ids, f = fio.load_jsonl_features(str(e), "image_id")

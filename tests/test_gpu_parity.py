@@ -111,17 +111,23 @@ def run_loss(dev, I, T, s, dt=torch.float16, **kw):
     return loss.detach().cpu(), acc, Ic.grad.cpu(), Tc.grad.cpu(), sc.grad.cpu()
 
 
+@pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16], ids=["fp16", "bf16"])
 @pytest.mark.parametrize("name", ["a", "b", "c", "d", "e"])
-def test_loss_matches_reference_get_loss(dev, golden_dir, name):
-    """Golden outputs of the reference's own get_loss (aggregate=False)."""
+def test_loss_matches_reference_get_loss(dev, golden_dir, name, dt):
+    """Golden outputs of the reference's own get_loss (aggregate=False).  Every fixture runs in the
+    product's default operand type (fp16) at the 1e-3 bar of BASELINE.json; bf16 operands are an extra
+    at 3e-3 (fixture d holds general fp32 features: bf16 rounding of the features themselves is
+    outside what the 16-bit-exact comparison covers, so it is fp16 only)."""
+    if name == "d" and dt == torch.bfloat16:
+        pytest.skip("fixture d: fp32 features, not bf16-exact")
     g = np.load(golden_dir / f"loss_w1_{name}.npz")
     I, T, s = torch.from_numpy(g["img"]), torch.from_numpy(g["txt"]), float(g["s"])
     n, d = I.shape
-    loss, acc, dI, dT, ds = run_loss(dev, I, T, s, torch.bfloat16 if name != "d" else torch.float16)
+    loss, acc, dI, dT, ds = run_loss(dev, I, T, s, dt)
     # absolute floor: the loss is a mean of (lse - logit) with |logit| <= s, i.e. fp32 ulp(s) noise
     assert abs(float(loss) - float(g["loss"])) <= TOL * abs(float(g["loss"])) + 1e-6 * s
     assert abs(float(acc["i2t"]) - float(g["i2t"])) < 1e-6 and abs(float(acc["t2i"]) - float(g["t2i"])) < 1e-6
-    tol = TOL if name == "d" else 3e-3  # bf16 operand for G: see DESIGN.md "Precision"
+    tol = TOL if dt == torch.float16 else 3e-3  # bf16 operand for G: see DESIGN.md "Precision"
     assert grad_ok(dI, torch.from_numpy(g["dI"]), n, s, tol)
     assert grad_ok(dT, torch.from_numpy(g["dT"]), n, s, tol)
     want_ds = float(g["dlogit_scale_log"]) / s
@@ -141,6 +147,9 @@ def test_loss_fwd_bwd_vs_oracle_fp16(dev, n, d, s, corr):
     want = OL.global_loss_and_grads(I, T, s, torch.float64)
     loss, acc, dI, dT, ds = run_loss(dev, I, T, s)
     assert abs(float(loss) - float(want["loss"])) <= TOL * abs(float(want["loss"])) + 1e-6 * s
+    # one flipped row is allowed: the kernel takes the arg-max of fp32-accumulated fp16 products summed in
+    # tensor-core order, the oracle of an fp64 product; rows whose two best logits are closer than that
+    # rounding difference (~1e-6 * s) may pick the other one.  The reference fixtures above are exact.
     assert abs(float(acc["i2t"]) - float(want["i2t"])) <= 1.5 / n
     assert abs(float(acc["t2i"]) - float(want["t2i"])) <= 1.5 / n
     assert grad_ok(dI, want["dI"], n, s), f"dI rel {relerr(dI, want['dI']):.3e}"
@@ -309,9 +318,12 @@ def test_backward_with_supplied_lse_minmax(dev):
     assert grad_ok(a[0].cpu(), glob["dI"], n, s)
 
 
-def test_accumulate_path_rows(dev, golden_dir):
-    """Gradient only for chunk j's rows (train.py:48-51), against the reference's own output."""
+@pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16], ids=["fp16", "bf16"])
+def test_accumulate_path_rows(dev, golden_dir, dt):
+    """Gradient only for chunk j's rows (train.py:48-51), against the reference's own output
+    (fp16 operands at 1e-3, bf16 at 3e-3)."""
     from nans_clip_b200.loss import clip_contrastive_loss
+    tol = TOL if dt == torch.float16 else 3e-3
     for j in range(3):
         g = np.load(golden_dir / f"loss_accum_j{j}.npz")
         B = int(g["B"])
@@ -320,11 +332,11 @@ def test_accumulate_path_rows(dev, golden_dir):
         ct = T[j * B:(j + 1) * B].clone().requires_grad_(True)
         s = torch.tensor(float(g["s"]), device=dev, requires_grad=True)
         loss, _ = clip_contrastive_loss(ci, ct, s, full_image_features=I, full_text_features=T, row_begin=j * B,
-                                        feat_dtype=torch.bfloat16)
+                                        feat_dtype=dt)
         loss.backward()
         assert abs(float(loss) - float(g["loss"])) <= TOL * float(g["loss"])
-        assert relerr(ci.grad.cpu(), torch.from_numpy(g["dI"])) < 3e-3
-        assert relerr(ct.grad.cpu(), torch.from_numpy(g["dT"])) < 3e-3
+        assert relerr(ci.grad.cpu(), torch.from_numpy(g["dI"])) < tol
+        assert relerr(ct.grad.cpu(), torch.from_numpy(g["dT"])) < tol
 
 
 def test_incremental_accumulate_path_matches_reference(dev, golden_dir, monkeypatch):
@@ -462,6 +474,46 @@ def test_get_loss_dropin_signature_and_values(dev, golden_dir):
     assert abs(float(model.logit_scale.grad) - s * float(want["ds"])) <= TOL * abs(s * float(want["ds"])) + 1e-7
 
 
+def test_evaluate_dropin_local_batches(dev):
+    """the reference's evaluate() (train.py:333-400) served by the fused forward — three
+    validation batches of different sizes (the last one ragged), each its own softmax; totals against
+    the literal per-batch logits / CrossEntropyLoss / argmax of train.py:363-382 in fp64."""
+    import types
+    import torch.nn as nn
+    from nans_clip_b200.training.train import evaluate
+    sizes, d, ls = [300, 300, 77], 512, 2.6593
+    feats = [synth(n, d, 900 + k, 0.5) for k, n in enumerate(sizes)]
+
+    class Model(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.logit_scale = nn.Parameter(torch.tensor(ls, device=dev))
+            self.k = 0
+
+        def forward(self, images, texts, mask_ratio=0):
+            I, T = feats[self.k]
+            self.k += 1
+            return I.to(dev), T.to(dev), self.logit_scale.exp()
+
+    batches = [(torch.zeros(n, 1), torch.zeros(n, 1), torch.zeros(n)) for n in sizes]
+    loader_iterable = type("L", (), {"num_batches": len(sizes), "num_samples": sum(sizes),
+                                     "__iter__": lambda self: iter(batches)})()
+    data = {"val": types.SimpleNamespace(dataloader=loader_iterable)}
+    args = types.SimpleNamespace(local_device_rank=0)
+    loss, i2t, t2i = evaluate(Model(), data, 0, args, 10)
+    s = math.exp(ls)
+    tot = hi = ht = 0.0
+    for (I, T), n in zip(feats, sizes):
+        logits = s * I.double() @ T.double().t()
+        gt = torch.arange(n)
+        tot += float((nn.functional.cross_entropy(logits, gt) + nn.functional.cross_entropy(logits.t(), gt)) / 2) * n
+        hi += float((logits.argmax(-1) == gt).sum())
+        ht += float((logits.t().argmax(-1) == gt).sum())
+    N = sum(sizes)
+    assert abs(loss - tot / N) <= TOL * tot / N
+    assert abs(i2t - hi / N) <= 1.5 / N and abs(t2i - ht / N) <= 1.5 / N
+
+
 @pytest.mark.parametrize("name", ["a", "b", "c", "d"])
 def test_lora_contrastive_loss_matches_reference(dev, golden_dir, name):
     """Golden outputs of the reference's train_lora.py `contrastive_loss` (normalise + label-smoothed
@@ -551,6 +603,158 @@ def test_full_size_properties(dev, d):
     assert abs(float(l3) - float(l1)) <= 1e-5 * float(l1)
     assert relerr(dI3, dI1[perm]) < 1e-4
     assert 0.0 <= float(acc["i2t"]) <= 1.0
+
+
+def device_checker(I, T, s, rows):
+    """The checker for shapes whose N x N logits the host oracle cannot hold: plain fp32 torch on the
+    device, in row blocks (train.py:87-88 / 103-104 / 112-115 restated blockwise).  Returns the natural-
+    log lse of every image row and text row, and dL/dI, dL/dT (mean-of-both-directions loss,
+    train.py:115) for the global rows `rows` (a LongTensor)."""
+    n = I.shape[0]
+    lse_i = torch.empty(n, device=I.device)
+    m = torch.full((n,), -float("inf"), device=I.device)
+    l = torch.zeros(n, device=I.device)
+    for b in range(0, n, 4096):
+        S = s * I[b:b + 4096] @ T.t()
+        lse_i[b:b + 4096] = torch.logsumexp(S, dim=1)
+        mb = torch.maximum(m, S.max(dim=0).values)
+        l = l * torch.exp(m - mb) + torch.exp(S - mb[None, :]).sum(dim=0)
+        m = mb
+        del S
+    lse_t = m + torch.log(l)
+    dI = torch.empty(len(rows), I.shape[1], device=I.device)
+    dT = torch.empty(len(rows), I.shape[1], device=I.device)
+    for b in range(0, len(rows), 2048):
+        r = rows[b:b + 2048]
+        ar = torch.arange(len(r), device=I.device)
+        S = s * I[r] @ T.t()
+        G = torch.exp(S - lse_i[r][:, None]) + torch.exp(S - lse_t[None, :])
+        G[ar, r] -= 2
+        dI[b:b + 2048] = s / (2 * n) * (G @ T)
+        S = s * T[r] @ I.t()
+        G = torch.exp(S - lse_t[r][:, None]) + torch.exp(S - lse_i[None, :])
+        G[ar, r] -= 2
+        dT[b:b + 2048] = s / (2 * n) * (G @ I)
+        del S, G
+    return lse_i, lse_t, dI, dT
+
+
+def synth_dev(dev, n, d, seed, corr=0.5):
+    g = torch.Generator(device=dev).manual_seed(seed)
+    base = torch.randn(n, d, device=dev, generator=g)
+    I = torch.nn.functional.normalize(corr * base + (1 - corr) * torch.randn(n, d, device=dev, generator=g), dim=-1)
+    T = torch.nn.functional.normalize(corr * base + (1 - corr) * torch.randn(n, d, device=dev, generator=g), dim=-1)
+    return I.half().float(), T.half().float()
+
+
+@pytest.mark.parametrize("W,rank,n_loc,d,chunk", [(8, 5, 4096, 512, None), (8, 0, 4096, 512, None),
+                                                   (8, 3, 8192, 768, (2, 1024)), (2, 1, 16384, 512, None)])
+def test_rank_strip_at_bench_sizes(dev, W, rank, n_loc, d, chunk):
+    """One rank's share of the jobs SCALE runs (BASELINE configs 2 and 3: W = 8, n_loc = 4096, D = 512;
+    W = 8, n_loc = 8192, D = 768 with the accumulate path's row window of one chunk), driven exactly as
+    loss.py drives the kernels on a tile-aligned shard: local block, then the gathered buffer with the
+    local tiles SKIPPED, one launch per strip; then the backward.  Checked against fp32 torch on the
+    device (the N x N logits do not fit the host oracle): lse of the rank's rows, the rank's partial
+    loss sums, and the gradients of the rank's (chunk's) rows at 1e-3."""
+    from nans_clip_b200 import kernels as K
+    N, s = W * n_loc, 14.2857
+    I, T = synth_dev(dev, N, d, 1000 + W + d)
+    lo, hi = rank * n_loc, (rank + 1) * n_loc
+    r0, rn = (chunk[0] * chunk[1], chunk[1]) if chunk else (0, n_loc)
+    rows = torch.arange(lo + r0, lo + r0 + rn, device=dev)
+    lse_i, lse_t, want_dI, want_dT = device_checker(I, T, s, rows)
+    I16, T16 = I.half(), T.half()
+    s_dev = torch.tensor([s], device=dev)
+    n_other = N - n_loc
+    slots = [K.fwd_phase_slots(n_loc, n_loc, d), K.fwd_phase_slots(n_loc, n_other, d, "img")]
+    assert slots[1] == K.fwd_phase_slots(n_loc, n_other, d, "txt")
+    ws = K.fwd_workspace(n_loc, sum(slots), dev)
+    K.fwd_phase(I16[lo:hi], T16[lo:hi], T16[lo:hi], I16[lo:hi], col_global_begin=lo, label_begin=lo, s_dev=s_dev,
+                with_acc=True, ws=ws, slot_begin=0)
+    for strip in ("img", "txt"):
+        K.fwd_phase(I16[lo:hi], T16[lo:hi], T16, I16, col_global_begin=0, label_begin=lo, s_dev=s_dev,
+                    with_acc=True, ws=ws, slot_begin=slots[0], skip_begin=lo, skip_count=n_loc, strip=strip)
+    lse, sc, _ = K.fwd_finalize(n_loc, sum(slots), lo, s_dev, True, ws)
+    LN2 = math.log(2.0)
+    assert torch.allclose(lse[0] * LN2, lse_i[lo:hi], rtol=1e-5, atol=2e-4)
+    assert torch.allclose(lse[1] * LN2, lse_t[lo:hi], rtol=1e-5, atol=2e-4)
+    diag = s * (I[lo:hi] * T[lo:hi]).sum(-1)
+    want0, want1 = float((lse_i[lo:hi] - diag).sum()), float((lse_t[lo:hi] - diag).sum())
+    assert abs(float(sc[0]) - want0) <= 1e-4 * abs(want0) and abs(float(sc[1]) - want1) <= 1e-4 * abs(want1)
+    lse_all = (torch.stack([lse_i, lse_t]) / LN2).contiguous()
+    dI, dT = K.bwd(I16[lo:hi], T16[lo:hi], T16, I16, label_begin=lo, s_dev=s_dev, lse_all=lse_all,
+                   grad_out=torch.ones(1, device=dev), grad_mult=1.0, row_begin=r0, row_count=rn,
+                   out_dtype=torch.float32)
+    assert relerr(dI, want_dI) < TOL, relerr(dI, want_dI)
+    assert relerr(dT, want_dT) < TOL, relerr(dT, want_dT)
+
+
+def test_config3_accumulate_call_at_full_size(dev):
+    """BASELINE config 3 on one GPU through the public call: N = 65536, D = 768, A = 8 (the chunk that
+    carries gradient is N / A = 8192 rows), against the device-side fp32 checker."""
+    from nans_clip_b200.loss import clip_contrastive_loss
+    N, d, A, j, s = 65536, 768, 8, 5, 14.2857
+    I, T = synth_dev(dev, N, d, 4242)
+    B = N // A
+    rows = torch.arange(j * B, (j + 1) * B, device=dev)
+    lse_i, lse_t, want_dI, want_dT = device_checker(I, T, s, rows)
+    diag = s * (I * T).sum(-1)
+    want_loss = float(((lse_i - diag).sum() + (lse_t - diag).sum()) / (2 * N))
+    ci, ct = I[rows].clone().requires_grad_(True), T[rows].clone().requires_grad_(True)
+    sc = torch.tensor(s, device=dev, requires_grad=True)
+    loss, _ = clip_contrastive_loss(ci, ct, sc, full_image_features=I, full_text_features=T, row_begin=j * B)
+    loss.backward()
+    assert abs(float(loss) - want_loss) <= 1e-4 * abs(want_loss)
+    assert relerr(ci.grad, want_dI) < TOL and relerr(ct.grad, want_dT) < TOL
+
+
+@pytest.mark.parametrize("name", ["a", "b", "c"])
+def test_patch_clip_forward_and_get_similarity(dev, golden_dir, name):
+    """The binding of INTEGRATION.md section A, executed: `patch_clip` on a CLIP-shaped module whose
+    towers return the fixture's raw features; `forward` and `get_similarity` against what the reference's
+    own CLIP.forward tail / get_similarity produced from the same raw features (model.py:402-431)."""
+    import torch.nn as nn
+    from nans_clip_b200.clip.model import patch_clip
+    g = np.load(golden_dir / f"tail_{name}.npz")
+
+    class Towers(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.raw_i = nn.Parameter(torch.from_numpy(g["raw_i"]).to(dev))
+            self.raw_t = nn.Parameter(torch.from_numpy(g["raw_t"]).to(dev))
+            self.logit_scale = nn.Parameter(torch.tensor(float(g["logit_scale_log"]), device=dev))
+
+        def encode_image(self, image, mask_ratio=0):
+            return self.raw_i
+
+        def encode_text(self, text):
+            return self.raw_t
+
+        def forward(self, image, text, mask_ratio=0):
+            raise AssertionError("patch_clip must replace forward")
+
+    model = patch_clip(Towers())
+    I, T, sc = model(object(), object(), 0.5)
+    assert float((I.detach().cpu() - torch.from_numpy(g["I"])).abs().max()) <= 2e-7
+    assert float((T.detach().cpu() - torch.from_numpy(g["T"])).abs().max()) <= 2e-7
+    assert abs(float(sc) - float(g["s"])) <= 1e-6 * float(g["s"])
+    (I * torch.from_numpy(g["gI"]).to(dev)).sum().backward()
+    assert relerr(model.raw_i.grad.cpu(), torch.from_numpy(g["d_raw_i"])) < 1e-5
+    # one-sided calls return the tower output untouched (model.py:404-408)
+    assert model(None, object()) is model.raw_t and model(object(), None) is model.raw_i
+    with pytest.raises(AssertionError):
+        model(None, None)
+    lpi, lpt = model.get_similarity(object(), object())
+    want = torch.from_numpy(g["lpi"])
+    assert float((lpi.detach().cpu() - want).abs().max()) <= 1e-5 * float(want.abs().max())
+    assert float((lpt.detach().cpu() - torch.from_numpy(g["lpt"])).abs().max()) <= 1e-5 * float(want.abs().max())
+    # DDP-style wrapper: the method lands on .module
+    class Wrap(nn.Module):
+        def __init__(self, m):
+            super().__init__()
+            self.module = m
+    w = patch_clip(Wrap(Towers()))
+    assert w.module.forward.__func__.__module__.endswith("clip.model")
 
 
 # --------------------------------------------------------------------------------------------

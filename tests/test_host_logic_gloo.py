@@ -75,6 +75,67 @@ def test_distributed_loss_matches_reference(name, port):
         assert all(ok), f"rank {rank}: {ok} {info}"
 
 
+def _kd_worker(rank, W, port, fixture, q):
+    """get_loss with args.distillation against the reference's own output (loss_kd_*.npz): student /
+    teacher gather orders and the gradient through the gather under gather_with_grad."""
+    try:
+        if W > 1:
+            _init(rank, W, port)
+        else:
+            sys.path.insert(0, str(ROOT))
+            sys.path.insert(0, str(ROOT / "tests"))
+            from nans_clip_b200 import kernels as K
+            import _fake_kernels
+            _fake_kernels.install(K)
+        import types
+        import torch.nn as nn
+        from nans_clip_b200.training import train as TR
+        TR.FEAT_DTYPE = torch.float32   # CPU stand-in kernels
+        g = np.load(fixture)
+        n_loc = int(g["n_loc"])
+        sl = slice(rank * n_loc, (rank + 1) * n_loc)
+
+        class Stub(nn.Module):
+            def __init__(self):
+                super().__init__()
+                self.img = nn.Parameter(torch.from_numpy(g["img"])[sl].clone())
+                self.txt = nn.Parameter(torch.from_numpy(g["txt"])[sl].clone())
+                self.logit_scale = nn.Parameter(torch.tensor(float(g["logit_scale_log"])))
+
+            def forward(self, images, texts, mask_ratio=0):
+                return self.img, self.txt, self.logit_scale.exp()
+
+        teacher = types.SimpleNamespace()
+        teacher.module = types.SimpleNamespace(get_feature=lambda images: torch.from_numpy(g["teacher"])[sl])
+        args = types.SimpleNamespace(accum_freq=1, mask_ratio=0, distillation=True, aggregate=W > 1,
+                                     gather_with_grad=bool(g["gather_with_grad"]), local_device_rank=0,
+                                     report_training_batch_acc=False, kd_loss_weight=float(g["kd_loss_weight"]))
+        model = Stub()
+        total, _ = TR.get_loss(model, None, None, nn.CrossEntropyLoss(), nn.CrossEntropyLoss(), args,
+                               teacher_model=teacher)
+        total.backward()
+        ok = [abs(float(total) - float(g["loss"][rank])) <= 5e-6 * abs(float(g["loss"][rank]))]
+        for got, want in ((model.img.grad, g["dI"][rank]), (model.txt.grad, g["dT"][rank])):
+            want = torch.from_numpy(want)
+            ok.append(float((got - want).abs().max()) <= 1e-4 * float(want.abs().max()) + 1e-9)
+        want = float(g["dlogit_scale_log"][rank])
+        ok.append(abs(float(model.logit_scale.grad) - want) <= 1e-4 * abs(want) + 1e-8)
+        q.put((rank, ok, float(total)))
+        if W > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+    except Exception:
+        import traceback
+        q.put((rank, [False], traceback.format_exc()))
+
+
+@pytest.mark.parametrize("name,port", [("w1", 29731), ("w2", 29732), ("w2g", 29733)])
+def test_distillation_branch_matches_reference(name, port):
+    g = np.load(GOLDEN / f"loss_kd_{name}.npz")
+    for rank, ok, info in _spawn(_kd_worker, int(g["W"]), port, str(GOLDEN / f"loss_kd_{name}.npz")):
+        assert all(ok), f"rank {rank}: {ok} {info}"
+
+
 def _smoothing_worker(rank, W, port, gwg, q):
     """Label smoothing across ranks: the column sums / diagonal sum are all-reduced, the fix-up uses
     the global sums and the rank's rows (oracle: smoothed CE on the concatenated batch)."""
