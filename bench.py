@@ -1,22 +1,30 @@
 """bench.py — the reference's headline metric for the hot path, measured on B200.
 
-    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload loss|retrieval]
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--only loss|retrieval|...]
     (N > 1: launched by torch.distributed.run, one rank per GPU over NCCL)
 
-Workload "loss" (default; BASELINE.json configs[1]): ViT-B/16-width contrastive loss forward +
-backward, GLOBAL batch 32768 x D=512 sharded over the N ranks (strong scaling: the global batch
-is fixed), synthetic unit-norm features as SURVEY.md §8d.  A step is one fwd+bwd of the loss
-(`clip_contrastive_loss`: 16-bit cast, feature all-gather, fused forward, scalar/lse exchange,
-fused backward).
+The ONE JSON line describes BASELINE.json configs[1] (`metric` / `value` / `e2e` / `roofline`):
+ViT-B/16-width contrastive loss forward + backward, GLOBAL batch 32768 x D=512 sharded over the N
+ranks (strong scaling: the global batch is fixed), synthetic unit-norm features as SURVEY.md §8d.
+A step is one fwd+bwd of the loss through the public call (`clip_contrastive_loss`: 16-bit cast,
+feature exchange, fused forward, lse/scalar exchange, fused backward).
   value : pairs/s = 32768 / step time, inputs resident in HBM, CUDA events, max over ranks
-  e2e   : the same step through the public call with HOST (pinned) fp32 features: H2D of the
-          step's features inside the timed region, loss scalar read back
+  e2e   : the same step with HOST (pinned) fp32 features: H2D of the step's features inside the timed
+          region, loss scalar read back
   roofline : the dominant kernel (fused backward), algorithmic flops / its measured launch time,
-             against the measured bf16 peak in MEASURED_PEAKS.json
-  cpu_baseline : the oracle (fp32 torch port of the reference path) on this box's host cores
+             against the measured bf16 burst peak in MEASURED_PEAKS.json
+  cpu_baseline : the oracle (fp32 torch port of the reference path) on this box's host cores (N=1 only)
+  parity_check : N > 1 only — every rank's loss, d(scale) and gradient slice against the single-GPU
+                 fused path on the full batch (which tests/ hold to the oracle); exits non-zero on failure
 
-`--impl reference` times the reference's own algorithm (the oracle port: the reference is
-PyTorch code, its arithmetic IS these torch ops) on the host cores, rank 0 only.
+The other BASELINE.json configs and kernels ride in the same line under `workloads` (time-boxed, each
+with its own roofline): `retrieval` (configs[4]: top-10, Q=30000 x G=1e6, gallery sharded x N),
+`loss_d1024` (configs[3]), `accum_n65536_d768_a8` (configs[2], the gradient-accumulation call site),
+`l2norm` (kernel (1), HBM GB/s).  `--only X` runs one of them alone.
+
+`--impl reference` times the reference's own algorithm on the host cores, rank 0 only, on the same
+config string: the oracle port (the reference is PyTorch code: its arithmetic IS these torch ops;
+/root/reference itself cannot travel to the GPU box), really at N=32768, every step measured.
 """
 from __future__ import annotations
 
@@ -37,6 +45,13 @@ N_GLOBAL = 32768
 D = 512
 LOGIT_SCALE = 14.285714  # exp(ln(1/0.07)), model.py:356
 RET_Q, RET_G, RET_K = 30000, 1000000, 10
+WORKLOADS = ("retrieval", "loss_d1024", "accum_n65536_d768_a8", "l2norm")
+
+
+def workload_string(W: int) -> str:
+    """The same string in both arms (the driver compares them)."""
+    return (f"ViT-B/16-width contrastive loss fwd+bwd, global batch {N_GLOBAL}, D={D}, "
+            f"{N_GLOBAL // W} rows/rank (BASELINE.json configs[1])")
 
 
 def measured_peaks():
@@ -65,6 +80,18 @@ def synth_features(n_rows, row0, d, seed=1235, corr=0.5):
     txt = torch.cat(outs_t)[row0 - b0 * blk: row0 - b0 * blk + n_rows]
     img = (img / img.norm(dim=-1, keepdim=True)).bfloat16().float()
     txt = (txt / txt.norm(dim=-1, keepdim=True)).bfloat16().float()
+    return img, txt
+
+
+def synth_features_device(n_rows, d, dev, seed, corr=0.5):
+    """The same recipe on the device (the secondary workloads; identical on every rank for one seed)."""
+    g = torch.Generator(device=dev).manual_seed(seed)
+    base = torch.randn(n_rows, d, device=dev, generator=g)
+    img = corr * base + (1 - corr) * torch.randn(n_rows, d, device=dev, generator=g)
+    txt = corr * base + (1 - corr) * torch.randn(n_rows, d, device=dev, generator=g)
+    del base
+    img = torch.nn.functional.normalize(img, dim=-1).bfloat16().float()
+    txt = torch.nn.functional.normalize(txt, dim=-1).bfloat16().float()
     return img, txt
 
 
@@ -104,6 +131,7 @@ class ClockSampler:
         if self.nv is not None:
             self._thread = threading.Thread(target=self._run, daemon=True)
             self._thread.start()
+        return self
 
     def stop(self):
         self._stop.set()
@@ -114,16 +142,16 @@ class ClockSampler:
                 "reasons": sorted(self.reasons), "samples": len(s)}
 
 
-def dist_setup(n_gpus):
+def dist_setup():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
     if world > 1:
         import torch.distributed as dist
-        torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         return dist, world, rank, local
-    return None, 1, 0, 0
+    return None, 1, 0, local
 
 
 def timed_steps(step_fn, steps, warmup, flush, dist, dev):
@@ -155,85 +183,184 @@ def timed_steps(step_fn, steps, warmup, flush, dist, dev):
     return float(t.item())
 
 
-def cpu_loss_baseline(budget_s=20.0):
-    """The oracle (port of train.py:87-115 + autograd) on the host cores, bounded sample."""
+# ================================================================================================
+# CPU legs (the only places that execute oracle/): reported baselines, never the product path
+# ================================================================================================
+def host_threads() -> int:
+    # torchrun exports OMP_NUM_THREADS=1 to every rank; a CPU leg is rank 0 alone on the host cores,
+    # so it takes all of them (what a plain `python bench.py --impl reference` gets by default)
+    try:
+        n = max(1, len(os.sched_getaffinity(0)))
+    except (AttributeError, OSError):
+        n = max(1, os.cpu_count() or 1)
+    torch.set_num_threads(n)
+    return n
+
+
+def cpu_loss_steps(steps, warmup, budget_s, n=None):
+    """The oracle (port of model.py:412-415 + train.py:87-115 + autograd backward) REALLY at
+    N = 32768, D = 512 on the host cores: `warmup` untimed steps (at most 1 is enough to fault the
+    20 GB of temporaries in), then up to `steps` timed ones inside `budget_s` (at least 2).
+    Returns (per-step seconds list, threads)."""
     from oracle import clip_loss as OL
-    n = 8192
-    img, txt = synth_features(n, 0, D)
-    threads = torch.get_num_threads()
+    threads = host_threads()
+    img, txt = synth_features(n or N_GLOBAL, 0, D)
     t0 = time.perf_counter()
-    OL.global_loss_and_grads(img[:1024], txt[:1024], LOGIT_SCALE)  # warm-up
-    reps, spent = 0, 0.0
-    while reps < 1 or (spent < budget_s / 2 and reps < 5):
+    OL.global_loss_and_grads(img[:2048], txt[:2048], LOGIT_SCALE)
+    est = None
+    for _ in range(min(warmup, 1)):
         t1 = time.perf_counter()
         OL.global_loss_and_grads(img, txt, LOGIT_SCALE)
-        spent += time.perf_counter() - t1
-        reps += 1
-    per = spent / reps
-    full = per * (N_GLOBAL / n) ** 2  # cost is quadratic in the global batch
-    return {"value": N_GLOBAL / full, "unit": "pairs/s", "cores": threads, "kind": "port",
-            "sample": f"fp32 torch fwd+bwd at N={n}, D={D}: {per:.3f} s/step over {reps} reps; "
-                      f"extrapolated x{(N_GLOBAL // n) ** 2} (cost ~ N^2) to N={N_GLOBAL}",
-            "measured_pairs_per_s_at_sample": n / per, "wall_s": time.perf_counter() - t0}
+        est = time.perf_counter() - t1
+    times = []
+    while len(times) < steps:
+        if len(times) >= 2 and est is not None and (time.perf_counter() - t0) + est > budget_s:
+            break
+        t1 = time.perf_counter()
+        OL.global_loss_and_grads(img, txt, LOGIT_SCALE)
+        times.append(time.perf_counter() - t1)
+        est = times[-1]
+    return times, threads
 
 
-def cpu_topk_baseline(budget_s=15.0):
+def cpu_loss_baseline(reps=2):
+    times, threads = cpu_loss_steps(reps, 1, 1e9)
+    per = sum(times) / len(times)
+    return {"value": N_GLOBAL / per, "unit": "pairs/s", "cores": threads, "kind": "port",
+            "sample": f"fp32 torch fwd+bwd of the oracle port REALLY at N={N_GLOBAL}, D={D} (no extrapolation): "
+                      f"1 warm-up + {len(times)} timed steps, {per:.2f} s/step"}
+
+
+def cpu_topk_baseline(n_vec=512, n_lit=8):
+    """BASELINE.md §3 legs B3 (the literal per-query loop of make_topk_predictions.py:71-85) and B4 (its
+    vectorised restatement) at G = 1e6, on a bounded sample of the 30000 queries."""
     from oracle import topk as OT
+    threads = host_threads()
     g = torch.Generator().manual_seed(77)
     gal = torch.nn.functional.normalize(torch.randn(RET_G, D, generator=g), dim=-1)
-    q = torch.nn.functional.normalize(torch.randn(512, D, generator=g), dim=-1)
-    t0 = time.perf_counter()
+    q = torch.nn.functional.normalize(torch.randn(n_vec, D, generator=g) + 0.5 * gal[(torch.arange(n_vec) * 33) % RET_G], dim=-1)
     OT.topk_vectorised(gal, q[:64], RET_K)
     t1 = time.perf_counter()
-    OT.topk_vectorised(gal, q, RET_K, block=128)
-    per = (time.perf_counter() - t1) / q.shape[0]
-    return {"value": 1.0 / per, "unit": "queries/s", "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"vectorised fp32 Q@G^T + stable sort, {q.shape[0]} of {RET_Q} queries x G={RET_G}",
-            "wall_s": time.perf_counter() - t0}
+    _, vi = OT.topk_vectorised(gal, q, RET_K, block=128)
+    per_vec = (time.perf_counter() - t1) / n_vec
+    ids = list(range(1000000, 1000000 + RET_G))
+    gal_np = gal.numpy()
+    t1 = time.perf_counter()
+    same = True
+    for i in range(n_lit):
+        got, _ = OT.topk_literal(ids, gal_np, q[i].numpy(), RET_K)
+        same &= [g_ - 1000000 for g_ in got] == vi[i].tolist()
+    per_lit = (time.perf_counter() - t1) / n_lit
+    return {"value": 1.0 / per_vec, "unit": "queries/s", "cores": threads, "kind": "port",
+            "sample": f"B4: vectorised fp32 Q@G^T + stable sort, {n_vec} of {RET_Q} queries x G={RET_G}",
+            "literal_loop": {"value": 1.0 / per_lit, "unit": "queries/s", "cores": threads,
+                             "sample": f"B3: literal loop of make_topk_predictions.py:71-85, {n_lit} queries x G={RET_G} "
+                                       f"({per_lit:.2f} s/query; 30000 queries would take {per_lit * RET_Q / 3600:.1f} h)",
+                             "same_ids_as_vectorised": bool(same)}}
 
 
 def run_reference_arm(args):
-    """The reference's own CPU path for the same metric/config (rank 0 only)."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    """The reference's own CPU path for the same metric/config (rank 0 only; other ranks exit 0)."""
+    if int(os.environ.get("RANK", "0")) != 0:
         return
-    # torchrun exports OMP_NUM_THREADS=1 to every rank; the reference arm is rank 0 alone on the host
-    # cores, so it takes all of them (what a plain `python bench.py --impl reference` gets by default)
-    try:
-        torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
-    except (AttributeError, OSError):
-        torch.set_num_threads(max(1, os.cpu_count() or 1))
-    if args.workload == "retrieval":
+    W = max(1, args.gpus)
+    if args.only == "retrieval":
         base = cpu_topk_baseline()
-        metric, cfg = "retrieval_queries_per_s", {"workload": f"top-{RET_K} retrieval Q={RET_Q} G={RET_G} D={D}"}
-    else:
-        base = cpu_loss_baseline()
-        metric, cfg = "contrastive_fwd_bwd_pairs_per_s", {"workload": f"contrastive loss fwd+bwd, global batch {N_GLOBAL}, D={D}"}
-    line = {"impl": "reference", "metric": metric, "value": base["value"], "unit": base["unit"],
-            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1e3 * (N_GLOBAL if args.workload == "loss" else RET_Q) / base["value"],
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": cfg,
-            "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
-            "e2e": {"value": base["value"], "unit": base["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        line = {"impl": "reference", "metric": "retrieval_queries_per_s", "value": base["value"], "unit": base["unit"],
+                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * RET_Q / base["value"],
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": f"top-{RET_K} retrieval Q={RET_Q} G={RET_G} D={D}"},
+                "cpu_baseline": base,
+                "e2e": {"value": base["value"], "unit": base["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        emit(line)
+        return
+    budget = float(os.environ.get("NANS_REF_BUDGET_S", "240"))
+    n = args.contract_test_n or N_GLOBAL
+    times, threads = cpu_loss_steps(args.steps, args.warmup, budget, n)
+    per = sum(times) / len(times)
+    value = n / per
+    sample = (f"oracle port (fp32 torch, train.py:87-115 + autograd) REALLY at N={n}, D={D}: "
+              f"{min(args.warmup, 1)} warm-up + {len(times)} timed steps of {args.steps} requested "
+              f"(time budget {budget:.0f} s), {per:.2f} s/step, no extrapolation")
+    line = {"impl": "reference", "metric": "contrastive_fwd_bwd_pairs_per_s", "value": value, "unit": "pairs/s",
+            "n_gpus": args.gpus, "steps": len(times), "steps_requested": args.steps, "warmup": min(args.warmup, 1),
+            "ms_per_step": 1e3 * per, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_string(W) if n == N_GLOBAL else f"CONTRACT TEST ONLY: global batch {n}",
+                       "global_batch": n, "D": D, "logit_scale": LOGIT_SCALE,
+                       "where": f"host cores of the box ({threads} threads), rank 0 only"},
+            "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    if not args.no_secondary:
+        try:
+            line["workloads"] = {"retrieval": cpu_topk_baseline(n_vec=256, n_lit=8)}
+        except Exception as exc:  # the headline line must survive a secondary leg
+            line["workloads"] = {"retrieval": {"error": repr(exc)}}
     emit(line)
 
 
-def bench_loss(args):
+# ================================================================================================
+# the loss step (configs[1]) and its relatives
+# ================================================================================================
+def parity_check(dist, W, rank, dev, group, feat_dt):
+    """N > 1: the multi-rank path against the single-GPU fused path on the full batch (rank 0 computes
+    it and broadcasts), in both gather modes.  The single-GPU path is what tests/ hold to the oracle and
+    to the reference's fixtures at 1e-3; here every rank compares its loss, d(scale) and its dI / dT slice
+    (x W under gather_with_grad)."""
+    from nans_clip_b200.loss import clip_contrastive_loss
+    n_loc = N_GLOBAL // W
+    ref = torch.empty((2, N_GLOBAL, D), dtype=torch.float32, device=dev)
+    sc = torch.empty(2, dtype=torch.float32, device=dev)
+    if rank == 0:
+        img, txt = synth_features(N_GLOBAL, 0, D)
+        a = img.to(dev).requires_grad_(True)
+        b = txt.to(dev).requires_grad_(True)
+        s = torch.tensor(LOGIT_SCALE, device=dev, requires_grad=True)
+        loss, _ = clip_contrastive_loss(a, b, s, group=None, feat_dtype=feat_dt)
+        loss.backward()
+        ref[0], ref[1] = a.grad, b.grad
+        sc[0], sc[1] = loss.detach(), s.grad
+        del a, b
+    dist.broadcast(ref, 0)
+    dist.broadcast(sc, 0)
+    img, txt = synth_features(n_loc, rank * n_loc, D)
+    worst = torch.zeros(4, dtype=torch.float64, device=dev)
+    sl = slice(rank * n_loc, (rank + 1) * n_loc)
+    for gwg in (False, True):
+        a = img.to(dev).requires_grad_(True)
+        b = txt.to(dev).requires_grad_(True)
+        s = torch.tensor(LOGIT_SCALE, device=dev, requires_grad=True)
+        loss, _ = clip_contrastive_loss(a, b, s, group=group, gather_with_grad=gwg, feat_dtype=feat_dt)
+        loss.backward()
+        mult = float(W) if gwg else 1.0
+        errs = torch.stack([
+            (loss.detach() - sc[0]).abs() / sc[0].abs(),
+            (s.grad - sc[1]).abs() / sc[1].abs(),
+            (a.grad - mult * ref[0, sl]).norm() / (mult * ref[0, sl]).norm(),
+            (b.grad - mult * ref[1, sl]).norm() / (mult * ref[1, sl]).norm()]).double()
+        worst = torch.maximum(worst, torch.nan_to_num(errs, nan=1e9))
+    dist.all_reduce(worst, op=dist.ReduceOp.MAX)
+    w = [float(x) for x in worst.tolist()]
+    tol = 1e-3
+    return {"against": "single-GPU fused path on the full batch (rank 0), both gather modes, max over ranks",
+            "loss_rel": w[0], "dscale_rel": w[1], "dI_rel": w[2], "dT_rel": w[3], "tol": tol,
+            "ok": bool(max(w) <= tol)}
+
+
+def loss_step_bench(args, dist, W, rank, dev, n_global, d, with_e2e, kernel_rooflines, sampler_index):
+    """Times the loss step at (n_global, d) sharded over the W ranks.  Returns a dict (rank 0 uses it)."""
     from nans_clip_b200 import kernels as K
     from nans_clip_b200.loss import clip_contrastive_loss
-
-    dist, W, rank, local = dist_setup(args.gpus)
-    dev = torch.device("cuda", local)
-    torch.cuda.set_device(dev)
-    assert N_GLOBAL % W == 0
-    n_loc = N_GLOBAL // W
+    n_loc = n_global // W
     group = dist.group.WORLD if dist is not None else None
     feat_dt = torch.float16
     peaks = measured_peaks()
-
-    img, txt = synth_features(n_loc, rank * n_loc, D)
-    img_h, txt_h = img.pin_memory(), txt.pin_memory()
+    if d == D and n_global == N_GLOBAL:
+        img, txt = synth_features(n_loc, rank * n_loc, d)
+    else:
+        fi, ft = synth_features_device(n_global, d, dev, 4000 + d)
+        img, txt = fi[rank * n_loc:(rank + 1) * n_loc].clone(), ft[rank * n_loc:(rank + 1) * n_loc].clone()
+        del fi, ft
     img_d = img.to(dev).requires_grad_(True)
     txt_d = txt.to(dev).requires_grad_(True)
     s = torch.tensor(LOGIT_SCALE, device=dev, requires_grad=True)
@@ -245,25 +372,13 @@ def bench_loss(args):
         loss.backward()
         return loss
 
-    def step_e2e():
-        i = img_h.to(dev, non_blocking=True).requires_grad_(True)
-        t = txt_h.to(dev, non_blocking=True).requires_grad_(True)
-        s.grad = None
-        loss, _ = clip_contrastive_loss(i, t, s, group=group, feat_dtype=feat_dt)
-        loss.backward()
-        return float(loss.item())  # D2H read of the step's result
-
-    sampler = ClockSampler(local)
     l0 = K.LAUNCHES
     for _ in range(args.warmup):
         step()
     torch.cuda.synchronize()
     launches_per_step = (K.LAUNCHES - l0) // max(args.warmup, 1)
-    run_step = step
-    graphed = False
+    run_step, graphed = step, False
     if args.graph and dist is None:  # NCCL collectives inside a captured step hung at 2 GPUs: 1 GPU only
-        # capture one whole step (casts, gathers, fused forward, exchange, fused backward) in a CUDA
-        # graph and replay it: same kernels and collectives, no per-launch host latency
         try:
             g = torch.cuda.CUDAGraph()
             side = torch.cuda.Stream()
@@ -273,193 +388,356 @@ def bench_loss(args):
                     step()
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
-            if dist is not None:
-                dist.barrier()
             with torch.cuda.graph(g):
                 step()
             torch.cuda.synchronize()
-            run_step = g.replay
-            graphed = True
+            run_step, graphed = g.replay, True
             for _ in range(2):
                 run_step()
             torch.cuda.synchronize()
         except Exception as exc:  # fall back to eager launches, say so in the line
             print(f"[bench] CUDA graph capture failed, timing eager launches: {exc!r}", file=sys.stderr)
             run_step = step
-    sampler.start()
-    total_ms = timed_steps(run_step, args.steps, 0, flush, dist, dev)
+    sampler = ClockSampler(sampler_index).start()
+    ms = timed_steps(run_step, args.steps, 0, flush, dist, dev) / args.steps
     clocks = sampler.stop()
-    ms = total_ms / args.steps
-    e2e_ms = timed_steps(step_e2e, args.steps, min(args.warmup, 3), flush, dist, dev) / args.steps
+    out = {"ms_per_step": ms, "launches_per_step": launches_per_step, "graphed": graphed, "clocks": clocks,
+           "n_loc": n_loc}
+    if with_e2e:
+        img_h, txt_h = img.pin_memory(), txt.pin_memory()
 
-    # ---- dominant kernel (fused backward) timed alone, on this rank ----
-    with torch.no_grad():
-        I16, _, _ = K.l2norm_cast(img_d.detach(), feat_dt, normalize=False)
-        T16, _, _ = K.l2norm_cast(txt_d.detach(), feat_dt, normalize=False)
+        def step_e2e():
+            i = img_h.to(dev, non_blocking=True).requires_grad_(True)
+            t = txt_h.to(dev, non_blocking=True).requires_grad_(True)
+            s.grad = None
+            loss, _ = clip_contrastive_loss(i, t, s, group=group, feat_dtype=feat_dt)
+            loss.backward()
+            return float(loss.item())  # D2H read of the step's result
+
+        out["e2e_ms"] = timed_steps(step_e2e, args.steps, min(args.warmup, 3), flush, dist, dev) / args.steps
+    if kernel_rooflines:
+        # ---- forward and backward kernels timed alone, on this rank ----
+        with torch.no_grad():
+            I16, _, _ = K.l2norm_cast(img_d.detach(), feat_dt, normalize=False)
+            T16, _, _ = K.l2norm_cast(txt_d.detach(), feat_dt, normalize=False)
+            if W > 1:
+                I_all = torch.empty((n_global, d), dtype=feat_dt, device=dev)
+                T_all = torch.empty((n_global, d), dtype=feat_dt, device=dev)
+                dist.all_gather_into_tensor(I_all, I16)
+                dist.all_gather_into_tensor(T_all, T16)
+            else:
+                I_all, T_all = I16, T16
+            s_dev = s.detach().reshape(1)
+            slots = K.fwd_phase_slots(n_loc, n_global, d)
+            ws = K.fwd_workspace(n_loc, slots, dev)
+
+            def fwd_only():
+                K.fwd_phase(I16, T16, T_all, I_all, col_global_begin=0, label_begin=rank * n_loc, s_dev=s_dev,
+                            with_acc=False, ws=ws, slot_begin=0)
+
+            fwd_only()
+            lse, _sc, _ = K.fwd_finalize(n_loc, slots, rank * n_loc, s_dev, False, ws)
+            if W > 1:
+                lse_g = torch.empty((W * 2, n_loc), dtype=torch.float32, device=dev)
+                dist.all_gather_into_tensor(lse_g, lse.contiguous())
+                lse_all = lse_g.view(W, 2, n_loc).permute(1, 0, 2).reshape(2, n_global)
+            else:
+                lse_all = lse
+            pad = (n_global + 3) // 4 * 4
+            lse_pad = torch.empty((2, pad), dtype=torch.float32, device=dev)[:, :n_global]
+            lse_pad.copy_(lse_all)
+            gout = torch.ones(1, device=dev)
+
+            def bwd_only():
+                K.bwd(I16, T16, T_all, I_all, label_begin=rank * n_loc, s_dev=s_dev, lse_all=lse_pad,
+                      grad_out=gout, grad_mult=1.0, row_begin=0, row_count=n_loc, out_dtype=torch.float32)
+
+            kb = max(3, min(args.steps, 10))
+            bwd_ms = timed_steps(bwd_only, kb, 2, flush, None, dev) / kb
+            fwd_ms = timed_steps(fwd_only, kb, 2, flush, None, dev) / kb
+        # algorithmic work per rank: backward 4 * n_loc * N * D (dI and dT; the logit
+        # recompute is not counted), forward 2 * n_loc * N * D
+        bwd_alg = 4.0 * n_loc * n_global * d
+        fwd_alg = 2.0 * n_loc * n_global * d
+        out["roofline"] = {"kernel": "clip_bwd_np_kernel", "bound": "tensor", "achieved": bwd_alg / (bwd_ms / 1e3) / 1e12,
+                           "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                           "frac": bwd_alg / (bwd_ms / 1e3) / 1e12 / peaks["bf16_tflops"], "traffic": None,
+                           "launch_ms": bwd_ms, "algorithmic_flops_per_launch": bwd_alg,
+                           "hardware_tflops": 2 * bwd_alg / (bwd_ms / 1e3) / 1e12,
+                           "peak_source": f"{peaks['source']} burst bf16 (kernel timed alone)"}
+        out["roofline_fwd"] = {"kernel": "clip_fwd_kernel", "bound": "tensor", "achieved": fwd_alg / (fwd_ms / 1e3) / 1e12,
+                               "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                               "frac": fwd_alg / (fwd_ms / 1e3) / 1e12 / peaks["bf16_tflops"], "launch_ms": fwd_ms,
+                               "hardware_tflops": 2 * fwd_alg / (fwd_ms / 1e3) / 1e12}
+    del flush
+    return out
+
+
+def bench_loss_d1024(args, dist, W, rank, dev, local):
+    """BASELINE.json configs[3]: ViT-H/14 width, N = 32768, D = 1024 over the W ranks."""
+    n, d = N_GLOBAL, 1024
+    sub = argparse.Namespace(**vars(args))
+    sub.steps, sub.warmup, sub.graph = max(3, min(args.steps, 6)), 3, False
+    r = loss_step_bench(sub, dist, W, rank, dev, n, d, False, True, local)
+    peaks = measured_peaks()
+    alg = 6.0 * n * n * d
+    return {"config": f"BASELINE.json configs[3]: contrastive loss fwd+bwd, global batch {n}, D={d}, {n // W} rows/rank",
+            "value": n / (r["ms_per_step"] / 1e3), "unit": "pairs/s", "ms_per_step": r["ms_per_step"], "steps": sub.steps,
+            "algorithmic_tflops": alg / (r["ms_per_step"] / 1e3) / 1e12,
+            "frac_of_bf16_peak_algorithmic": alg / (r["ms_per_step"] / 1e3) / 1e12 / (W * peaks["bf16_tflops"]),
+            "roofline": r["roofline"], "roofline_fwd": r["roofline_fwd"], "clocks": r["clocks"]}
+
+
+def bench_accum(args, dist, W, rank, dev, local):
+    """BASELINE.json configs[2]: ViT-L/14 width, global batch 65536, D = 768, gradient-accumulation path
+    with A = 8 (train.py:205-247): one optimizer step = A calls of the drop-in get_loss, each with the
+    re-forwarded chunk j (B = N / (W A) rows per rank) + backward.  FLIP masking only changes the towers."""
+    import types
+    import torch.nn as nn
+    from nans_clip_b200.training.train import get_loss
+    n, d, A = 65536, 768, 8
+    n_loc = n // W
+    B = n_loc // A
+    fi, ft = synth_features_device(n, d, dev, 6500)
+    img, txt = fi[rank * n_loc:(rank + 1) * n_loc].clone(), ft[rank * n_loc:(rank + 1) * n_loc].clone()
+    del fi, ft
+    ls = torch.tensor(2.6593, device=dev)
+
+    class Chunk(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.j = 0
+            self.logit_scale = nn.Parameter(ls.clone())
+            self.img = nn.Parameter(img.clone())
+            self.txt = nn.Parameter(txt.clone())
+
+        def forward(self, images, texts, mask_ratio=0):
+            sl = slice(self.j * B, (self.j + 1) * B)
+            return self.img[sl], self.txt[sl], self.logit_scale.exp()
+
+    model = Chunk()
+    a = types.SimpleNamespace(accum_freq=A, mask_ratio=0.5, distillation=False, aggregate=W > 1, gather_with_grad=False,
+                              local_device_rank=local, report_training_batch_acc=False)
+    crit = nn.CrossEntropyLoss()
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+
+    def optimizer_step():
+        # the cache pass of train.py:205-232 is the towers' (out of scope): the cached features exist
+        cache_i = [img[c * B:(c + 1) * B].clone() for c in range(A)]
+        cache_t = [txt[c * B:(c + 1) * B].clone() for c in range(A)]
+        model.zero_grad(set_to_none=True)
+        for j in range(A):
+            model.j = j
+            total, _ = get_loss(model, None, None, crit, crit, a, cache_i, cache_t, j)
+            total.backward()
+
+    steps = max(2, min(args.steps, 3))
+    sampler = ClockSampler(local).start()
+    ms = timed_steps(optimizer_step, steps, 2, flush, dist, dev) / steps
+    clocks = sampler.stop()
+    peaks = measured_peaks()
+    # algorithmic work of the REFERENCE's A calls (SURVEY.md §8d): each recomputes the whole forward
+    per_call = 2.0 * n * n * d + 4.0 * (n / A) * n * d
+    return {"config": f"BASELINE.json configs[2]: accumulate path, global batch {n}, D={d}, A={A}, {n_loc} rows/rank "
+                      f"({B}-row chunks), through the drop-in get_loss",
+            "ms_per_optimizer_step": ms, "ms_per_call": ms / A, "steps": steps,
+            "value": n / (ms / 1e3), "unit": "pairs/s (global batch / optimizer step of A get_loss calls)",
+            "reference_algorithmic_tflop_per_call": per_call / 1e12,
+            "frac_of_bf16_peak_reference_algorithmic": per_call * A / (ms / 1e3) / 1e12 / (W * peaks["bf16_tflops"]),
+            "note": "the incremental forward (accum.py) does 4 N_l N D / A + one full forward per optimizer step "
+                    "instead of the reference's A full forwards: the fraction is against the reference's flops",
+            "clocks": clocks}
+
+
+def bench_l2norm(args, dev, local):
+    """Kernel (1) alone: [1e6, 512] fp32 -> fp16, normalise + cast (+ inv_norm), HBM-bound."""
+    from nans_clip_b200 import kernels as K
+    rows = 1000000
+    x = torch.randn(rows, D, device=dev, generator=torch.Generator(device=dev).manual_seed(1))
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    peaks = measured_peaks()
+
+    def run():
+        K.l2norm_cast(x, torch.float16, normalize=True, want_inv_norm=True)
+
+    steps = max(5, min(args.steps, 20))
+    sampler = ClockSampler(local).start()
+    ms = timed_steps(run, steps, 3, flush, None, dev) / steps
+    clocks = sampler.stop()
+    nbytes = rows * D * (4 + 2) + rows * 4
+    return {"config": f"kernel (1): L2-normalise + fp16 cast of [{rows}, {D}] fp32 (+ inv_norm), kernel alone",
+            "ms_per_launch": ms, "steps": steps,
+            "roofline": {"kernel": "l2norm_cast_kernel", "bound": "hbm", "achieved": nbytes / (ms / 1e3) / 1e9,
+                         "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": nbytes / (ms / 1e3) / 1e9 / peaks["hbm_gbs"],
+                         "algorithmic_bytes_per_launch": nbytes, "traffic": None,
+                         "peak_source": f"{peaks['source']} copy bandwidth (a copy writes as much as it reads; this "
+                                        "kernel writes a third of what it reads, so > 1.0 is possible)"},
+            "clocks": clocks}
+
+
+def bench_retrieval_core(args, dist, W, rank, dev, local, steps):
+    """BASELINE.json configs[4]: top-10 of 30000 queries over a 1M-row gallery sharded x W.  SURVEY.md
+    §8d data: every query carries its planted match (gallery row (q * 33) mod G mixed in at 0.5), ids
+    offset by 1e6.  Also times an ASCENDING-score gallery (the worst case of threshold-gated insertion)."""
+    from nans_clip_b200 import kernels as K
+    from nans_clip_b200.retrieval import GalleryShard
+    peaks = measured_peaks()
+    lo, hi = RET_G * rank // W, RET_G * (rank + 1) // W
+    g = torch.Generator(device=dev).manual_seed(4242)
+    gal_full = torch.nn.functional.normalize(torch.randn(RET_G, D, device=dev, generator=g), dim=-1).bfloat16().float()
+    planted = (torch.arange(RET_Q, device=dev) * 33) % RET_G
+    qry = torch.nn.functional.normalize(torch.randn(RET_Q, D, device=dev, generator=g) + 0.5 * gal_full[planted] * (D ** 0.5),
+                                        dim=-1).bfloat16().float()
+    gal = gal_full[lo:hi].clone()
+    del gal_full
+    shard = GalleryShard(gal, dev, torch.float16, 1000000 + lo)
+    q16, _, _ = K.l2norm_cast(qry, torch.float16, normalize=False)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    qry_h = qry.cpu().pin_memory()
+
+    def merge(s, i):
         if W > 1:
-            I_all = torch.empty((N_GLOBAL, D), dtype=feat_dt, device=dev)
-            T_all = torch.empty((N_GLOBAL, D), dtype=feat_dt, device=dev)
-            dist.all_gather_into_tensor(I_all, I16)
-            dist.all_gather_into_tensor(T_all, T16)
-        else:
-            I_all, T_all = I16, T16
-        s_dev = s.detach().reshape(1)
-        slots = K.fwd_phase_slots(n_loc, N_GLOBAL, D)
-        ws = K.fwd_workspace(n_loc, slots, dev)
+            all_s = torch.empty((W * RET_Q, RET_K), dtype=s.dtype, device=dev)
+            all_i = torch.empty((W * RET_Q, RET_K), dtype=i.dtype, device=dev)
+            dist.all_gather_into_tensor(all_s, s)
+            dist.all_gather_into_tensor(all_i, i)
+            s, i = K.topk_merge(all_s.view(W, RET_Q, RET_K), all_i.view(W, RET_Q, RET_K))
+        return s, i
 
-        def fwd_only():
-            K.fwd_phase(I16, T16, T_all, I_all, col_global_begin=0, label_begin=rank * n_loc, s_dev=s_dev,
-                        with_acc=False, ws=ws, slot_begin=0)
+    def step():
+        return merge(*K.topk_ip(q16, shard.g16, qry, shard.g32, RET_K, 16, shard.index_offset))[1]
 
-        fwd_only()
-        lse, _sc, _ = K.fwd_finalize(n_loc, slots, rank * n_loc, s_dev, False, ws)
-        if W > 1:
-            lse_g = torch.empty((W * 2, n_loc), dtype=torch.float32, device=dev)
-            dist.all_gather_into_tensor(lse_g, lse.contiguous())
-            lse_all = lse_g.view(W, 2, n_loc).permute(1, 0, 2).reshape(2, N_GLOBAL)
-        else:
-            lse_all = lse
-        pad = (N_GLOBAL + 3) // 4 * 4
-        lse_pad = torch.empty((2, pad), dtype=torch.float32, device=dev)[:, :N_GLOBAL]
-        lse_pad.copy_(lse_all)
-        gout = torch.ones(1, device=dev)
+    def step_e2e():
+        q = qry_h.to(dev, non_blocking=True)
+        return merge(*shard.search(q, RET_K))[1].cpu()
 
-        def bwd_only():
-            K.bwd(I16, T16, T_all, I_all, label_begin=rank * n_loc, s_dev=s_dev, lse_all=lse_pad,
-                  grad_out=gout, grad_mult=1.0, row_begin=0, row_count=n_loc, out_dtype=torch.float32)
+    l0 = K.LAUNCHES
+    for _ in range(3):
+        idx = step()
+    torch.cuda.synchronize()
+    lps = (K.LAUNCHES - l0) // 3
+    # the planted match must be every query's top-1 (cosine ~0.45 against ~0.2 for the best of 1e6 strangers)
+    top1_ok = bool((idx[:, 0] == planted + 1000000).all())
+    sampler = ClockSampler(local).start()
+    ms = timed_steps(step, steps, 0, flush, dist, dev) / steps
+    clocks = sampler.stop()
+    ne = max(2, steps // 4)
+    e2e_ms = timed_steps(step_e2e, ne, 1, flush, dist, dev) / ne
+    # ascending gallery: this shard's rows re-ordered by their score against the mean query direction
+    u = torch.nn.functional.normalize(qry.mean(dim=0), dim=0)
+    order = torch.argsort(shard.g32 @ u)
+    asc = GalleryShard(shard.g32[order].contiguous(), dev, torch.float16, 1000000 + lo)
 
-        kb = max(3, min(args.steps, 10))
-        bwd_ms = timed_steps(bwd_only, kb, 2, flush, None, dev) / kb
-        fwd_ms = timed_steps(fwd_only, kb, 2, flush, None, dev) / kb
-    # algorithmic work per rank: backward 4 * n_loc * N * D (dI and dT; the logit
-    # recompute is not counted), forward 2 * n_loc * N * D
-    bwd_alg = 4.0 * n_loc * N_GLOBAL * D
-    fwd_alg = 2.0 * n_loc * N_GLOBAL * D
-    traffic = None
-    tf = ROOT / "profiles" / "traffic.json"
-    if tf.exists():
-        try:
-            traffic = json.loads(tf.read_text()).get("clip_bwd_np_kernel", {}).get(f"W{W}")
-        except Exception:
-            traffic = None
+    def step_asc():
+        return merge(*K.topk_ip(q16, asc.g16, qry, asc.g32, RET_K, 16, asc.index_offset))[1]
 
+    na = max(2, steps // 4)
+    asc_ms = timed_steps(step_asc, na, 1, flush, dist, dev) / na
+    flops = 2.0 * RET_Q * (hi - lo) * D
+    return {"config": f"BASELINE.json configs[4]: top-{RET_K} text->image retrieval, Q={RET_Q}, G={RET_G}, D={D}, gallery "
+                      f"sharded x{W}, planted matches (SURVEY 8d), fp16 candidate pass (k_cand 16) + fp32 rescoring",
+            "value": RET_Q / (ms / 1e3), "unit": "queries/s", "ms_per_step": ms, "steps": steps,
+            "planted_top1_found": top1_ok,
+            "e2e": {"value": RET_Q / (e2e_ms / 1e3), "unit": "queries/s", "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": RET_Q * D * 4, "d2h_bytes_per_step": RET_Q * RET_K * 8},
+            "ascending_gallery": {"ms_per_step": asc_ms, "value": RET_Q / (asc_ms / 1e3), "unit": "queries/s",
+                                  "what": "gallery rows sorted by ascending score against the mean query direction"},
+            "gpu_launches_per_step": lps,
+            "roofline": {"kernel": "topk_floor_kernel+topk_sweep_kernel+topk_finalize_kernel", "bound": "tensor",
+                         "achieved": flops / (ms / 1e3) / 1e12, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                         "frac": flops / (ms / 1e3) / 1e12 / peaks["bf16_tflops"], "traffic": None,
+                         "algorithmic_flops_per_launch": flops,
+                         "peak_source": f"{peaks['source']} burst bf16"},
+            "clocks": clocks}
+
+
+def bench_main(args):
+    from nans_clip_b200 import kernels as K
+
+    dist, W, rank, local = dist_setup()
+    dev = torch.device("cuda", local)
+    assert N_GLOBAL % W == 0
+    peaks = measured_peaks()
     line = None
-    if rank == 0:
-        cpu = cpu_loss_baseline() if (W == 1 and not args.no_cpu_baseline) else None
+    rc = 0
+    if args.only in (None, "loss"):
+        pc = parity_check(dist, W, rank, dev, dist.group.WORLD, torch.float16) if W > 1 else None
+        r = loss_step_bench(args, dist, W, rank, dev, N_GLOBAL, D, True, True, local)
+        ms, e2e_ms, n_loc = r["ms_per_step"], r["e2e_ms"], r["n_loc"]
+        traffic = None
+        tf = ROOT / "profiles" / "traffic.json"
+        if tf.exists():
+            try:
+                traffic = json.loads(tf.read_text()).get("clip_bwd_np_kernel", {}).get(f"W{W}")
+            except Exception:
+                traffic = None
+        r["roofline"]["traffic"] = traffic
         step_alg = 6.0 * N_GLOBAL * N_GLOBAL * D
         line = {
             "metric": "contrastive_fwd_bwd_pairs_per_s", "value": N_GLOBAL / (ms / 1e3), "unit": "pairs/s",
             "n_gpus": W, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f16",
             "data": "synthetic",
-            "config": {"workload": f"ViT-B/16-width contrastive loss fwd+bwd, global batch {N_GLOBAL}, D={D}, "
-                                   f"{n_loc} rows/rank (BASELINE.json configs[1])",
+            "config": {"workload": workload_string(W),
                        "global_batch": N_GLOBAL, "D": D, "operand_dtype": "fp16 (fp32 accumulate)",
                        "logit_scale": LOGIT_SCALE, "parallelism": f"dp{W}",
                        "l2": "flushed (256 MB write) before every timed step",
-                       "launch": "cuda-graph replay of one captured step" if graphed else "eager",
+                       "launch": "cuda-graph replay of one captured step" if r["graphed"] else "eager",
                        "step_algorithmic_tflop": step_alg / 1e12},
-            "algorithmic_tflops": step_alg / (ms / 1e3) / 1e12 ,
-            "frac_of_bf16_peak_algorithmic": step_alg / (ms / 1e3) / 1e12 / (W * peaks["bf16_tflops_sustained"]),
+            "algorithmic_tflops": step_alg / (ms / 1e3) / 1e12,
+            # the step is timed alone between L2 flushes (milliseconds): the burst peak is its denominator
+            "frac_of_bf16_peak_algorithmic": step_alg / (ms / 1e3) / 1e12 / (W * peaks["bf16_tflops"]),
             "e2e": {"value": N_GLOBAL / (e2e_ms / 1e3), "unit": "pairs/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": 2 * n_loc * D * 4, "d2h_bytes_per_step": 4},
-            "gpu_launches": launches_per_step * args.steps,
-            "gpu_launches_per_step": launches_per_step,
-            "roofline": {"kernel": "clip_bwd_np_kernel", "bound": "tensor", "achieved": bwd_alg / (bwd_ms / 1e3) / 1e12,
-                         "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-                         "frac": bwd_alg / (bwd_ms / 1e3) / 1e12 / peaks["bf16_tflops"], "traffic": traffic,
-                         "launch_ms": bwd_ms, "algorithmic_flops_per_launch": bwd_alg,
-                         "hardware_tflops": 2 * bwd_alg / (bwd_ms / 1e3) / 1e12,
-                         "peak_source": f"{peaks['source']} burst bf16 (kernel timed alone)"},
-            "roofline_fwd": {"kernel": "clip_fwd_kernel", "bound": "tensor", "achieved": fwd_alg / (fwd_ms / 1e3) / 1e12,
-                             "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-                             "frac": fwd_alg / (fwd_ms / 1e3) / 1e12 / peaks["bf16_tflops"], "launch_ms": fwd_ms,
-                             "hardware_tflops": 2 * fwd_alg / (fwd_ms / 1e3) / 1e12},
-            "clocks": clocks,
+            "gpu_launches": r["launches_per_step"] * args.steps,
+            "gpu_launches_per_step": r["launches_per_step"],
+            "roofline": r["roofline"], "roofline_fwd": r["roofline_fwd"],
+            "clocks": r["clocks"],
         }
-        if cpu is not None:
-            line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
-        emit(line)
-    if dist is not None:
-        dist.barrier()
-        dist.destroy_process_group()
-
-
-def bench_retrieval(args):
-    from nans_clip_b200 import kernels as K
-    from nans_clip_b200.retrieval import GalleryShard
-
-    dist, W, rank, local = dist_setup(args.gpus)
-    dev = torch.device("cuda", local)
-    torch.cuda.set_device(dev)
-    peaks = measured_peaks()
-    lo, hi = RET_G * rank // W, RET_G * (rank + 1) // W
-    g = torch.Generator(device=dev).manual_seed(4242 + rank)
-    gal = torch.nn.functional.normalize(torch.randn(hi - lo, D, device=dev, generator=g), dim=-1).bfloat16().float()
-    gq = torch.Generator(device=dev).manual_seed(99)
-    qry = torch.nn.functional.normalize(torch.randn(RET_Q, D, device=dev, generator=gq), dim=-1).bfloat16().float()
-    shard = GalleryShard(gal, dev, torch.float16, lo)
-    q16, _, _ = K.l2norm_cast(qry, torch.float16, normalize=False)
-    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
-    qry_h = qry.cpu().pin_memory()
-
-    def step():
-        s, i = K.topk_ip(q16, shard.g16, qry, shard.g32, RET_K, 16, lo)
-        if W > 1:
-            all_s = torch.empty((W * RET_Q, RET_K), dtype=s.dtype, device=dev)
-            all_i = torch.empty((W * RET_Q, RET_K), dtype=i.dtype, device=dev)
-            dist.all_gather_into_tensor(all_s, s)
-            dist.all_gather_into_tensor(all_i, i)
-            s, i = K.topk_merge(all_s.view(W, RET_Q, RET_K), all_i.view(W, RET_Q, RET_K))
-        return i
-
-    def step_e2e():
-        q = qry_h.to(dev, non_blocking=True)
-        if W > 1:
-            s, i = shard.search(q, RET_K)
-            all_s = torch.empty((W * RET_Q, RET_K), dtype=s.dtype, device=dev)
-            all_i = torch.empty((W * RET_Q, RET_K), dtype=i.dtype, device=dev)
-            dist.all_gather_into_tensor(all_s, s)
-            dist.all_gather_into_tensor(all_i, i)
-            s, i = K.topk_merge(all_s.view(W, RET_Q, RET_K), all_i.view(W, RET_Q, RET_K))
-        else:
-            s, i = shard.search(q, RET_K)
-        return i.cpu()
-
-    sampler = ClockSampler(local)
-    l0 = K.LAUNCHES
-    for _ in range(args.warmup):
-        step()
-    torch.cuda.synchronize()
-    lps = (K.LAUNCHES - l0) // max(args.warmup, 1)
-    sampler.start()
-    ms = timed_steps(step, args.steps, 0, flush, dist, dev) / args.steps
-    clocks = sampler.stop()
-    e2e_ms = timed_steps(step_e2e, max(2, args.steps // 4), 1, flush, dist, dev) / max(2, args.steps // 4)
-    flops = 2.0 * RET_Q * (hi - lo) * D
+        if pc is not None:
+            line["parity_check"] = pc
+            if not pc["ok"]:
+                rc = 3
+    workloads = {}
+    todo = [w for w in WORKLOADS if (args.only == w or (args.only is None and not args.no_secondary))]
+    for name in todo:
+        try:
+            torch.cuda.empty_cache()
+            if name == "retrieval":
+                workloads[name] = bench_retrieval_core(args, dist, W, rank, dev, local, max(4, min(args.steps, 10)))
+            elif name == "loss_d1024":
+                workloads[name] = bench_loss_d1024(args, dist, W, rank, dev, local)
+            elif name == "accum_n65536_d768_a8":
+                workloads[name] = bench_accum(args, dist, W, rank, dev, local)
+            elif name == "l2norm":
+                workloads[name] = bench_l2norm(args, dev, local)
+        except Exception as exc:  # a secondary workload must not take the headline line down
+            import traceback
+            traceback.print_exc()
+            workloads[name] = {"error": repr(exc)}
+            if dist is not None:
+                raise  # ranks would desynchronise: fail loudly instead
     if rank == 0:
-        line = {"metric": "retrieval_queries_per_s", "value": RET_Q / (ms / 1e3), "unit": "queries/s", "n_gpus": W,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-                "scaling": "strong", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
-                "config": {"workload": f"top-{RET_K} text->image retrieval, Q={RET_Q}, G={RET_G}, D={D}, gallery "
-                                       f"sharded x{W} (BASELINE.json configs[4])",
-                           "l2": "flushed (256 MB write) before every timed step", "k_cand": 16,
-                           "operand_dtype": "fp16 candidate pass + fp32 rescoring"},
-                "e2e": {"value": RET_Q / (e2e_ms / 1e3), "unit": "queries/s", "ms_per_step": e2e_ms,
-                        "h2d_bytes_per_step": RET_Q * D * 4, "d2h_bytes_per_step": RET_Q * RET_K * 8},
-                "gpu_launches": lps * args.steps, "gpu_launches_per_step": lps,
-                "roofline": {"kernel": "topk_sweep_kernel+finalize", "bound": "tensor",
-                             "achieved": flops / (ms / 1e3) / 1e12, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-                             "frac": flops / (ms / 1e3) / 1e12 / peaks["bf16_tflops"], "traffic": None,
-                             "peak_source": f"{peaks['source']} burst bf16"},
-                "clocks": clocks}
-        if W == 1 and not args.no_cpu_baseline:
-            cpu = cpu_topk_baseline()
-            line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        if line is None:  # --only <secondary>: that workload's dict is the line
+            name = todo[0]
+            line = {"metric": name, "n_gpus": W, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True,
+                    "scaling": "strong", "vs_baseline": None, "dtype": "f16", "data": "synthetic", **workloads[name]}
+            line.setdefault("value", None)
+            line["config"] = {"workload": workloads[name].get("config", name)}
+        else:
+            if workloads:
+                line["workloads"] = workloads
+            if W == 1 and not args.no_cpu_baseline:
+                cpu = cpu_loss_baseline()
+                line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+                if "retrieval" in workloads and "error" not in workloads["retrieval"]:
+                    workloads["retrieval"]["cpu_baseline"] = cpu_topk_baseline(n_vec=256, n_lit=4)
         emit(line)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+    if rc:
+        sys.exit(rc)
 
 
 _JSON_OUT = None
@@ -488,10 +766,18 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    ap.add_argument("--workload", choices=["loss", "retrieval"], default="loss")
+    ap.add_argument("--only", choices=["loss", *WORKLOADS], default=None,
+                    help="run one workload alone (default: the loss line with every other workload inside it)")
+    ap.add_argument("--workload", choices=["loss", "retrieval"], default=None, help="alias of --only (round-1 flag)")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the `workloads` section")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--contract-test-n", type=int, default=0,
+                    help="tests/test_bench_contract.py only: reference arm at a reduced global batch (the line's "
+                         "config.workload says so); never used by a measurement")
     ap.add_argument("--graph", action="store_true", help="1 GPU only: time a CUDA-graph replay of the step (value only)")
     args = ap.parse_args()
+    if args.workload and not args.only:
+        args.only = args.workload
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference_arm(args)
@@ -499,7 +785,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback "
                          "(use --impl reference for the CPU arm)")
-    (bench_loss if args.workload == "loss" else bench_retrieval)(args)
+    bench_main(args)
 
 
 if __name__ == "__main__":

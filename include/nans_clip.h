@@ -259,6 +259,12 @@ int nans_label_smooth_bwd(float* dI, float* dT, const float* I_rows, const float
 int nans_jsonl_scan(const char* buf, int64_t len, const char* id_key, int64_t* rows, int64_t* D);
 int nans_jsonl_parse(const char* buf, int64_t len, const char* id_key, int64_t rows, int64_t D,
                      int64_t* ids, float* feats, int n_threads);
+/*   nans_jsonl_parse_rows: ids[rows] for every line, feature lists only for the lines
+ *                     [row_begin, row_begin + row_count) into feats[row_count, D]: one rank's gallery
+ *                     shard (the reference parses the whole file on its single GPU's host,
+ *                     make_topk_predictions.py:57-65; a sharded run must not do that W times). */
+int nans_jsonl_parse_rows(const char* buf, int64_t len, const char* id_key, int64_t rows, int64_t D,
+                          int64_t row_begin, int64_t row_count, int64_t* ids, float* feats, int n_threads);
 
 /* ---- (4) top-k inner-product retrieval ---------------------------------------------------- */
 /*

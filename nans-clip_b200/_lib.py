@@ -71,6 +71,8 @@ _SIGNATURES = {
                                       c_void_p, c_void_p, c_void_p, c_float, c_float, c_void_p]),
     "nans_jsonl_scan": (c_int, [c_void_p, c_int64, c_char_p, c_void_p, c_void_p]),
     "nans_jsonl_parse": (c_int, [c_void_p, c_int64, c_char_p, c_int64, c_int64, c_void_p, c_void_p, c_int]),
+    "nans_jsonl_parse_rows": (c_int, [c_void_p, c_int64, c_char_p, c_int64, c_int64, c_int64, c_int64, c_void_p,
+                                      c_void_p, c_int]),
     "nans_topk_ip_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64, c_int]),
     "nans_topk_ip": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int64, c_int64,
                              c_int64, c_int, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_size_t,

@@ -69,6 +69,10 @@ int parse_line(const char* p, const char* e, const char* id_key, size_t id_klen,
     const char* a = skip_ws(ri.ptr, e);
     if (a >= e || (*a != ',' && *a != '}')) return 10;
   }
+  if (cap < 0) {  // id only (rows outside this rank's gallery shard)
+    *nvals = -1;
+    return 0;
+  }
   const char* f = find_key(p, e, "feature", 7);
   if (!f) return 3;
   f = skip_ws(f, e);
@@ -152,7 +156,17 @@ extern "C" int nans_jsonl_scan(const char* buf, int64_t len, const char* id_key,
 // (the caller falls back to a general JSON parser).  n_threads <= 0: hardware concurrency.
 extern "C" int nans_jsonl_parse(const char* buf, int64_t len, const char* id_key, int64_t rows, int64_t D,
                                 int64_t* ids, float* feats, int n_threads) {
-  if (!buf || len < 0 || !id_key || rows < 0 || D < 0 || (rows > 0 && (!ids || (D > 0 && !feats)))) {
+  return nans_jsonl_parse_rows(buf, len, id_key, rows, D, 0, rows, ids, feats, n_threads);
+}
+
+// The same, with the feature lists parsed only for lines [row_begin, row_begin + row_count) — one rank's
+// gallery shard — into feats[row_count, D]; ids[rows] still covers every line (rank 0 writes the ids of
+// all shards).  The other lines cost a quote scan and one integer.
+extern "C" int nans_jsonl_parse_rows(const char* buf, int64_t len, const char* id_key, int64_t rows, int64_t D,
+                                     int64_t row_begin, int64_t row_count, int64_t* ids, float* feats,
+                                     int n_threads) {
+  if (!buf || len < 0 || !id_key || rows < 0 || D < 0 || row_begin < 0 || row_count < 0 ||
+      row_begin + row_count > rows || (rows > 0 && !ids) || (row_count > 0 && D > 0 && !feats)) {
     set_error("jsonl_parse: bad arguments");
     return NANS_ERR_ARG;
   }
@@ -182,9 +196,10 @@ extern "C" int nans_jsonl_parse(const char* buf, int64_t len, const char* id_key
     const int64_t lo = rows * t / nt, hi = rows * (t + 1) / nt;
     for (int64_t r = lo; r < hi; ++r) {
       int64_t nv = 0;
+      const bool mine = r >= row_begin && r < row_begin + row_count;
       const int rc = parse_line(lines[static_cast<size_t>(r)].first, lines[static_cast<size_t>(r)].second, id_key, klen,
-                                ids + r, feats + r * D, D, &nv);
-      if (rc != 0 || nv != D) {
+                                ids + r, mine ? feats + (r - row_begin) * D : nullptr, mine ? D : -1, &nv);
+      if (rc != 0 || (mine && nv != D)) {
         bad[static_cast<size_t>(t)] = r;
         code[static_cast<size_t>(t)] = rc != 0 ? rc : 8;
         return;

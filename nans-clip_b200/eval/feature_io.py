@@ -223,9 +223,11 @@ def _load_jsonl_python(path: str, id_key: str):
     return ids, arr
 
 
-def _load_jsonl_native(path: str, id_key: str, n_threads: int = 0):
+def _load_jsonl_native(path: str, id_key: str, n_threads: int = 0, shard: tuple[int, int] | None = None):
     """The same parse in C++ (csrc/jsonl.cu: correctly rounded std::from_chars, lines in parallel):
-    bit-identical arrays, ~10x faster per core.  Raises on anything but {"<id_key>": int, "feature": [...]}."""
+    bit-identical arrays, ~10x faster per core.  Raises on anything but {"<id_key>": int, "feature": [...]}.
+    `shard` = (rank, world): ids of every line, feature rows only of this rank's contiguous share
+    [rows * rank // world, rows * (rank + 1) // world)."""
     import ctypes
     from .. import _lib
     lib = _lib.load()
@@ -236,31 +238,47 @@ def _load_jsonl_native(path: str, id_key: str, n_threads: int = 0):
     rows, D = ctypes.c_int64(0), ctypes.c_int64(0)
     key = id_key.encode("utf-8")
     _lib.check(lib.nans_jsonl_scan(buf.ctypes.data, size, key, ctypes.byref(rows), ctypes.byref(D)))
-    ids = np.empty((rows.value,), dtype=np.int64)
-    feats = np.empty((rows.value, D.value), dtype=np.float32)
-    _lib.check(lib.nans_jsonl_parse(buf.ctypes.data, size, key, rows.value, D.value, ids.ctypes.data,
-                                    feats.ctypes.data, int(n_threads)))
+    n = rows.value
+    lo, hi = (0, n) if shard is None else (n * shard[0] // shard[1], n * (shard[0] + 1) // shard[1])
+    ids = np.empty((n,), dtype=np.int64)
+    feats = np.empty((hi - lo, D.value), dtype=np.float32)
+    _lib.check(lib.nans_jsonl_parse_rows(buf.ctypes.data, size, key, n, D.value, lo, hi - lo, ids.ctypes.data,
+                                         feats.ctypes.data, int(n_threads)))
     return ids.tolist(), feats
 
 
-def load_jsonl_features(path: str, id_key: str):
+def load_jsonl_features(path: str, id_key: str, shard: tuple[int, int] | None = None):
     """{"<id_key>": int, "feature": [floats]} per line -> (ids list, float32 [n, D] array); the
     parsing of make_topk_predictions.py:57-65.  Native parser first; anything it does not accept
-    (non-integer ids, ragged rows, other JSON) goes through json.loads exactly like the reference."""
+    (non-integer ids, ragged rows, other JSON) goes through json.loads exactly like the reference.
+    With `shard` = (rank, world) the array holds only this rank's contiguous share of the rows (the ids
+    still cover the whole file)."""
     if os.environ.get("NANS_JSONL_PYTHON", "0") != "1":
         try:
-            return _load_jsonl_native(path, id_key)
+            return _load_jsonl_native(path, id_key, shard=shard)
         except Exception:
             pass
-    return _load_jsonl_python(path, id_key)
+    ids, arr = _load_jsonl_python(path, id_key)
+    if shard is not None:
+        n = len(ids)
+        arr = arr[n * shard[0] // shard[1]: n * (shard[0] + 1) // shard[1]]
+    return ids, arr
 
 
-def load_features(path: str, id_key: str):
-    """JSONL or binary shard -> (ids, feat32 [n, D], feat16 bit patterns | None, dtype16 code)."""
+def load_features(path: str, id_key: str, shard: tuple[int, int] | None = None):
+    """JSONL or binary shard -> (ids, feat32 [n, D], feat16 bit patterns | None, dtype16 code).
+    `shard` = (rank, world): feat32 / feat16 hold only the rows [n * rank // world, n * (rank + 1) // world)
+    (a binary shard is memory-mapped, so only that slice is ever read; a JSONL file has only that
+    slice's feature lists parsed)."""
     if is_shard(path):
         ids, f32, f16, h = read_shard(path)
+        if shard is not None:
+            n = len(ids)
+            lo, hi = n * shard[0] // shard[1], n * (shard[0] + 1) // shard[1]
+            f32 = f32[lo:hi]
+            f16 = f16[lo:hi] if f16 is not None else None
         return ids, f32, f16, h["dtype16"]
-    ids, f32 = load_jsonl_features(path, id_key)
+    ids, f32 = load_jsonl_features(path, id_key, shard)
     return ids, f32, None, DT16_NONE
 
 

@@ -69,7 +69,8 @@ def run(args, query_key=QUERY_KEY, query_path=None, gallery_key=GALLERY_KEY, gal
         group = dist.group.WORLD
 
     log(f"Begin to load {GALLERY_NAME if gallery_key == GALLERY_KEY else 'gallery'} features...")
-    gallery_ids, gallery, gallery16, g16_code = load_features(gallery_path, gallery_key)
+    # every rank reads the ids of the whole gallery but only ITS contiguous share of the feature rows
+    gallery_ids, gallery, gallery16, g16_code = load_features(gallery_path, gallery_key, shard=(rank, world))
     log("Finished loading features.")
     G = len(gallery_ids)
     lo, hi = (G * rank) // world, (G * (rank + 1)) // world
@@ -77,16 +78,19 @@ def run(args, query_key=QUERY_KEY, query_path=None, gallery_key=GALLERY_KEY, gal
     queries = np.array(queries, dtype=np.float32)
     k = min(args.top_k, 32)
     if args.top_k > 32:
+        # the kernel's per-thread candidate list holds at most 32 entries (INTEGRATION.md "Limits");
+        # evaluation.py consumes exactly 10 (evaluation.py:15-58) and the reference's default is 10
         raise ValueError("--top-k above 32 is not supported by the fused kernel")
     feat_dtype = torch.float16 if args.feat_dtype == "fp16" else torch.bfloat16
 
     log(f"Begin to compute top-{args.top_k} predictions...")
     positions = []
     qb = max(int(args.eval_batch_size), 1)
-    shard = torch.from_numpy(np.array(gallery[lo:hi], dtype=np.float32))  # a writable copy of the mmap slice
+    shard = torch.from_numpy(np.array(gallery, dtype=np.float32))  # a writable copy of the (mmap) slice
+    assert shard.shape[0] == hi - lo
     shard16 = None
     if gallery16 is not None and g16_code == (DT16_F16 if feat_dtype == torch.float16 else DT16_BF16):
-        shard16 = torch.from_numpy(np.array(gallery16[lo:hi]).view(np.int16)).view(feat_dtype)
+        shard16 = torch.from_numpy(np.array(gallery16).view(np.int16)).view(feat_dtype)
     if queries.shape[0] > 0 and G > 0:
         if group is None:
             from ..retrieval import GalleryShard

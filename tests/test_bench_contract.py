@@ -12,8 +12,8 @@ ROOT = Path(__file__).resolve().parent.parent
 def _run(extra_env, *args):
     env = dict(os.environ)
     env.update(extra_env)
-    r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
-                        *args], capture_output=True, text=True, env=env, timeout=600, cwd=str(ROOT))
+    r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1",
+                        "--contract-test-n", "2048", "--no-secondary", *args], capture_output=True, text=True, env=env, timeout=600, cwd=str(ROOT))
     assert r.returncode == 0, r.stderr[-2000:]
     return r.stdout
 
@@ -31,7 +31,17 @@ def test_reference_arm_prints_one_contract_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0))
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
-    assert "workload" in d["config"]
+    assert "workload" in d["config"] and d["steps"] == 2 and d["config"]["global_batch"] == 2048
+    # measured, not extrapolated: ms_per_step x steps is time this process really spent
+    assert d["ms_per_step"] * d["steps"] / 1e3 < 120
+
+
+def test_both_arms_print_the_same_workload_string():
+    sys.path.insert(0, str(ROOT))
+    import importlib
+    bench = importlib.import_module("bench")
+    for W in (1, 2, 4, 8):
+        assert f"{32768 // W} rows/rank" in bench.workload_string(W) and "configs[1]" in bench.workload_string(W)
 
 
 def test_reference_arm_other_ranks_are_silent():

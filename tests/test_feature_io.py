@@ -163,3 +163,40 @@ def test_native_jsonl_parser_falls_back(tmp_path):
     _write(e, [])
     ids, f = fio.load_jsonl_features(str(e), "image_id")
     assert ids == [] and f.shape[0] == 0
+
+
+def test_sharded_jsonl_load_parses_only_the_rank_rows(tmp_path):
+    """load_features(shard=(rank, world)): ids of the whole file, feature rows of the rank's contiguous
+    share only (what a torchrun'd make_topk_predictions does per rank), native and json.loads paths."""
+    rng = np.random.default_rng(5)
+    n, d, W = 103, 24, 4
+    f32 = rng.standard_normal((n, d)).astype(np.float32)
+    ids = rng.integers(0, 10 ** 9, n).tolist()
+    p = tmp_path / "g.jsonl"
+    _write(p, [json.dumps({"image_id": i, "feature": r.tolist()}) + "\n" for i, r in zip(ids, f32)])
+    for native in (True, False):
+        got_rows = []
+        for r in range(W):
+            if native:
+                a_ids, a = fio._load_jsonl_native(str(p), "image_id", shard=(r, W))
+            else:
+                os.environ["NANS_JSONL_PYTHON"] = "1"
+                try:
+                    a_ids, a, _, _ = fio.load_features(str(p), "image_id", shard=(r, W))
+                finally:
+                    del os.environ["NANS_JSONL_PYTHON"]
+            assert a_ids == ids and a.shape == (n * (r + 1) // W - n * r // W, d)
+            got_rows.append(a)
+        assert np.array_equal(np.concatenate(got_rows), f32)
+    s = tmp_path / "g.nansf"
+    fio.jsonl_to_shard(str(p), "image_id", str(s))
+    parts = [np.array(fio.load_features(str(s), "image_id", shard=(r, W))[1]) for r in range(W)]
+    assert np.array_equal(np.concatenate(parts), f32)
+    # a malformed feature list outside the rank's rows does not concern that rank; inside it does
+    bad = tmp_path / "bad.jsonl"
+    lines = [json.dumps({"image_id": i, "feature": r.tolist()}) + "\n" for i, r in zip(ids, f32)]
+    lines[1] = '{"image_id": 5, "feature": [oops]}\n'
+    _write(bad, lines)
+    fio._load_jsonl_native(str(bad), "image_id", shard=(3, W))
+    with pytest.raises(Exception):
+        fio._load_jsonl_native(str(bad), "image_id", shard=(0, W))

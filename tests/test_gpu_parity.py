@@ -804,6 +804,48 @@ def test_topk_vs_oracle(dev, Q, G, D, k, kc):
     check_topk(i - 1000000, s.cpu(), gal, qry, k)
 
 
+@pytest.mark.parametrize("G", [5000, 200000])
+def test_topk_ascending_score_gallery(dev, G):
+    """Worst case of the threshold-gated candidate lists: a gallery whose scores rise along the sweep for
+    EVERY query (rows ordered by their component along the queries' common direction), so that new
+    columns keep beating the running k-th best; with and without the floor pass (G >= 49152)."""
+    from nans_clip_b200 import kernels as K
+    D, Q, k = 256, 300, 10
+    g = torch.Generator().manual_seed(G)
+    u = torch.nn.functional.normalize(torch.randn(D, generator=g), dim=0)
+    t = torch.linspace(0.0, 0.9, G)[:, None]
+    gal = torch.nn.functional.normalize(t * u[None, :] + 0.05 * torch.nn.functional.normalize(torch.randn(G, D, generator=g), dim=-1), dim=-1)
+    gal = gal.half().float()
+    qry = torch.nn.functional.normalize(u[None, :] + 0.02 * torch.randn(Q, D, generator=g), dim=-1).half().float()
+    sc = qry @ gal.t()
+    assert float((sc[:, 1:] > sc[:, :-1]).float().mean()) > 0.5   # rising (noisy) along the sweep
+    s, i = K.topk_ip(qry.half().to(dev), gal.half().to(dev), qry.to(dev), gal.to(dev), k, 16, 0)
+    check_topk(i.cpu(), s.cpu(), gal, qry, k)
+    assert bool((i >= G - 5000).all())   # the winners sit at the end of the sweep
+
+
+def test_topk_nan_rows_still_emit_valid_ids(dev):
+    """A zero-norm feature row normalised to NaN (extract_features.py divides by the norm): the reference
+    always writes k valid ids; an all-NaN query leaves its stable sort in gallery order
+    (make_topk_predictions.py:84).  The kernel must not leave output slots unwritten."""
+    from nans_clip_b200 import kernels as K
+    g = torch.Generator().manual_seed(3)
+    gal = torch.nn.functional.normalize(torch.randn(500, 64, generator=g), dim=-1).half().float()
+    qry = torch.nn.functional.normalize(torch.randn(6, 64, generator=g), dim=-1).half().float()
+    qry[2] = float("nan")
+    gal[17] = float("nan")
+    s, i = K.topk_ip(qry.half().to(dev), gal.half().to(dev), qry.to(dev), gal.to(dev), 10, 16, 7000)
+    i, s = i.cpu(), s.cpu()
+    assert i[2].tolist() == list(range(7000, 7010))          # all-NaN query: gallery order
+    assert bool(((i >= 7000) & (i < 7500)).all())
+    assert all(len(set(r)) == 10 for r in i.tolist())
+    ok = [r for r in range(6) if r != 2]
+    clean = gal.clone()
+    clean[17] = 0                                            # the NaN row can never be a candidate
+    rs, ri = torch.sort(qry[ok] @ clean.t(), dim=1, descending=True, stable=True)
+    assert torch.equal(i[ok] - 7000, ri[:, :10])
+
+
 def test_topk_exact_ties_keep_gallery_order(dev):
     from nans_clip_b200 import kernels as K
     g = torch.Generator().manual_seed(1)
