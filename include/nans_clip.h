@@ -224,6 +224,95 @@ int nans_clip_loss_bwd_minmax(const void* I_loc, const void* T_loc, int64_t ld_l
 int nans_clip_loss_exchange_finish(const float* gathered, int64_t world, int64_t n_loc, int64_t pad,
                                    float* lse_all, int64_t ld, float* out, int* lse_minmax, void* stream);
 
+/* ---- (2x/3x) multi-GPU exchange over NVLink peer memory --------------------------------------- */
+/*
+ * Replaces the collectives of cn_clip/training/train.py:53-84 (two feature all-gathers per get_loss call)
+ * and the lse / scalar exchange of this library's own multi-rank path with a PUSH data plane: the cast
+ * kernel of rank r writes every 16-bit row block straight into the gathered buffers of all peers (plain
+ * st.global on peer-mapped memory, NVLink / NVSwitch), then raises a per-64-row flag there; the forward's
+ * TMA producer polls the flag of a tile just before loading it, so remote tiles are consumed as they
+ * land and no collective kernel sits between the cast and the backward.  The per-rank log-sum-exps and
+ * partial scalars travel the same way.  Everything is plain kernels on the caller's stream: capturable
+ * in a CUDA graph (the step counter lives in device memory), no NCCL, no host synchronisation.
+ *
+ * Memory: every rank allocates ONE exchange buffer with nans_peer_alloc (cudaMalloc + a 64-byte CUDA IPC
+ * handle), the host exchanges the handles (any transport: torch.distributed, MPI, a file), and every
+ * rank maps its peers' buffers with nans_peer_open.  nans_xchg_t then describes the job: the buffers as
+ * mapped in THIS process and the layout inside them (identical on all ranks; sizes from
+ * nans_xchg_layout).  Features are double-buffered by step parity: a rank can be one forward ahead of a
+ * peer that is still in the previous step's backward without overwriting what that peer reads.
+ *
+ * Requirements: n_loc a multiple of 256 (whole column tiles per rank), world <= NANS_MAX_PEERS, all
+ * ranks on one NVLink domain with peer access; one process per GPU (kernels of different ranks wait on
+ * each other's flags: never run two ranks of one job on the same GPU concurrently).
+ */
+#define NANS_MAX_PEERS 16
+#define NANS_XCHG_FLAG_ROWS 64 /* rows per arrival flag */
+
+typedef struct {
+  int32_t world, rank;
+  void* base[NANS_MAX_PEERS]; /* base[r]: rank r's exchange buffer as mapped here (base[rank] = own)  */
+  int64_t n_loc, D;           /* rows per rank, feature width (elements) of the CURRENT layout         */
+  int64_t feat_off;           /* 16-bit [2 modalities: 0 image, 1 text][2 slots][world * n_loc][D]      */
+  int64_t lse_off;            /* fp32   [2 slots][world][lse_len]    lse_len = 2 * pad4(n_loc) + 8      */
+  int64_t lse_len;
+  int64_t fflag_off;          /* uint32 [2 modalities][world][n_loc / 64]   value = step of arrival     */
+  int64_t lflag_off;          /* uint32 [world]                                                        */
+  int64_t bytes;              /* total bytes the layout needs                                          */
+  uint32_t* epoch;            /* LOCAL device word (not peer-mapped): completed forward exchanges      */
+} nans_xchg_t;
+
+/* cudaMalloc `bytes` (zero-filled) on the current device and export it: handle64 receives the 64-byte
+ * cudaIpcMemHandle_t.  nans_peer_free releases it. */
+int nans_peer_alloc(size_t bytes, void** ptr, void* handle64);
+int nans_peer_free(void* ptr);
+/* Map a peer's buffer from its handle (peer access is enabled lazily); nans_peer_close unmaps. */
+int nans_peer_open(const void* handle64, void** ptr);
+int nans_peer_close(void* ptr);
+/* Zero `bytes` of a buffer on `stream` (a new layout moves the flag words: stale bytes must not read as
+ * "arrived").  The caller brackets it with its own cross-rank barriers. */
+int nans_peer_zero(void* ptr, size_t bytes, void* stream);
+/* Fills the layout fields (n_loc, D, *_off, lse_len, bytes) of `x` for a job of x->world ranks. */
+int nans_xchg_layout(nans_xchg_t* x, int64_t n_loc, int64_t D);
+
+/* Kernel (1) fused with the feature exchange: casts (optionally L2-normalises) this rank's image and
+ * text rows to the 16-bit operand type, keeps a local copy (I16_loc / T16_loc, [n_loc, D] contiguous:
+ * the row operand of the strips) and pushes the rows into slot (step & 1) of every rank's gathered
+ * buffers, peers in the order rank-1, rank-2, ... so that each destination is served by one source at a
+ * time; then flags them.  img / txt: [n_loc, D] of x_dtype (NANS_F32/F16/BF16), row pitch ld_x. */
+int nans_xchg_cast_push(const nans_xchg_t* x, const void* img, const void* txt, int x_dtype, int64_t ld_x,
+                        int feat_dtype, int normalize, void* I16_loc, void* T16_loc, void* stream);
+
+/* Kernel (2) over the gathered buffers: both strips of this rank against all world * n_loc columns in
+ * ONE launch.  Every unit walks the column tiles source by source starting with its own rank's (local,
+ * already there) and waits for a tile's flags right before its TMA loads.  Fills workspace slots
+ * [0, nans_clip_loss_fwd_xchg_slots(...)); finish with nans_clip_loss_fwd_finalize_push. */
+int64_t nans_clip_loss_fwd_xchg_slots(int64_t n_loc, int64_t world, int64_t D);
+int nans_clip_loss_fwd_xchg(const nans_xchg_t* x, const void* I16_loc, const void* T16_loc, int feat_dtype,
+                            const float* s_dev, int flags, void* ws, size_t ws_bytes, void* stream);
+
+/* nans_clip_loss_fwd_finalize for this rank's rows (label_begin = rank * n_loc) that also PUSHES the packed
+ * result [lse_img (pad) | lse_txt (pad) | scalars[8]] into slot (step & 1), row `rank`, of every rank's
+ * lse table and flags it.  lse_*_loc / scalars: the local copies, as in nans_clip_loss_fwd_finalize. */
+int nans_clip_loss_fwd_finalize_push(const nans_xchg_t* x, int64_t total_slots, const float* s_dev, int flags,
+                                     void* ws, size_t ws_bytes, float* lse_img_loc, float* lse_txt_loc,
+                                     float* scalars, void* stream);
+
+/* nans_clip_loss_exchange_finish on the pushed table: waits (on the device) until every rank's packed
+ * row of this step has arrived, then writes lse_all / out / lse_minmax exactly like
+ * nans_clip_loss_exchange_finish, stores the step number in step_out[0] (a device word owned by this
+ * call: the backward finds its slot through it) and publishes the step in x->epoch. */
+int nans_clip_loss_exchange_finish_xchg(const nans_xchg_t* x, float* lse_all, int64_t ld, float* out,
+                                        int* lse_minmax, uint32_t* step_out, void* stream);
+
+/* nans_clip_loss_bwd_minmax with the column operands taken from the gathered buffers of the step
+ * recorded in step_dev (the word nans_clip_loss_exchange_finish_xchg wrote).  D <= 1024. */
+int nans_clip_loss_bwd_xchg(const nans_xchg_t* x, const uint32_t* step_dev, const void* I16_loc,
+                            const void* T16_loc, int feat_dtype, const float* s_dev, const float* lse_img_all,
+                            const float* lse_txt_all, const int* lse_minmax, const float* grad_out_dev,
+                            float grad_mult, int64_t grad_row_begin, int64_t grad_row_count, void* dI_loc,
+                            void* dT_loc, int out_dtype, void* ws, size_t ws_bytes, void* stream);
+
 /* ---- (3b) label-smoothed variant ---------------------------------------------------------- */
 /*
  * Replaces the fork's train_lora.py:95-110 (`contrastive_loss`: F.cross_entropy(logits, arange,

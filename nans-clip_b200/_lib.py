@@ -66,6 +66,24 @@ _SIGNATURES = {
                                           c_void_p, c_size_t, c_void_p]),
     "nans_clip_loss_exchange_finish": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_void_p,
                                                c_void_p, c_void_p]),
+    "nans_peer_alloc": (c_int, [c_size_t, c_void_p, c_void_p]),
+    "nans_peer_free": (c_int, [c_void_p]),
+    "nans_peer_open": (c_int, [c_void_p, c_void_p]),
+    "nans_peer_close": (c_int, [c_void_p]),
+    "nans_peer_zero": (c_int, [c_void_p, c_size_t, c_void_p]),
+    "nans_xchg_layout": (c_int, [c_void_p, c_int64, c_int64]),
+    "nans_xchg_cast_push": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_void_p, c_void_p,
+                                    c_void_p]),
+    "nans_clip_loss_fwd_xchg_slots": (c_int64, [c_int64, c_int64, c_int64]),
+    "nans_clip_loss_fwd_xchg": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_size_t,
+                                        c_void_p]),
+    "nans_clip_loss_fwd_finalize_push": (c_int, [c_void_p, c_int64, c_void_p, c_int, c_void_p, c_size_t, c_void_p,
+                                                 c_void_p, c_void_p, c_void_p]),
+    "nans_clip_loss_exchange_finish_xchg": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p,
+                                                    c_void_p]),
+    "nans_clip_loss_bwd_xchg": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
+                                        c_void_p, c_void_p, c_float, c_int64, c_int64, c_void_p, c_void_p, c_int,
+                                        c_void_p, c_size_t, c_void_p]),
     "nans_label_smooth_stats": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p]),
     "nans_label_smooth_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64,
                                       c_void_p, c_void_p, c_void_p, c_float, c_float, c_void_p]),

@@ -20,7 +20,7 @@ LIBDIR = PKG / "lib"
 OBJDIR = PKG / "lib" / "obj"
 LIB = LIBDIR / "libnans_clip.so"
 
-SOURCES = ["api.cu", "jsonl.cu", "l2norm.cu", "smooth.cu", "strip_fwd.cu", "strip_bwd.cu", "topk.cu"]
+SOURCES = ["api.cu", "exchange.cu", "jsonl.cu", "l2norm.cu", "smooth.cu", "strip_fwd.cu", "strip_bwd.cu", "topk.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -41,7 +41,13 @@ struct BwdParams {
   int npairs;
   int npp_units, npp_t1;    // persistent kernel, helper mode (npp_t1 > 0): pairs [0, npp_units) sweep tiles [0, npp_t1) of
                             // their own unit, the remaining pairs share the tiles [npp_t1, ntiles) of all units
+  // exchange mode (nans_clip_loss_bwd_xchg): the column operands are the double-buffered gathered tensors
+  // [2 slots * ncols, D]; column tile coordinates are shifted by (*col_step & 1) * ncols rows.  Narrow kernels only.
+  const uint32_t* col_step;
 };
+__device__ __forceinline__ int col_slot_offset(const BwdParams& p) {
+  return p.col_step != nullptr ? static_cast<int>(*p.col_step & 1u) * p.ncols : 0;
+}
 
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d)

@@ -230,9 +230,10 @@ clip_bwd_np_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
     }
     int sr = 0;
     uint32_t pr = 0;
+    const int coff = col_slot_offset(p);  // exchange mode: this step's slot of the gathered tensors
     for (int tau = 0; tau <= ntiles; ++tau) {
       if (tau < ntiles) {
-        const int col0 = (tile_begin + tau) * TK + static_cast<int>(rank) * (TK / 2);
+        const int col0 = (tile_begin + tau) * TK + static_cast<int>(rank) * (TK / 2) + coff;
         for (int j = 0; j < n1; ++j) {
           const int nck = min(CPS, p.kchunks - CPS * j);
           mbar_wait_parked(&emptyR[sr], pr ^ 1u);
@@ -249,7 +250,7 @@ clip_bwd_np_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
         }
       }
       if (tau >= 1) {
-        const int col0 = (tile_begin + tau - 1) * TK;
+        const int col0 = (tile_begin + tau - 1) * TK + coff;
         for (int kh = 0; kh < KH; ++kh) {
           for (int fb = 0; fb < nfb; ++fb) {
             mbar_wait_parked(&emptyR[sr], pr ^ 1u);
@@ -609,6 +610,7 @@ clip_bwd_npp_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
   if (warp == 0) {
     int sr = 0;
     uint32_t pr = 0;
+    const int coff = col_slot_offset(p);  // exchange mode: this step's slot of the gathered tensors
     NppCursor cur = npp_begin(g0, nt, p, tile_lo, tile_hi), prv = cur;
     for (long long tau = 0; tau <= nt; ++tau) {
       if (tau < nt) {
@@ -625,7 +627,7 @@ clip_bwd_npp_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
           }
           __syncwarp();
         }
-        const int col0 = cur.tile * NP_KT + static_cast<int>(rank) * (NP_KT / 2);
+        const int col0 = cur.tile * NP_KT + static_cast<int>(rank) * (NP_KT / 2) + coff;
         for (int j = 0; j < n1; ++j) {
           const int nck = min(2, p.kchunks - 2 * j);
           mbar_wait_parked(&emptyR[sr], pr ^ 1u);
@@ -641,7 +643,7 @@ clip_bwd_npp_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
       }
       if (tau >= 1) {
         const CUtensorMap* tmBm = prv.strip == 0 ? &tmBm0 : &tmBm1;
-        const int col0 = prv.tile * NP_KT;
+        const int col0 = prv.tile * NP_KT + coff;
         for (int kh = 0; kh < 2; ++kh) {
           for (int fb = 0; fb < nfb; ++fb) {
             mbar_wait_parked(&emptyR[sr], pr ^ 1u);

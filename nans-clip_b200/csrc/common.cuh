@@ -138,6 +138,32 @@ __device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity)
   }
 }
 
+// ---- cross-GPU flags (peer-mapped memory over NVLink; exchange.cu, strip_fwd.cu) ---------------------
+// A producer GPU writes payload with plain stores, fences at system scope and then raises a flag word
+// in the consumer's memory; the consumer polls the flag with an acquire load at system scope.  When
+// the payload is then read through the async proxy (TMA), a proxy fence orders the two.
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_global() {
+  asm volatile("fence.proxy.async.global;" ::: "memory");
+}
+// Wait until *flag >= step (steps only grow; a wrap would take 2^31 forwards).  Bounded like mbar_wait:
+// a peer that never arrives ends in a trap (a reported launch failure), not in a hung GPU.
+__device__ __forceinline__ void wait_flag_sys(const uint32_t* flag, uint32_t step) {
+  if (static_cast<int32_t>(ld_acquire_sys(flag) - step) >= 0) return;
+  const long long t0 = clock64();
+  while (static_cast<int32_t>(ld_acquire_sys(flag) - step) < 0) {
+    __nanosleep(64);
+    if (clock64() - t0 > 20000000000ll) __trap();  // ~10 s of SM clocks
+  }
+}
+
 // ---- TMA -------------------------------------------------------------------------------------
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tmap) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");

@@ -1,0 +1,257 @@
+// exchange.cu — the multi-GPU data plane of the loss path: peer-mapped exchange buffers (CUDA IPC) and
+// kernel (1) fused with the feature exchange.
+//
+// Replaces the two feature all-gathers of cn_clip/training/train.py:53-84 (torch.distributed
+// all_gather of image_features / text_features in every get_loss call).  Instead of a collective that
+// sits between the cast and the forward, the cast kernel itself stores every 16-bit row into the
+// gathered buffers of all ranks (its own through local memory, the peers' through NVLink: plain
+// 16-byte st.global on peer-mapped addresses) and raises one arrival flag per 64 rows; the forward
+// (strip_fwd.cu, exchange mode of strip_sweep.cuh) polls a tile's flags right before its TMA loads.
+//
+// Order of the pushes: source r serves destination r-1 first, then r-2, ... while destination d
+// consumes its sources in the order d, d+1, d+2, ...: at any moment every destination is written by one
+// source and every source writes one destination, and tiles arrive in the order they are consumed.
+//
+// Roofline: NVLink.  Bytes that must cross the link per rank and step: 2 modalities x (world - 1) x
+// n_loc x D x 2 B (56 MiB at world 8, n_loc 4096, D 512: 76 us at the measured 770 GB/s per direction),
+// hidden behind the forward, which needs 2 x that time for the same columns.
+#include <string.h>
+
+#include "common.cuh"
+
+namespace nans {
+namespace {
+
+constexpr int PUSH_ROWS = NANS_XCHG_FLAG_ROWS;  // rows per CTA = rows per arrival flag
+constexpr int PUSH_THREADS = 256;
+
+struct PushParams {
+  const void* src[2];   // image, text rows of this rank
+  void* loc16[2];       // local 16-bit copies [n_loc, D]
+  int x_dtype, feat_dtype, normalize;
+  int n_loc, D;
+  long long ld_x;
+  int world, rank;
+  long long feat_off, fflag_off;
+  long long slot_rows;  // world * n_loc
+  const uint32_t* epoch;
+  uint8_t* base[NANS_MAX_PEERS];
+};
+
+__device__ __forceinline__ void load8(const void* row, int x_dtype, int e0, float (&f)[8]) {
+  if (x_dtype == NANS_F32) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(static_cast<const float*>(row) + e0));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(static_cast<const float*>(row) + e0 + 4));
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w;
+    f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+  } else {
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(row) + e0));
+    if (x_dtype == NANS_F16) {
+      const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 t = __half22float2(h[i]);
+        f[2 * i] = t.x; f[2 * i + 1] = t.y;
+      }
+    } else {
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 t = __bfloat1622float2(h[i]);
+        f[2 * i] = t.x; f[2 * i + 1] = t.y;
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ uint4 pack8(const float (&f)[8], int feat_dtype) {
+  uint32_t w[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (feat_dtype == NANS_BF16) {
+      const __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+      w[i] = *reinterpret_cast<const uint32_t*>(&h);
+    } else {
+      const __half2 h = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+      w[i] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+  }
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// grid = (n_loc / 64, 2 modalities); a CTA owns the 64 rows of one arrival flag: 8 warps x 8 rows, a
+// warp moves a row in 16-byte pieces (lane = piece).  Destinations are visited in the order rank,
+// rank - 1, rank - 2, ...; the CTA raises the flag of a destination as soon as ITS 64 rows are there.
+__global__ void __launch_bounds__(PUSH_THREADS) cast_push_kernel(const PushParams p) {
+  const int mod = blockIdx.y;
+  const int blk = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t step = *p.epoch + 1u;
+  const long long slot = step & 1u;
+  const int D = p.D;
+  const int esz = p.x_dtype == NANS_F32 ? 4 : 2;
+  // byte offset of this modality's slot, then of global row (rank * n_loc + r) in it
+  const long long mod_off = p.feat_off + (static_cast<long long>(mod) * 2 + slot) * p.slot_rows * D * 2;
+
+  for (int k = 0; k < p.world; ++k) {
+    int dst = p.rank - k;
+    if (dst < 0) dst += p.world;
+    uint8_t* dbase = p.base[dst] + mod_off;
+    for (int i = 0; i < PUSH_ROWS / (PUSH_THREADS / 32); ++i) {
+      const int r = blk * PUSH_ROWS + i * (PUSH_THREADS / 32) + warp;
+      const uint8_t* srow = static_cast<const uint8_t*>(p.src[mod]) + static_cast<long long>(r) * p.ld_x * esz;
+      float inv = 1.0f;
+      if (p.normalize) {
+        float ss = 0.f;
+        for (int e0 = lane * 8; e0 < D; e0 += 256) {
+          float f[8];
+          load8(srow, p.x_dtype, e0, f);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) ss = fmaf(f[e], f[e], ss);
+        }
+        inv = 1.0f / sqrtf(warp_sum(ss));  // same arithmetic as l2norm_cast_kernel
+      }
+      uint8_t* drow = dbase + (static_cast<long long>(p.rank) * p.n_loc + r) * D * 2;
+      uint8_t* lrow = static_cast<uint8_t*>(p.loc16[mod]) + static_cast<long long>(r) * D * 2;
+      for (int e0 = lane * 8; e0 < D; e0 += 256) {
+        // the source row is re-read per destination: after the first pass it sits in L1/L2, and holding
+        // a whole 64-row block in registers across the destination loop would cap D
+        float f[8];
+        load8(srow, p.x_dtype, e0, f);
+        if (p.normalize) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) f[e] *= inv;
+        }
+        const uint4 v = pack8(f, p.feat_dtype);
+        *reinterpret_cast<uint4*>(drow + e0 * 2) = v;
+        if (k == 0) *reinterpret_cast<uint4*>(lrow + e0 * 2) = v;
+      }
+    }
+    // this CTA's 64 rows are on their way to `dst`: order them before the flag at system scope
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint32_t* flag = reinterpret_cast<uint32_t*>(p.base[dst] + p.fflag_off) +
+                       (static_cast<long long>(mod) * p.world + p.rank) * (p.n_loc / PUSH_ROWS) + blk;
+      st_release_sys(flag, step);
+    }
+  }
+}
+
+}  // namespace
+}  // namespace nans
+
+using namespace nans;
+
+extern "C" int nans_peer_alloc(size_t bytes, void** ptr, void* handle64) {
+  int rc = check_device();
+  if (rc != NANS_OK) return rc;
+  NANS_REQUIRE(bytes > 0 && ptr && handle64, "peer_alloc: bad arguments");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+  void* p = nullptr;
+  NANS_CUDA_OK(cudaMalloc(&p, bytes));
+  cudaError_t e = cudaMemset(p, 0, bytes);
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  cudaIpcMemHandle_t h;
+  if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) {
+    cudaFree(p);
+    set_error("peer_alloc: %s", cudaGetErrorString(e));
+    return NANS_ERR_CUDA;
+  }
+  memcpy(handle64, &h, sizeof(h));
+  *ptr = p;
+  return NANS_OK;
+}
+
+extern "C" int nans_peer_free(void* ptr) {
+  if (ptr) NANS_CUDA_OK(cudaFree(ptr));
+  return NANS_OK;
+}
+
+extern "C" int nans_peer_open(const void* handle64, void** ptr) {
+  int rc = check_device();
+  if (rc != NANS_OK) return rc;
+  NANS_REQUIRE(handle64 && ptr, "peer_open: null pointer");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, sizeof(h));
+  void* p = nullptr;
+  NANS_CUDA_OK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  *ptr = p;
+  return NANS_OK;
+}
+
+extern "C" int nans_peer_close(void* ptr) {
+  if (ptr) NANS_CUDA_OK(cudaIpcCloseMemHandle(ptr));
+  return NANS_OK;
+}
+
+extern "C" int nans_peer_zero(void* ptr, size_t bytes, void* stream) {
+  NANS_REQUIRE(ptr != nullptr, "peer_zero: null pointer");
+  NANS_CUDA_OK(cudaMemsetAsync(ptr, 0, bytes, static_cast<cudaStream_t>(stream)));
+  return NANS_OK;
+}
+
+extern "C" int nans_xchg_layout(nans_xchg_t* x, int64_t n_loc, int64_t D) {
+  NANS_REQUIRE(x != nullptr && x->world >= 1 && x->world <= NANS_MAX_PEERS, "xchg_layout: world must be in [1, %d]",
+               NANS_MAX_PEERS);
+  NANS_REQUIRE(n_loc > 0 && n_loc % 256 == 0 && D > 0 && D % 8 == 0 && D <= 8192,
+               "xchg_layout: n_loc must be a positive multiple of 256 and D a multiple of 8 (n_loc=%lld, D=%lld)",
+               (long long)n_loc, (long long)D);
+  const int64_t W = x->world, N = W * n_loc, pad = (n_loc + 3) / 4 * 4;
+  NANS_REQUIRE(N < (1ll << 29), "xchg_layout: global batch too large");
+  x->n_loc = n_loc;
+  x->D = D;
+  int64_t off = 0;
+  x->feat_off = off;
+  off += static_cast<int64_t>(align_up(static_cast<size_t>(2) * 2 * N * D * 2, 1024));
+  x->lse_len = 2 * pad + 8;
+  x->lse_off = off;
+  off += static_cast<int64_t>(align_up(static_cast<size_t>(2) * W * x->lse_len * 4, 1024));
+  x->fflag_off = off;
+  off += static_cast<int64_t>(align_up(static_cast<size_t>(2) * W * (n_loc / NANS_XCHG_FLAG_ROWS) * 4, 1024));
+  x->lflag_off = off;
+  off += 1024;
+  x->bytes = off;
+  return NANS_OK;
+}
+
+extern "C" int nans_xchg_cast_push(const nans_xchg_t* x, const void* img, const void* txt, int x_dtype,
+                                   int64_t ld_x, int feat_dtype, int normalize, void* I16_loc, void* T16_loc,
+                                   void* stream) {
+  int rc = check_device();
+  if (rc != NANS_OK) return rc;
+  NANS_REQUIRE(x != nullptr && x->world >= 1 && x->world <= NANS_MAX_PEERS && x->rank >= 0 && x->rank < x->world,
+               "xchg_cast_push: bad exchange descriptor");
+  NANS_REQUIRE(x_dtype == NANS_F32 || x_dtype == NANS_F16 || x_dtype == NANS_BF16, "xchg_cast_push: bad x_dtype");
+  NANS_REQUIRE(feat_dtype == NANS_F16 || feat_dtype == NANS_BF16, "xchg_cast_push: feat_dtype must be NANS_F16 or NANS_BF16");
+  const int64_t n_loc = x->n_loc, D = x->D;
+  NANS_REQUIRE(n_loc > 0 && n_loc % 256 == 0 && D > 0 && D % 8 == 0 && ld_x >= D, "xchg_cast_push: bad sizes");
+  NANS_REQUIRE(img && txt && I16_loc && T16_loc && x->epoch, "xchg_cast_push: null pointer");
+  NANS_REQUIRE((reinterpret_cast<uintptr_t>(img) & 15) == 0 && (reinterpret_cast<uintptr_t>(txt) & 15) == 0 &&
+                   (ld_x * (x_dtype == NANS_F32 ? 4 : 2)) % 16 == 0,
+               "xchg_cast_push: feature rows must be 16-byte aligned");
+  for (int r = 0; r < x->world; ++r) NANS_REQUIRE(x->base[r] != nullptr, "xchg_cast_push: peer %d is not mapped", r);
+  PushParams p;
+  p.src[0] = img;
+  p.src[1] = txt;
+  p.loc16[0] = I16_loc;
+  p.loc16[1] = T16_loc;
+  p.x_dtype = x_dtype;
+  p.feat_dtype = feat_dtype;
+  p.normalize = normalize ? 1 : 0;
+  p.n_loc = static_cast<int>(n_loc);
+  p.D = static_cast<int>(D);
+  p.ld_x = ld_x;
+  p.world = x->world;
+  p.rank = x->rank;
+  p.feat_off = x->feat_off;
+  p.fflag_off = x->fflag_off;
+  p.slot_rows = static_cast<long long>(x->world) * n_loc;
+  p.epoch = x->epoch;
+  for (int r = 0; r < NANS_MAX_PEERS; ++r) p.base[r] = r < x->world ? static_cast<uint8_t*>(x->base[r]) : nullptr;
+  const dim3 grid(static_cast<unsigned>(n_loc / PUSH_ROWS), 2);
+  cast_push_kernel<<<grid, PUSH_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  NANS_CUDA_OK(cudaGetLastError());
+  return NANS_OK;
+}

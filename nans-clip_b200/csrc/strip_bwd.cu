@@ -261,6 +261,13 @@ BwdSchedule plan_bwd_schedule(int64_t grad_row_count, int64_t N, int64_t D) {
 
 using namespace nans;
 
+static int bwd_dispatch(const void* I_loc, const void* T_loc, int64_t ld_loc, const void* T_all, const void* I_all,
+                        int64_t ld_all, const uint32_t* col_step, int feat_dtype, int64_t n_loc, int64_t N, int64_t D,
+                        int64_t label_begin, const float* s_dev, const float* lse_img_all, const float* lse_txt_all,
+                        const int* lse_minmax, const float* grad_out_dev, float grad_mult, int64_t grad_row_begin,
+                        int64_t grad_row_count, void* dI_loc, void* dT_loc, int out_dtype, void* ws, size_t ws_bytes,
+                        void* stream);
+
 extern "C" size_t nans_clip_loss_bwd_workspace_bytes(int64_t grad_row_count, int64_t N, int64_t D) {
   (void)N;
   if (grad_row_count <= 0 || D <= 0) return 512;
@@ -302,6 +309,39 @@ extern "C" int nans_clip_loss_bwd_minmax(const void* I_loc, const void* T_loc, i
                                          const float* grad_out_dev, float grad_mult, int64_t grad_row_begin,
                                          int64_t grad_row_count, void* dI_loc, void* dT_loc, int out_dtype,
                                          void* ws, size_t ws_bytes, void* stream) {
+  return bwd_dispatch(I_loc, T_loc, ld_loc, T_all, I_all, ld_all, nullptr, feat_dtype, n_loc, N, D, label_begin, s_dev,
+                      lse_img_all, lse_txt_all, lse_minmax, grad_out_dev, grad_mult, grad_row_begin, grad_row_count,
+                      dI_loc, dT_loc, out_dtype, ws, ws_bytes, stream);
+}
+
+// Exchange mode: the column operands are this rank's gathered buffers ([2 slots * N, D] per modality);
+// the slot is selected on the device from the step recorded by nans_clip_loss_exchange_finish_xchg.
+extern "C" int nans_clip_loss_bwd_xchg(const nans_xchg_t* x, const uint32_t* step_dev, const void* I16_loc,
+                                       const void* T16_loc, int feat_dtype, const float* s_dev,
+                                       const float* lse_img_all, const float* lse_txt_all, const int* lse_minmax,
+                                       const float* grad_out_dev, float grad_mult, int64_t grad_row_begin,
+                                       int64_t grad_row_count, void* dI_loc, void* dT_loc, int out_dtype, void* ws,
+                                       size_t ws_bytes, void* stream) {
+  NANS_REQUIRE(x != nullptr && x->world >= 1 && x->world <= NANS_MAX_PEERS && x->rank >= 0 && x->rank < x->world &&
+                   x->n_loc > 0 && x->D > 0 && x->base[x->rank] != nullptr,
+               "loss_bwd_xchg: bad exchange descriptor");
+  NANS_REQUIRE(step_dev != nullptr && lse_minmax != nullptr, "loss_bwd_xchg: step_dev and lse_minmax are required");
+  const int64_t N = static_cast<int64_t>(x->world) * x->n_loc;
+  const uint8_t* own = static_cast<const uint8_t*>(x->base[x->rank]);
+  const size_t mod_bytes = static_cast<size_t>(2) * N * x->D * 2;
+  return bwd_dispatch(I16_loc, T16_loc, x->D, own + x->feat_off + mod_bytes, own + x->feat_off, x->D, step_dev,
+                      feat_dtype, x->n_loc, N, x->D, static_cast<int64_t>(x->rank) * x->n_loc, s_dev, lse_img_all,
+                      lse_txt_all, lse_minmax, grad_out_dev, grad_mult, grad_row_begin, grad_row_count, dI_loc, dT_loc,
+                      out_dtype, ws, ws_bytes, stream);
+}
+
+// col_step != nullptr: T_all / I_all hold 2 * N rows (two slots), see BwdParams::col_step
+static int bwd_dispatch(const void* I_loc, const void* T_loc, int64_t ld_loc, const void* T_all, const void* I_all,
+                        int64_t ld_all, const uint32_t* col_step, int feat_dtype, int64_t n_loc, int64_t N, int64_t D,
+                        int64_t label_begin, const float* s_dev, const float* lse_img_all, const float* lse_txt_all,
+                        const int* lse_minmax, const float* grad_out_dev, float grad_mult, int64_t grad_row_begin,
+                        int64_t grad_row_count, void* dI_loc, void* dT_loc, int out_dtype, void* ws, size_t ws_bytes,
+                        void* stream) {
   int rc = check_device();
   if (rc != NANS_OK) return rc;
   NANS_REQUIRE(feat_dtype == NANS_F16 || feat_dtype == NANS_BF16,
@@ -325,6 +365,9 @@ extern "C" int nans_clip_loss_bwd_minmax(const void* I_loc, const void* T_loc, i
   cudaStream_t st = static_cast<cudaStream_t>(stream);
 
   const BwdSchedule sc = plan_bwd_schedule(grad_row_count, N, D);
+  NANS_REQUIRE(col_step == nullptr || sc.kind == BWD_NARROW || sc.kind == BWD_NARROW_PERSISTENT,
+               "loss_bwd_xchg: the exchange mode needs the narrow-pair backward (D <= 1024, no NANS_BWD_* overrides)");
+  const int64_t tm_rows = col_step != nullptr ? 2 * N : N;  // rows of the column operands' tensor maps
   const int kchunks = sc.kchunks;
   const size_t out_bytes = static_cast<size_t>(grad_row_count) * D * 4;
   // workspace: [0,256) lse min/max slots, then (16-bit outputs only) the two fp32 gradient buffers
@@ -372,11 +415,11 @@ extern "C" int nans_clip_loss_bwd_minmax(const void* I_loc, const void* T_loc, i
 
   CUtensorMap tmA0, tmB0, tmA1, tmB1, tmBk0, tmBk1;
   if ((rc = make_tmap_16b(&tmA0, I_loc, feat_dtype, n_loc, D, ld_loc, BM)) != NANS_OK) return rc;
-  if ((rc = make_tmap_16b(&tmB0, T_all, feat_dtype, N, D, ld_all, KT)) != NANS_OK) return rc;
+  if ((rc = make_tmap_16b(&tmB0, T_all, feat_dtype, tm_rows, D, ld_all, KT)) != NANS_OK) return rc;
   if ((rc = make_tmap_16b(&tmA1, T_loc, feat_dtype, n_loc, D, ld_loc, BM)) != NANS_OK) return rc;
-  if ((rc = make_tmap_16b(&tmB1, I_all, feat_dtype, N, D, ld_all, KT)) != NANS_OK) return rc;
-  if ((rc = make_tmap_16b(&tmBk0, T_all, feat_dtype, N, D, ld_all, KT / 2)) != NANS_OK) return rc;
-  if ((rc = make_tmap_16b(&tmBk1, I_all, feat_dtype, N, D, ld_all, KT / 2)) != NANS_OK) return rc;
+  if ((rc = make_tmap_16b(&tmB1, I_all, feat_dtype, tm_rows, D, ld_all, KT)) != NANS_OK) return rc;
+  if ((rc = make_tmap_16b(&tmBk0, T_all, feat_dtype, tm_rows, D, ld_all, KT / 2)) != NANS_OK) return rc;
+  if ((rc = make_tmap_16b(&tmBk1, I_all, feat_dtype, tm_rows, D, ld_all, KT / 2)) != NANS_OK) return rc;
   CUtensorMap tmAn0, tmAn1;  // narrow pairs: 64-row A boxes
   if ((rc = make_tmap_16b(&tmAn0, I_loc, feat_dtype, n_loc, D, ld_loc, NP_ROWS)) != NANS_OK) return rc;
   if ((rc = make_tmap_16b(&tmAn1, T_loc, feat_dtype, n_loc, D, ld_loc, NP_ROWS)) != NANS_OK) return rc;
@@ -412,6 +455,7 @@ extern "C" int nans_clip_loss_bwd_minmax(const void* I_loc, const void* T_loc, i
   p.out[1] = out32[1];
   p.accumulate = sc.nsplit > 1 ? 1 : 0;
   p.lse_minmax = minmax;
+  p.col_step = col_step;
   {
     const char* e = getenv("NANS_BWD_DEBUG");
     p.debug = e ? atoi(e) : 0;

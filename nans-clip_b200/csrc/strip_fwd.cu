@@ -41,6 +41,11 @@ struct FwdParams {
   float* diag;
   int slot_begin;
   long long slot_stride;  // floats between consecutive slots
+  // exchange mode (nans_clip_loss_fwd_xchg; see SweepArgs): xw = 0 otherwise
+  int xw, xrank, xsrc_tiles;
+  int xslot_rows;                // rows of one slot of the gathered tensor (= N)
+  const uint32_t* xflags[2];     // per strip: arrival flags of its column modality
+  const uint32_t* xepoch;        // device word: completed steps; this launch belongs to step *xepoch + 1
 };
 
 template <bool WITH_ACC>
@@ -138,8 +143,22 @@ clip_fwd_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
   a.tmA = strip == 0 ? &tmA0 : &tmA1;
   a.tmB = strip == 0 ? &tmB0 : &tmB1;
   a.row0 = CP ? rb * 2 * BM + static_cast<int>(blockIdx.x & 1) * BM : rb * BM;
-  a.tile_begin = static_cast<int>(static_cast<long long>(split) * p.ntiles / p.nsplit);
-  a.tile_end = static_cast<int>(static_cast<long long>(split + 1) * p.ntiles / p.nsplit);
+  if (p.xw > 0) {
+    // column split = a sub-range of every source rank's tiles
+    a.xw = p.xw;
+    a.xrank = p.xrank;
+    a.xsrc_tiles = p.xsrc_tiles;
+    a.xsub_begin = static_cast<int>(static_cast<long long>(split) * p.xsrc_tiles / p.nsplit);
+    a.xsub_count = static_cast<int>(static_cast<long long>(split + 1) * p.xsrc_tiles / p.nsplit) - a.xsub_begin;
+    a.xstep = *p.xepoch + 1u;
+    a.xrow_off = static_cast<int>(a.xstep & 1u) * p.xslot_rows;
+    a.xflags = p.xflags[strip];
+    a.tile_begin = 0;
+    a.tile_end = p.xw * a.xsub_count;
+  } else {
+    a.tile_begin = static_cast<int>(static_cast<long long>(split) * p.ntiles / p.nsplit);
+    a.tile_end = static_cast<int>(static_cast<long long>(split + 1) * p.ntiles / p.nsplit);
+  }
   a.skip_begin = p.skip_begin;
   a.skip_count = p.skip_count;
   a.kchunks = p.kchunks;
@@ -165,9 +184,8 @@ clip_fwd_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
   // does this unit sweep the tile that holds the row's label?  (swept index = tile index minus the
   // skipped tiles before it; tiles inside the skipped range belong to another phase)
   const int lab_tile = epi.label >= 0 && epi.label < p.ncols ? epi.label / BN : -1;
-  const bool lab_skipped = lab_tile >= a.skip_begin && lab_tile < a.skip_begin + a.skip_count;
-  const int lab_swept = lab_tile < a.skip_begin ? lab_tile : lab_tile - a.skip_count;
-  const bool has_diag = lab_tile >= 0 && !lab_skipped && lab_swept >= a.tile_begin && lab_swept < a.tile_end;
+  const int lab_at = swept_index_of(a, lab_tile);  // swept index at which this unit visits the label's tile
+  const bool has_diag = lab_at >= 0;
   if (warp >= 8) {
     xm[0 * 128 + r] = epi.m;
     xm[1 * 128 + r] = L;
@@ -184,7 +202,7 @@ clip_fwd_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
     L = L * s1 + xm[1 * 128 + r] * s2;
     Wt = Wt * s1 + xm[2 * 128 + r] * s2;
     // the label column lies in exactly one tile: the set that owns that tile holds cos there
-    const int lab_set = has_diag ? ((lab_swept - a.tile_begin) & 1) : 0;
+    const int lab_set = has_diag ? (lab_at & 1) : 0;
     const float diag = lab_set == 0 ? epi.diag : xm[3 * 128 + r];
     float bv = epi.bv;
     int bi = epi.bi;
@@ -227,6 +245,12 @@ struct FinParams {
   unsigned* counter;
   float* scalars;  // [8]
   float* row_stats;  // optional [3][2 * n_loc]: per-row loss term, d/ds term, arg-max column (int bits)
+  // push mode (nans_clip_loss_fwd_finalize_push): the packed result [lse_img (pad) | lse_txt (pad) | 8
+  // scalars] also goes to row xrank of slot (step & 1) of every rank's lse table, then their flag xrank
+  int xw, xrank, xpad;
+  long long xlse_off, xlse_len, xlflag_off;
+  const uint32_t* xepoch;
+  uint8_t* xbase[NANS_MAX_PEERS];
 };
 
 __global__ void __launch_bounds__(256) clip_fwd_finalize_kernel(const FinParams p) {
@@ -261,6 +285,12 @@ __global__ void __launch_bounds__(256) clip_fwd_finalize_kernel(const FinParams 
     const float lse = lse2 * kLn2;
     const float cosd = p.diag[gid];
     (strip == 0 ? p.lse_img : p.lse_txt)[row] = lse2;
+    if (p.xw > 0) {
+      const uint32_t step = *p.xepoch + 1u;
+      const long long at = p.xlse_off + ((static_cast<long long>(step & 1u) * p.xw + p.xrank) * p.xlse_len +
+                                         static_cast<long long>(strip) * p.xpad + row) * 4;
+      for (int r = 0; r < p.xw; ++r) *reinterpret_cast<float*>(p.xbase[r] + at) = lse2;
+    }
     acc[strip] = static_cast<double>(lse) - static_cast<double>(sc) * cosd;
     acc[2 + strip] = static_cast<double>(Wt) / static_cast<double>(L) - cosd;
     if (p.with_acc) acc[4 + strip] = (bi == p.label_begin + row) ? 1.0 : 0.0;
@@ -285,7 +315,10 @@ __global__ void __launch_bounds__(256) clip_fwd_finalize_kernel(const FinParams 
     for (int i = 0; i < 8; ++i) v += red[threadIdx.x][i];
     p.block_part[blockIdx.x * 6 + threadIdx.x] = v;
   }
-  __threadfence();
+  // every thread's stores (block partials; in push mode also the lse values written into the peers'
+  // tables) are made visible — at system scope when they crossed NVLink — before this block is counted
+  if (p.xw > 0) __threadfence_system();
+  else __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) {
     const unsigned done = atomicAdd(p.counter, 1u);
@@ -300,8 +333,25 @@ __global__ void __launch_bounds__(256) clip_fwd_finalize_kernel(const FinParams 
         for (unsigned b = 0; b < gridDim.x; ++b)
           v += *(volatile double*)&p.block_part[b * 6 + threadIdx.x];
       p.scalars[threadIdx.x] = static_cast<float>(v);
+      if (p.xw > 0) {
+        const uint32_t step = *p.xepoch + 1u;
+        const long long at = p.xlse_off + ((static_cast<long long>(step & 1u) * p.xw + p.xrank) * p.xlse_len +
+                                           2ll * p.xpad + threadIdx.x) * 4;
+        for (int r = 0; r < p.xw; ++r) *reinterpret_cast<float*>(p.xbase[r] + at) = static_cast<float>(v);
+      }
     }
     if (threadIdx.x == 0) *p.counter = 0;
+    if (p.xw > 0) {
+      // all blocks' pushes happen-before their counter increment (fence.sys above), which this block
+      // observed; its own scalar pushes are fenced here: then one release store per peer raises the flag
+      __threadfence_system();
+      __syncthreads();
+      if (threadIdx.x < p.xw) {
+        const uint32_t step = *p.xepoch + 1u;
+        uint32_t* flag = reinterpret_cast<uint32_t*>(p.xbase[threadIdx.x] + p.xlflag_off) + p.xrank;
+        st_release_sys(flag, step);
+      }
+    }
   }
 }
 
@@ -312,13 +362,28 @@ __global__ void __launch_bounds__(256) clip_fwd_finalize_kernel(const FinParams 
 //   out[0] loss = (S0 + S1) / 2N   out[1] dloss/ds = (S2 + S3) / 2N   out[2], out[3] accuracies = S4/N, S5/N
 // and the order-preserving int encodings of min / max over all lse values (kernel (3)'s one-exp form).
 // A single block: 2N floats are at most a few hundred KB, the loads are independent.
+//
+// Push mode (lflags != nullptr, nans_clip_loss_exchange_finish_xchg): `gathered` is slot 0 of this rank's
+// own lse table, filled by the peers' finalize kernels over NVLink; the block first waits for the W
+// arrival flags of step *epoch + 1, reads the slot of that step, and at the end publishes the step
+// (step_out for this call's backward, *epoch for the next forward).
 __global__ void __launch_bounds__(1024) clip_exchange_finish_kernel(const float* __restrict__ gathered, int W,
                                                                     int n_loc, int pad, float* __restrict__ lse_all,
                                                                     long long ld, float* __restrict__ out,
-                                                                    int* __restrict__ minmax) {
+                                                                    int* __restrict__ minmax,
+                                                                    const uint32_t* __restrict__ lflags,
+                                                                    uint32_t* __restrict__ epoch,
+                                                                    uint32_t* __restrict__ step_out) {
   __shared__ float slo[32], shi[32];
   const long long L = 2ll * pad + 8;
   const int total = W * n_loc;
+  uint32_t step = 0;
+  if (lflags != nullptr) {
+    step = *epoch + 1u;
+    if (threadIdx.x < W) wait_flag_sys(lflags + threadIdx.x, step);
+    __syncthreads();
+    gathered += static_cast<long long>(step & 1u) * W * L;
+  }
   float lo = INFINITY, hi = -INFINITY;
 #pragma unroll
   for (int strip = 0; strip < 2; ++strip) {
@@ -326,7 +391,7 @@ __global__ void __launch_bounds__(1024) clip_exchange_finish_kernel(const float*
     for (int idx = threadIdx.x; idx < total; idx += 1024) {
       const int rank = idx / n_loc;
       const int row = idx - rank * n_loc;
-      const float v = __ldg(gathered + rank * L + static_cast<long long>(strip) * pad + row);
+      const float v = __ldcg(gathered + rank * L + static_cast<long long>(strip) * pad + row);  // L2: peer-written
       lse_all[strip * ld + idx] = v;
       lo = fminf(lo, v);
       hi = fmaxf(hi, v);
@@ -353,7 +418,7 @@ __global__ void __launch_bounds__(1024) clip_exchange_finish_kernel(const float*
     // lanes 0..5: sum of partial scalar k over the ranks, in rank order (deterministic)
     float sum = 0.f;
     if (threadIdx.x < 6)
-      for (int r = 0; r < W; ++r) sum += __ldg(gathered + r * L + 2ll * pad + threadIdx.x);
+      for (int r = 0; r < W; ++r) sum += __ldcg(gathered + r * L + 2ll * pad + threadIdx.x);
     const float s01 = sum + __shfl_down_sync(0xffffffffu, sum, 1);  // lanes 0, 2: S0+S1, S2+S3
     const float n = static_cast<float>(total);
     if (threadIdx.x == 0) {
@@ -365,6 +430,10 @@ __global__ void __launch_bounds__(1024) clip_exchange_finish_kernel(const float*
     if (threadIdx.x == 2) out[1] = s01 / (2.0f * n);
     if (threadIdx.x == 4) out[2] = sum / n;
     if (threadIdx.x == 5) out[3] = sum / n;
+    if (lflags != nullptr && threadIdx.x == 0) {
+      *step_out = step;
+      *epoch = step;
+    }
   }
 }
 
@@ -433,10 +502,123 @@ int choose_nsplit(int64_t n_loc, int64_t ncols, int nstrips) {
   return best;
 }
 
+// exchange mode: a split is a sub-range of every source rank's tiles, so ns <= tiles per source
+int choose_nsplit_xchg(int64_t n_loc, int64_t world) {
+  const bool pair = fwd_pair_mode();
+  const int64_t base = 2 * ceil_div(n_loc, pair ? 2 * BM : BM);
+  const int64_t src_tiles = n_loc / BN;
+  const int sms = pair ? sm_count() / 2 : sm_count();
+  int best = 1;
+  double best_cost = 1e300;
+  const int64_t max_ns = src_tiles < 32 ? src_tiles : 32;
+  for (int64_t ns = 1; ns <= max_ns; ++ns) {
+    const double waves = static_cast<double>(ceil_div(base * ns, sms));
+    const double cost = waves * (static_cast<double>(world * ceil_div(src_tiles, ns)) + 0.75);
+    if (cost < best_cost - 1e-9) {
+      best_cost = cost;
+      best = static_cast<int>(ns);
+    }
+  }
+  return best;
+}
+
 }  // namespace
 }  // namespace nans
 
 using namespace nans;
+
+extern "C" int64_t nans_clip_loss_fwd_xchg_slots(int64_t n_loc, int64_t world, int64_t D) {
+  (void)D;
+  if (n_loc <= 0 || world <= 0 || n_loc % BN != 0) return 0;
+  return choose_nsplit_xchg(n_loc, world);
+}
+
+extern "C" int nans_clip_loss_fwd_xchg(const nans_xchg_t* x, const void* I16_loc, const void* T16_loc,
+                                       int feat_dtype, const float* s_dev, int flags, void* ws, size_t ws_bytes,
+                                       void* stream) {
+  int rc = check_device();
+  if (rc != NANS_OK) return rc;
+  NANS_REQUIRE(x != nullptr && x->world >= 1 && x->world <= NANS_MAX_PEERS && x->rank >= 0 && x->rank < x->world,
+               "loss_fwd_xchg: bad exchange descriptor");
+  NANS_REQUIRE(feat_dtype == NANS_F16 || feat_dtype == NANS_BF16, "loss_fwd_xchg: feat_dtype must be NANS_F16 or NANS_BF16");
+  const int64_t n_loc = x->n_loc, D = x->D, W = x->world, N = W * n_loc;
+  NANS_REQUIRE(n_loc > 0 && n_loc % BN == 0 && D > 0 && D % 8 == 0 && D <= 8192 && N < (1ll << 29),
+               "loss_fwd_xchg: n_loc must be a positive multiple of 256 and D a multiple of 8");
+  NANS_REQUIRE(I16_loc && T16_loc && s_dev && ws && x->base[x->rank] && x->epoch, "loss_fwd_xchg: null pointer");
+  NANS_REQUIRE((flags & (NANS_LOSS_STRIP_IMG | NANS_LOSS_STRIP_TXT)) == 0, "loss_fwd_xchg: both strips run in one launch");
+  const int nsplit = choose_nsplit_xchg(n_loc, W);
+  const size_t need = carve_fwd_ws(nullptr, n_loc, nsplit).bytes;
+  if (ws_bytes < need) {
+    set_error("loss_fwd_xchg: workspace %zu < %zu bytes", ws_bytes, need);
+    return NANS_ERR_WORKSPACE;
+  }
+  FwdWs w = carve_fwd_ws(ws, n_loc, nsplit);
+  const bool pair = fwd_pair_mode();
+  const int kchunks = static_cast<int>(ceil_div(D, BK));
+  const SmemPlan plan = plan_smem(kchunks, pair);
+
+  // gathered operands of this rank: per modality one [2 slots * N, D] tensor
+  uint8_t* own = static_cast<uint8_t*>(x->base[x->rank]);
+  const size_t mod_bytes = static_cast<size_t>(2) * N * D * 2;
+  const void* I_gath = own + x->feat_off;
+  const void* T_gath = own + x->feat_off + mod_bytes;
+  CUtensorMap tmA0, tmB0, tmA1, tmB1;
+  const uint32_t bbox = pair ? BN / 2 : BN;
+  if ((rc = make_tmap_16b(&tmA0, I16_loc, feat_dtype, n_loc, D, D, BM)) != NANS_OK) return rc;
+  if ((rc = make_tmap_16b(&tmB0, T_gath, feat_dtype, 2 * N, D, D, bbox)) != NANS_OK) return rc;
+  if ((rc = make_tmap_16b(&tmA1, T16_loc, feat_dtype, n_loc, D, D, BM)) != NANS_OK) return rc;
+  if ((rc = make_tmap_16b(&tmB1, I_gath, feat_dtype, 2 * N, D, D, bbox)) != NANS_OK) return rc;
+
+  FwdParams p;
+  p.n_loc = static_cast<int>(n_loc);
+  p.ncols = static_cast<int>(N);
+  p.kchunks = kchunks;
+  p.stages = plan.stages;
+  p.idesc = make_idesc(idesc_fmt(feat_dtype), idesc_fmt(feat_dtype), 0, 0, pair ? 2 * BM : BM, BN);
+  p.nrb = static_cast<int>(ceil_div(n_loc, pair ? 2 * BM : BM));
+  p.nsplit = nsplit;
+  p.strip0 = 0;
+  p.ntiles = static_cast<int>(N / BN);
+  p.skip_begin = 1 << 30;
+  p.skip_count = 0;
+  p.label_shift = static_cast<int>(x->rank * n_loc);
+  p.lab_row0 = 0;
+  p.lab_row1 = static_cast<int>(n_loc);
+  p.col_global_begin = 0;
+  p.s_dev = s_dev;
+  p.part_m = w.part_m;
+  p.part_l = w.part_l;
+  p.part_w = w.part_w;
+  p.part_bv = w.part_bv;
+  p.part_bi = w.part_bi;
+  p.diag = w.diag;
+  p.slot_begin = 0;
+  p.slot_stride = w.slot_stride;
+  p.xw = static_cast<int>(W);
+  p.xrank = x->rank;
+  p.xsrc_tiles = static_cast<int>(n_loc / BN);
+  p.xslot_rows = static_cast<int>(N);
+  const uint32_t* fflags = reinterpret_cast<const uint32_t*>(own + x->fflag_off);
+  const int64_t blocks = W * (n_loc / NANS_XCHG_FLAG_ROWS);
+  p.xflags[0] = fflags + blocks;  // strip 0 reads the TEXT columns (modality 1)
+  p.xflags[1] = fflags;           // strip 1 reads the IMAGE columns (modality 0)
+  p.xepoch = x->epoch;
+
+  const bool with_acc = (flags & NANS_LOSS_WITH_ACC) != 0;
+  void (*kern)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const FwdParams);
+  if (pair) {
+    kern = plan.a_resident ? (with_acc ? clip_fwd_kernel<true, true, true> : clip_fwd_kernel<true, false, true>)
+                           : (with_acc ? clip_fwd_kernel<false, true, true> : clip_fwd_kernel<false, false, true>);
+  } else {
+    kern = plan.a_resident ? (with_acc ? clip_fwd_kernel<true, true, false> : clip_fwd_kernel<true, false, false>)
+                           : (with_acc ? clip_fwd_kernel<false, true, false> : clip_fwd_kernel<false, false, false>);
+  }
+  NANS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(plan.bytes)));
+  const unsigned grid = static_cast<unsigned>((pair ? 2 : 1) * 2 * p.nrb * p.nsplit);
+  kern<<<grid, NUM_THREADS, plan.bytes, static_cast<cudaStream_t>(stream)>>>(tmA0, tmB0, tmA1, tmB1, p);
+  NANS_CUDA_OK(cudaGetLastError());
+  return NANS_OK;
+}
 
 extern "C" int64_t nans_clip_loss_fwd_phase_slots(int64_t n_loc, int64_t ncols, int64_t D) {
   (void)D;
@@ -541,6 +723,10 @@ extern "C" int nans_clip_loss_fwd_phase_rows(const void* I_loc, const void* T_lo
   p.diag = w.diag;
   p.slot_begin = static_cast<int>(slot_begin);
   p.slot_stride = w.slot_stride;
+  p.xw = 0;
+  p.xrank = p.xsrc_tiles = p.xslot_rows = 0;
+  p.xflags[0] = p.xflags[1] = nullptr;
+  p.xepoch = nullptr;
 
   const bool with_acc = (flags & NANS_LOSS_WITH_ACC) != 0;
   void (*kern)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const FwdParams);
@@ -601,6 +787,59 @@ extern "C" int nans_clip_loss_fwd_finalize_rows(int64_t n_loc, int64_t total_slo
   p.counter = w.counter;
   p.scalars = scalars;
   p.row_stats = row_stats;
+  p.xw = 0;
+  const unsigned grid = static_cast<unsigned>(ceil_div(2 * n_loc, 256));
+  clip_fwd_finalize_kernel<<<grid, 256, 0, st>>>(p);
+  NANS_CUDA_OK(cudaGetLastError());
+  return NANS_OK;
+}
+
+extern "C" int nans_clip_loss_fwd_finalize_push(const nans_xchg_t* x, int64_t total_slots, const float* s_dev,
+                                                int flags, void* ws, size_t ws_bytes, float* lse_img_loc,
+                                                float* lse_txt_loc, float* scalars, void* stream) {
+  int rc = check_device();
+  if (rc != NANS_OK) return rc;
+  NANS_REQUIRE(x != nullptr && x->world >= 1 && x->world <= NANS_MAX_PEERS && x->rank >= 0 && x->rank < x->world &&
+                   x->n_loc > 0 && x->epoch,
+               "loss_fwd_finalize_push: bad exchange descriptor");
+  const int64_t n_loc = x->n_loc, pad = (n_loc + 3) / 4 * 4;
+  NANS_REQUIRE(total_slots > 0 && x->lse_len == 2 * pad + 8, "loss_fwd_finalize_push: bad sizes");
+  NANS_REQUIRE(s_dev && ws && lse_img_loc && lse_txt_loc && scalars, "loss_fwd_finalize_push: null pointer");
+  for (int r = 0; r < x->world; ++r) NANS_REQUIRE(x->base[r] != nullptr, "loss_fwd_finalize_push: peer %d is not mapped", r);
+  FwdWs w = carve_fwd_ws(ws, n_loc, total_slots);
+  if (w.bytes > ws_bytes) {
+    set_error("loss_fwd_finalize_push: workspace %zu < %zu bytes", ws_bytes, w.bytes);
+    return NANS_ERR_WORKSPACE;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  NANS_CUDA_OK(cudaMemsetAsync(w.counter, 0, sizeof(unsigned), st));
+  FinParams p;
+  p.n_loc = static_cast<int>(n_loc);
+  p.total_slots = static_cast<int>(total_slots);
+  p.with_acc = (flags & NANS_LOSS_WITH_ACC) ? 1 : 0;
+  p.slot_stride = w.slot_stride;
+  p.label_begin = static_cast<int>(x->rank * n_loc);
+  p.s_dev = s_dev;
+  p.part_m = w.part_m;
+  p.part_l = w.part_l;
+  p.part_w = w.part_w;
+  p.part_bv = w.part_bv;
+  p.part_bi = w.part_bi;
+  p.diag = w.diag;
+  p.lse_img = lse_img_loc;
+  p.lse_txt = lse_txt_loc;
+  p.block_part = w.block_part;
+  p.counter = w.counter;
+  p.scalars = scalars;
+  p.row_stats = nullptr;
+  p.xw = x->world;
+  p.xrank = x->rank;
+  p.xpad = static_cast<int>(pad);
+  p.xlse_off = x->lse_off;
+  p.xlse_len = x->lse_len;
+  p.xlflag_off = x->lflag_off;
+  p.xepoch = x->epoch;
+  for (int r = 0; r < NANS_MAX_PEERS; ++r) p.xbase[r] = r < x->world ? static_cast<uint8_t*>(x->base[r]) : nullptr;
   const unsigned grid = static_cast<unsigned>(ceil_div(2 * n_loc, 256));
   clip_fwd_finalize_kernel<<<grid, 256, 0, st>>>(p);
   NANS_CUDA_OK(cudaGetLastError());
@@ -632,7 +871,27 @@ extern "C" int nans_clip_loss_exchange_finish(const float* gathered, int64_t wor
   NANS_REQUIRE(gathered && lse_all && out && lse_minmax, "loss_exchange_finish: null pointer");
   clip_exchange_finish_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(
       gathered, static_cast<int>(world), static_cast<int>(n_loc), static_cast<int>(pad), lse_all,
-      static_cast<long long>(ld), out, lse_minmax);
+      static_cast<long long>(ld), out, lse_minmax, nullptr, nullptr, nullptr);
+  NANS_CUDA_OK(cudaGetLastError());
+  return NANS_OK;
+}
+
+extern "C" int nans_clip_loss_exchange_finish_xchg(const nans_xchg_t* x, float* lse_all, int64_t ld, float* out,
+                                                   int* lse_minmax, uint32_t* step_out, void* stream) {
+  int rc = check_device();
+  if (rc != NANS_OK) return rc;
+  NANS_REQUIRE(x != nullptr && x->world >= 1 && x->world <= NANS_MAX_PEERS && x->rank >= 0 && x->rank < x->world &&
+                   x->n_loc > 0 && x->base[x->rank] && x->epoch,
+               "loss_exchange_finish_xchg: bad exchange descriptor");
+  const int64_t pad = (x->n_loc + 3) / 4 * 4;
+  NANS_REQUIRE(x->lse_len == 2 * pad + 8 && ld >= x->world * x->n_loc && x->world * x->n_loc < (1ll << 30),
+               "loss_exchange_finish_xchg: bad sizes");
+  NANS_REQUIRE(lse_all && out && lse_minmax && step_out, "loss_exchange_finish_xchg: null pointer");
+  uint8_t* own = static_cast<uint8_t*>(x->base[x->rank]);
+  clip_exchange_finish_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const float*>(own + x->lse_off), x->world, static_cast<int>(x->n_loc), static_cast<int>(pad),
+      lse_all, static_cast<long long>(ld), out, lse_minmax, reinterpret_cast<const uint32_t*>(own + x->lflag_off),
+      x->epoch, step_out);
   NANS_CUDA_OK(cudaGetLastError());
   return NANS_OK;
 }

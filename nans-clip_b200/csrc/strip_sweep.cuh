@@ -73,7 +73,44 @@ struct SweepArgs {
   int kchunks;     // ceil(D / 64)
   int stages;
   uint32_t idesc;  // M=128 (256 in pair mode), N=256, K-major A and B, fp32 accumulate
+  // Exchange mode (xw > 0; multi-GPU push data plane, exchange.cu): B is the gathered buffer of an
+  // xw-rank job, xsrc_tiles tiles per source rank.  The unit sweeps the tiles
+  // [xsub_begin, xsub_begin + xsub_count) of EVERY source, sources in the order xrank, xrank + 1, ...
+  // (its own rows first: they are there already; the others in the order the peers push them), so
+  // tile_begin = 0 and tile_end = xw * xsub_count.  Before a tile's loads the producer waits for the
+  // arrival flags (one per 64 rows, value >= xstep) of the rows it is about to read.
+  int xw = 0, xrank = 0, xsrc_tiles = 1, xsub_begin = 0, xsub_count = 1;
+  int xrow_off = 0;                  // row of column 0 in the gathered tensor map (slot of this step)
+  const uint32_t* xflags = nullptr;  // [xw][xsrc_tiles * 4] arrival flags of the column operand's modality
+  uint32_t xstep = 0;
 };
+
+// swept index t of a unit -> tile of the column operand (in logical, global column tiles)
+__device__ __forceinline__ int tile_of(const SweepArgs& a, int t) {
+  if (a.xw > 0) {
+    const int k = t / a.xsub_count;
+    int src = a.xrank + k;
+    if (src >= a.xw) src -= a.xw;
+    return src * a.xsrc_tiles + a.xsub_begin + (t - k * a.xsub_count);
+  }
+  const int tix = a.tile_begin + t;
+  return tix + (tix >= a.skip_begin ? a.skip_count : 0);
+}
+// inverse: the swept index at which this unit visits `tile`, or -1 if it does not
+__device__ __forceinline__ int swept_index_of(const SweepArgs& a, int tile) {
+  if (tile < 0) return -1;
+  if (a.xw > 0) {
+    const int src = tile / a.xsrc_tiles;
+    const int j = tile - src * a.xsrc_tiles - a.xsub_begin;
+    if (src >= a.xw || j < 0 || j >= a.xsub_count) return -1;
+    int k = src - a.xrank;
+    if (k < 0) k += a.xw;
+    return k * a.xsub_count + j;
+  }
+  if (tile >= a.skip_begin && tile < a.skip_begin + a.skip_count) return -1;
+  const int sw = tile < a.skip_begin ? tile : tile - a.skip_count;
+  return (sw >= a.tile_begin && sw < a.tile_end) ? sw - a.tile_begin : -1;
+}
 
 // Epi must provide:  __device__ void tile(uint32_t taddr, int tile_idx)
 //   taddr = TMEM address of this thread's warp lane group at column 0 of the accumulator buffer.
@@ -159,8 +196,15 @@ __device__ __forceinline__ uint8_t* run(const SweepArgs& a, Epi& epi) {
     int stage = 0;
     uint32_t phase = 0;
     for (int t = 0; t < ntiles; ++t) {
-      const int tix = a.tile_begin + t;
-      const int col0 = (tix + (tix >= a.skip_begin ? a.skip_count : 0)) * BN + (CP ? static_cast<int>(rank) * (BN / 2) : 0);
+      const int tile = tile_of(a, t);
+      const int col0 = tile * BN + (CP ? static_cast<int>(rank) * (BN / 2) : 0) + a.xrow_off;
+      if (a.xw > 0 && tile / a.xsrc_tiles != a.xrank) {
+        // remote rows [col0, col0 + rows of this CTA's part of the tile): one flag per 64 rows
+        constexpr int NFLAG = (CP ? BN / 2 : BN) / 64;
+        if (lane < NFLAG) wait_flag_sys(a.xflags + (col0 - a.xrow_off) / 64 + lane, a.xstep);
+        __syncwarp();
+        fence_proxy_async_global();  // the peer's generic-proxy writes -> this CTA's TMA (async proxy) reads
+      }
       for (int c = 0; c < a.kchunks; ++c) {
         mbar_wait(&empty[stage], phase ^ 1u);
         if (elect_one()) {
@@ -231,8 +275,7 @@ __device__ __forceinline__ uint8_t* run(const SweepArgs& a, Epi& epi) {
     for (int t = set; t < ntiles; t += 2) {
       mbar_wait(&tfull[set], acc_phase);
       tc_fence_after();
-      const int tix = a.tile_begin + t;
-      epi.tile(tmem_base + lane_base + static_cast<uint32_t>(set * BN), tix + (tix >= a.skip_begin ? a.skip_count : 0));
+      epi.tile(tmem_base + lane_base + static_cast<uint32_t>(set * BN), tile_of(a, t));
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {

@@ -238,6 +238,105 @@ def bwd(I_loc, T_loc, T_all, I_all, *, label_begin: int, s_dev: torch.Tensor,
 
 
 # --------------------------------------------------------------------------------------------
+# (2x/3x) multi-GPU exchange over NVLink peer memory (csrc/exchange.cu; descriptors: exchange.py)
+# --------------------------------------------------------------------------------------------
+def _desc_ref(desc):
+    import ctypes
+    return ctypes.byref(desc)
+
+
+def xchg_cast_push(desc, img: torch.Tensor, txt: torch.Tensor, feat_dtype: torch.dtype, normalize: bool = False):
+    """Kernel (1) + the feature exchange: returns the local 16-bit copies (I16, T16) of this rank's rows;
+    the rows are on their way into every rank's gathered buffers when the call returns."""
+    _require_cuda(img, txt)
+    img, txt = _rowmajor(img), _rowmajor(txt)
+    n_loc, D = img.shape
+    assert txt.shape == (n_loc, D) and img.dtype == txt.dtype and (n_loc, D) == (desc.n_loc, desc.D)
+    if img.stride(0) != txt.stride(0):
+        img, txt = img.contiguous(), txt.contiguous()
+    I16 = torch.empty((n_loc, D), dtype=feat_dtype, device=img.device)
+    T16 = torch.empty((n_loc, D), dtype=feat_dtype, device=img.device)
+    with _on_device(img.device) as stream:
+        check(_lib.load().nans_xchg_cast_push(_desc_ref(desc), img.data_ptr(), txt.data_ptr(), dtype_code(img.dtype),
+                                              img.stride(0), dtype_code(feat_dtype), 1 if normalize else 0,
+                                              I16.data_ptr(), T16.data_ptr(), stream))
+    _count(1)
+    return I16, T16
+
+
+def fwd_xchg_slots(n_loc: int, world: int, D: int) -> int:
+    return int(_lib.load().nans_clip_loss_fwd_xchg_slots(n_loc, world, D))
+
+
+def fwd_xchg(desc, I16: torch.Tensor, T16: torch.Tensor, s_dev: torch.Tensor, with_acc: bool, ws: torch.Tensor) -> None:
+    """Both strips of this rank over the gathered buffers, tiles consumed as their flags go up."""
+    _require_cuda(I16, T16, s_dev, ws)
+    assert I16.is_contiguous() and T16.is_contiguous() and I16.dtype == T16.dtype
+    with _on_device(I16.device) as stream:
+        check(_lib.load().nans_clip_loss_fwd_xchg(_desc_ref(desc), I16.data_ptr(), T16.data_ptr(), dtype_code(I16.dtype),
+                                                  s_dev.data_ptr(), NANS_LOSS_WITH_ACC if with_acc else 0,
+                                                  ws.data_ptr(), ws.numel(), stream))
+    _count(1)
+
+
+def fwd_finalize_push(desc, total_slots: int, s_dev: torch.Tensor, with_acc: bool, ws: torch.Tensor):
+    """fwd_finalize for this rank's rows + push of the packed result into every rank's lse table.
+    Returns (lse2 [2, n_loc], scalars [8]) — the local copies."""
+    n_loc = int(desc.n_loc)
+    pad = (n_loc + 3) // 4 * 4
+    packed = torch.empty((2 * pad + 8,), dtype=torch.float32, device=ws.device)
+    lse = packed[:2 * pad].view(2, pad)[:, :n_loc]
+    scalars = packed[2 * pad:]
+    with _on_device(ws.device) as stream:
+        check(_lib.load().nans_clip_loss_fwd_finalize_push(_desc_ref(desc), total_slots, s_dev.data_ptr(),
+                                                           NANS_LOSS_WITH_ACC if with_acc else 0, ws.data_ptr(),
+                                                           ws.numel(), lse[0].data_ptr(), lse[1].data_ptr(),
+                                                           scalars.data_ptr(), stream))
+    _count(1)
+    return lse, scalars
+
+
+def exchange_finish_xchg(desc, device):
+    """Waits on the device for every rank's packed row, then as exchange_finish.  Returns (lse_all [2, N],
+    out [4], lse_minmax int32 [2], step int32 [1] — the step word the backward takes)."""
+    N = int(desc.world) * int(desc.n_loc)
+    ld = (N + 3) // 4 * 4
+    lse_all = torch.empty((2, ld), dtype=torch.float32, device=device)[:, :N]
+    out = torch.empty((4,), dtype=torch.float32, device=device)
+    mm = torch.empty((2,), dtype=torch.int32, device=device)
+    step = torch.empty((1,), dtype=torch.int32, device=device)
+    with _on_device(device) as stream:
+        check(_lib.load().nans_clip_loss_exchange_finish_xchg(_desc_ref(desc), lse_all.data_ptr(), ld, out.data_ptr(),
+                                                              mm.data_ptr(), step.data_ptr(), stream))
+    _count(1)
+    return lse_all, out, mm, step
+
+
+def bwd_xchg(desc, step: torch.Tensor, I16: torch.Tensor, T16: torch.Tensor, *, s_dev: torch.Tensor,
+             lse_all: torch.Tensor, lse_minmax: torch.Tensor, grad_out: torch.Tensor, grad_mult: float,
+             row_begin: int, row_count: int, out_dtype: torch.dtype):
+    """bwd with the column operands taken from the gathered buffers of the forward's step."""
+    _require_cuda(I16, T16, s_dev, lse_all, grad_out, step, lse_minmax)
+    n_loc, D = I16.shape
+    N = int(desc.world) * n_loc
+    dev = I16.device
+    dI = torch.empty((row_count, D), dtype=out_dtype, device=dev)
+    dT = torch.empty((row_count, D), dtype=out_dtype, device=dev)
+    lib = _lib.load()
+    ws = torch.empty(int(lib.nans_clip_loss_bwd_workspace_bytes(row_count, N, D)), dtype=torch.uint8, device=dev)
+    assert lse_all.shape == (2, N) and lse_all.stride(1) == 1 and lse_all[1].data_ptr() % 16 == 0
+    assert grad_out.dtype == torch.float32 and grad_out.numel() == 1
+    with _on_device(dev) as stream:
+        check(lib.nans_clip_loss_bwd_xchg(_desc_ref(desc), step.data_ptr(), I16.data_ptr(), T16.data_ptr(),
+                                          dtype_code(I16.dtype), s_dev.data_ptr(), lse_all[0].data_ptr(),
+                                          lse_all[1].data_ptr(), lse_minmax.data_ptr(), grad_out.data_ptr(),
+                                          float(grad_mult), row_begin, row_count, dI.data_ptr(), dT.data_ptr(),
+                                          dtype_code(out_dtype), ws.data_ptr(), ws.numel(), stream))
+    _count(1 + (0 if out_dtype == torch.float32 else 2))
+    return dI, dT
+
+
+# --------------------------------------------------------------------------------------------
 # (3b) label smoothing (train_lora.py:95-110)
 # --------------------------------------------------------------------------------------------
 def smooth_stats(I32: torch.Tensor, T32: torch.Tensor) -> torch.Tensor:

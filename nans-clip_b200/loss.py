@@ -27,6 +27,7 @@ from typing import Optional
 import torch
 import torch.distributed as dist
 
+from . import exchange
 from . import kernels as K
 
 
@@ -82,10 +83,41 @@ class _ClipLossFn(torch.autograd.Function):
             raise ValueError("image and text feature blocks must have the same shape")
         N = W * n_loc
         dev = full_img.device
-        I16 = _as_operand(full_img.detach(), cfg.feat_dtype)
-        T16 = _as_operand(full_txt.detach(), cfg.feat_dtype)
         s_dev = s.detach().to(torch.float32).reshape(1).contiguous()
         label_begin = rank * n_loc
+
+        # ---- multi-GPU, NVLink push exchange (exchange.py / csrc/exchange.cu): no collective per step ----
+        ex = exchange.for_group(cfg.group) if (W > 1 and full_img.is_cuda and exchange.eligible(n_loc, D, W)) else None
+        desc = ex.ensure(n_loc, D) if ex is not None else None
+        if desc is not None:
+            I16, T16 = K.xchg_cast_push(desc, full_img.detach(), full_txt.detach(), cfg.feat_dtype)
+            nslots = K.fwd_xchg_slots(n_loc, W, D)
+            ws = K.fwd_workspace(n_loc, nslots, dev)
+            K.fwd_xchg(desc, I16, T16, s_dev, cfg.report_acc, ws)
+            K.fwd_finalize_push(desc, nslots, s_dev, cfg.report_acc, ws)
+            lse_all, res, lse_minmax, step = K.exchange_finish_xchg(desc, dev)
+            ex.forwards += 1
+            loss, dscale, acc_i2t, acc_t2i = res[0], res[1], res[2], res[3]
+            stats = I32 = T32 = None
+            eps = float(cfg.label_smoothing)
+            if eps != 0.0:
+                I32 = full_img.detach().to(torch.float32)
+                T32 = full_txt.detach().to(torch.float32)
+                stats = K.smooth_stats(I32, T32)
+                dist.all_reduce(stats, group=cfg.group)
+                corr = (eps / N) * stats[2 * D] - (eps / (float(N) * N)) * torch.dot(stats[:D], stats[D:2 * D])
+                loss = loss + s_dev[0] * corr
+                dscale = dscale + corr
+            ctx.save_for_backward(I16, T16, step, None, s_dev, lse_all, dscale, stats, I32, T32, lse_minmax)
+            ctx.cfg = cfg
+            ctx.xchg = (ex, desc, ex.forwards)
+            ctx.meta = (W, label_begin, int(row_begin), chunk_img.shape[0], chunk_img.dtype, chunk_txt.dtype)
+            ctx.mark_non_differentiable(acc_i2t, acc_t2i)
+            return loss, acc_i2t, acc_t2i
+        ctx.xchg = None
+
+        I16 = _as_operand(full_img.detach(), cfg.feat_dtype)
+        T16 = _as_operand(full_txt.detach(), cfg.feat_dtype)
 
         # ---- phases of the column sweep -----------------------------------------------------
         # a phase = (T columns, I columns, global index of column 0, skipped range (begin, count),
@@ -180,11 +212,23 @@ class _ClipLossFn(torch.autograd.Function):
             g = g_loss.detach().to(torch.float32).reshape(1).contiguous()
             out_dt = dt_i if (dt_i == dt_t and stats is None) else torch.float32
             mult = float(W) if cfg.gather_with_grad else 1.0
-            dI, dT = K.bwd(I16, T16, T_all, I_all, label_begin=label_begin, s_dev=s_dev,
-                           lse_all=lse_all, grad_out=g, grad_mult=mult,
-                           row_begin=row_begin, row_count=rows, out_dtype=out_dt, lse_minmax=lse_minmax)
+            if ctx.xchg is not None:
+                ex, desc, fwd_no = ctx.xchg
+                if ex.forwards - fwd_no > 1 or ex.shape != (int(desc.n_loc), int(desc.D)):
+                    # the gathered buffers are double-buffered by step: one later forward is fine (its
+                    # features went to the other slot), two are not
+                    raise RuntimeError("push exchange: backward() called after two later forwards of the same "
+                                       "process group overwrote this step's gathered features; call backward "
+                                       "right after the loss (as train.py does) or set NANS_EXCHANGE=nccl")
+                step = I_all   # saved in I_all's place
+                dI, dT = K.bwd_xchg(desc, step, I16, T16, s_dev=s_dev, lse_all=lse_all, lse_minmax=lse_minmax,
+                                    grad_out=g, grad_mult=mult, row_begin=row_begin, row_count=rows, out_dtype=out_dt)
+            else:
+                dI, dT = K.bwd(I16, T16, T_all, I_all, label_begin=label_begin, s_dev=s_dev,
+                               lse_all=lse_all, grad_out=g, grad_mult=mult,
+                               row_begin=row_begin, row_count=rows, out_dtype=out_dt, lse_minmax=lse_minmax)
             if stats is not None:
-                N = T_all.shape[0]
+                N = W * I16.shape[0]
                 K.smooth_bwd(dI, dT, I32[row_begin:row_begin + rows], T32[row_begin:row_begin + rows], stats,
                              s_dev, g, mult * float(cfg.label_smoothing) / N, 1.0 / N)
             dI = dI.to(dt_i) if ctx.needs_input_grad[0] else None

@@ -140,3 +140,83 @@ def test_incremental_accumulate_two_ranks_nccl():
         p.join(timeout=60)
     for rank, ok, info in res:
         assert all(ok), f"rank {rank}: {ok} {info}"
+
+
+def _push_worker(rank, W, port, q):
+    """The NVLink push exchange between REAL ranks (CUDA IPC peer buffers, flag-driven forward): several
+    steps with changing features in both gather modes against the fp64 oracle on the global batch, the
+    NCCL path on the same inputs, and the too-late-backward guard."""
+    try:
+        sys.path.insert(0, str(ROOT))
+        import torch.distributed as dist
+        os.environ["MASTER_ADDR"] = "127.0.0.1"
+        os.environ["MASTER_PORT"] = str(port)
+        torch.cuda.set_device(rank)
+        dev = torch.device("cuda", rank)
+        dist.init_process_group("nccl", rank=rank, world_size=W, device_id=dev)
+        from nans_clip_b200 import exchange
+        from nans_clip_b200.loss import clip_contrastive_loss
+        from oracle import clip_loss as OL
+        ok, info = [], []
+        for n_loc, D, s in ((512, 256, 14.2857), (256, 512, 40.0)):
+            for step in range(3):
+                gwg = step == 1
+                gen = torch.Generator().manual_seed(100 * n_loc + step)
+                base = torch.randn(W * n_loc, D, generator=gen)
+                I = torch.nn.functional.normalize(0.5 * base + 0.5 * torch.randn(W * n_loc, D, generator=gen), dim=-1).half().float()
+                T = torch.nn.functional.normalize(0.5 * base + 0.5 * torch.randn(W * n_loc, D, generator=gen), dim=-1).half().float()
+                want = OL.global_loss_and_grads(I, T, s, torch.float64)
+                sl = slice(rank * n_loc, (rank + 1) * n_loc)
+                outs = {}
+                for mode in ("push", "nccl"):
+                    os.environ["NANS_EXCHANGE"] = mode
+                    a = I[sl].to(dev).requires_grad_(True)
+                    b = T[sl].to(dev).requires_grad_(True)
+                    sc = torch.tensor(s, device=dev, requires_grad=True)
+                    loss, acc = clip_contrastive_loss(a, b, sc, group=dist.group.WORLD, gather_with_grad=gwg, report_acc=True)
+                    loss.backward()
+                    outs[mode] = (float(loss), a.grad.cpu(), b.grad.cpu(), float(sc.grad), float(acc["i2t"]))
+                os.environ["NANS_EXCHANGE"] = "push"
+                ex = exchange.for_group(dist.group.WORLD)
+                ok.append(ex is not None and not ex.broken and ex.shape == (n_loc, D))   # the push path really ran
+                mult = float(W) if gwg else 1.0
+                for mode, (l, dI, dT, ds, a_i2t) in outs.items():
+                    ok.append(abs(l - float(want["loss"])) <= 1e-3 * abs(float(want["loss"])))
+                    ok.append(float((dI.double() - mult * want["dI"][sl]).norm() / (mult * want["dI"][sl]).norm()) < 1e-3)
+                    ok.append(float((dT.double() - mult * want["dT"][sl]).norm() / (mult * want["dT"][sl]).norm()) < 1e-3)
+                    ok.append(abs(ds - float(want["ds"])) <= 1e-3 * abs(float(want["ds"])))
+                    ok.append(abs(a_i2t - float(want["i2t"])) <= 1.5 / (W * n_loc))
+                info.append((n_loc, step, outs["push"][0], outs["nccl"][0], float(want["loss"])))
+        # backward after two later forwards must refuse (the slot was overwritten), not compute garbage
+        a = I[sl].to(dev).requires_grad_(True)
+        first, _ = clip_contrastive_loss(a, T[sl].to(dev), torch.tensor(s, device=dev), group=dist.group.WORLD)
+        for _ in range(2):
+            clip_contrastive_loss(I[sl].to(dev), T[sl].to(dev), torch.tensor(s, device=dev), group=dist.group.WORLD)
+        try:
+            first.backward()
+            ok.append(False)
+        except RuntimeError as exc:
+            ok.append("push exchange" in str(exc))
+        torch.cuda.synchronize()
+        q.put((rank, ok, repr(info)))
+        dist.barrier()
+        dist.destroy_process_group()
+    except Exception:
+        import traceback
+        q.put((rank, [False], traceback.format_exc()))
+
+
+def test_push_exchange_two_ranks():
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_push_worker, args=(r, 2, 29821, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, ok, info in res:
+        assert all(ok), f"rank {rank}: {ok} {info}"
