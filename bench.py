@@ -378,7 +378,18 @@ def loss_step_bench(args, dist, W, rank, dev, n_global, d, with_e2e, kernel_roof
     torch.cuda.synchronize()
     launches_per_step = (K.LAUNCHES - l0) // max(args.warmup, 1)
     run_step, graphed = step, False
-    if args.graph and dist is None:  # NCCL collectives inside a captured step hung at 2 GPUs: 1 GPU only
+    exchange_kind = "none (1 GPU)"
+    push_active = False
+    if dist is not None:
+        from nans_clip_b200 import exchange
+        ex = exchange.for_group(group)
+        push_active = ex is not None and not ex.broken and ex.shape == (n_loc, d)
+        exchange_kind = ("NVLink push into peer-mapped buffers (CUDA IPC), flag-driven forward, no collective per step"
+                         if push_active else "NCCL all-gather (ProcessGroupNCCL), overlapped with the local block")
+    # A whole step (cast + push, forward, lse exchange, backward) is plain kernels on one stream with the
+    # step counter in device memory, so it can be captured once and replayed.  NCCL collectives inside a
+    # captured step hung on this image (round 1), so the NCCL path is timed eagerly.
+    if args.graph and (dist is None or push_active):
         try:
             g = torch.cuda.CUDAGraph()
             side = torch.cuda.Stream()
@@ -388,7 +399,10 @@ def loss_step_bench(args, dist, W, rank, dev, n_global, d, with_e2e, kernel_roof
                     step()
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
-            with torch.cuda.graph(g):
+            if dist is not None:
+                dist.barrier()
+            # thread_local: ProcessGroupNCCL's watchdog thread polls CUDA events while this thread captures
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
                 step()
             torch.cuda.synchronize()
             run_step, graphed = g.replay, True
@@ -397,12 +411,19 @@ def loss_step_bench(args, dist, W, rank, dev, n_global, d, with_e2e, kernel_roof
             torch.cuda.synchronize()
         except Exception as exc:  # fall back to eager launches, say so in the line
             print(f"[bench] CUDA graph capture failed, timing eager launches: {exc!r}", file=sys.stderr)
-            run_step = step
+            run_step, graphed = step, False
+        if dist is not None:   # every rank must time the same thing
+            flag = torch.tensor([1 if graphed else 0], device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if int(flag.item()) == 0:
+                run_step, graphed = step, False
     sampler = ClockSampler(sampler_index).start()
     ms = timed_steps(run_step, args.steps, 0, flush, dist, dev) / args.steps
     clocks = sampler.stop()
     out = {"ms_per_step": ms, "launches_per_step": launches_per_step, "graphed": graphed, "clocks": clocks,
-           "n_loc": n_loc}
+           "n_loc": n_loc, "exchange": exchange_kind}
+    if graphed:   # also the eager number, for the record
+        out["eager_ms_per_step"] = timed_steps(step, args.steps, 2, flush, dist, dev) / args.steps
     if with_e2e:
         img_h, txt_h = img.pin_memory(), txt.pin_memory()
 
@@ -683,6 +704,7 @@ def bench_main(args):
                        "logit_scale": LOGIT_SCALE, "parallelism": f"dp{W}",
                        "l2": "flushed (256 MB write) before every timed step",
                        "launch": "cuda-graph replay of one captured step" if r["graphed"] else "eager",
+                       "exchange": r["exchange"],
                        "step_algorithmic_tflop": step_alg / 1e12},
             "algorithmic_tflops": step_alg / (ms / 1e3) / 1e12,
             # the step is timed alone between L2 flushes (milliseconds): the burst peak is its denominator
@@ -694,6 +716,8 @@ def bench_main(args):
             "roofline": r["roofline"], "roofline_fwd": r["roofline_fwd"],
             "clocks": r["clocks"],
         }
+        if "eager_ms_per_step" in r:
+            line["eager_ms_per_step"] = r["eager_ms_per_step"]
         if pc is not None:
             line["parity_check"] = pc
             if not pc["ok"]:

@@ -158,7 +158,7 @@ def _push_worker(rank, W, port, q):
         from nans_clip_b200.loss import clip_contrastive_loss
         from oracle import clip_loss as OL
         ok, info = [], []
-        for n_loc, D, s in ((512, 256, 14.2857), (256, 512, 40.0)):
+        for n_loc, D, s in ((512, 256, 14.2857), (256, 512, 20.0)):
             for step in range(3):
                 gwg = step == 1
                 gen = torch.Generator().manual_seed(100 * n_loc + step)
@@ -181,10 +181,14 @@ def _push_worker(rank, W, port, q):
                 ok.append(ex is not None and not ex.broken and ex.shape == (n_loc, D))   # the push path really ran
                 mult = float(W) if gwg else 1.0
                 for mode, (l, dI, dT, ds, a_i2t) in outs.items():
-                    ok.append(abs(l - float(want["loss"])) <= 1e-3 * abs(float(want["loss"])))
-                    ok.append(float((dI.double() - mult * want["dI"][sl]).norm() / (mult * want["dI"][sl]).norm()) < 1e-3)
-                    ok.append(float((dT.double() - mult * want["dT"][sl]).norm() / (mult * want["dT"][sl]).norm()) < 1e-3)
-                    ok.append(abs(ds - float(want["ds"])) <= 1e-3 * abs(float(want["ds"])))
+                    # absolute floors as in test_gpu_parity.grad_ok: a saturated softmax (second shape) leaves
+                    # a loss of ~1e-5 and gradients of fp32-rounding size
+                    N = W * n_loc
+                    floor = 3e-5 * s / (2 * N) * (N ** 0.5) * mult
+                    ok.append(abs(l - float(want["loss"])) <= 1e-3 * abs(float(want["loss"])) + 1e-6 * s)
+                    ok.append(float((dI.double() - mult * want["dI"][sl]).norm()) <= 1e-3 * float((mult * want["dI"][sl]).norm()) + floor)
+                    ok.append(float((dT.double() - mult * want["dT"][sl]).norm()) <= 1e-3 * float((mult * want["dT"][sl]).norm()) + floor)
+                    ok.append(abs(ds - float(want["ds"])) <= 1e-3 * abs(float(want["ds"])) + 1e-6)
                     ok.append(abs(a_i2t - float(want["i2t"])) <= 1.5 / (W * n_loc))
                 info.append((n_loc, step, outs["push"][0], outs["nccl"][0], float(want["loss"])))
         # backward after two later forwards must refuse (the slot was overwritten), not compute garbage

@@ -868,13 +868,14 @@ def test_topk_ascending_score_gallery(dev, G):
     D, Q, k = 256, 300, 10
     g = torch.Generator().manual_seed(G)
     u = torch.nn.functional.normalize(torch.randn(D, generator=g), dim=0)
+    w = torch.randn(G, D, generator=g)
+    w = torch.nn.functional.normalize(w - (w @ u)[:, None] * u[None, :], dim=-1)      # unit rows orthogonal to u
     t = torch.linspace(0.0, 0.9, G)[:, None]
-    gal = torch.nn.functional.normalize(t * u[None, :] + 0.05 * torch.nn.functional.normalize(torch.randn(G, D, generator=g), dim=-1), dim=-1)
-    gal = gal.half().float()
+    gal = (t * u[None, :] + torch.sqrt(1 - t * t) * w).half().float()                  # unit rows, cos(u) = t rising
     qry = torch.nn.functional.normalize(u[None, :] + 0.02 * torch.randn(Q, D, generator=g), dim=-1).half().float()
     sc = qry @ gal.t()
-    blk = sc[:, : G // 100 * 100].view(Q, 100, -1).max(dim=2).values   # rising along the sweep: every 1 % block
-    assert bool((blk[:, 1:] > blk[:, :-1]).float().mean() > 0.95)      # of columns beats all earlier ones
+    blk = sc[:, : G // 20 * 20].view(Q, 20, -1).max(dim=2).values   # rising along the sweep: every 5 % block of
+    assert bool((blk[:, 1:] > blk[:, :-1]).all())                    # columns beats all earlier ones
     s, i = K.topk_ip(qry.half().to(dev), gal.half().to(dev), qry.to(dev), gal.to(dev), k, 16, 0)
     check_topk(i.cpu(), s.cpu(), gal, qry, k)
     assert bool((i >= G - 5000).all())   # the winners sit at the end of the sweep
