@@ -72,6 +72,9 @@ _SIGNATURES = {
     "nans_peer_close": (c_int, [c_void_p]),
     "nans_peer_zero": (c_int, [c_void_p, c_size_t, c_void_p]),
     "nans_xchg_layout": (c_int, [c_void_p, c_int64, c_int64]),
+    "nans_xchg_cast_local": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_void_p, c_void_p,
+                                     c_void_p]),
+    "nans_xchg_push": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "nans_xchg_cast_push": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_void_p, c_void_p,
                                     c_void_p]),
     "nans_clip_loss_fwd_xchg_slots": (c_int64, [c_int64, c_int64, c_int64]),

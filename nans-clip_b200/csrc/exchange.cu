@@ -80,62 +80,99 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8], int feat_dtype) {
 }
 
 // grid = (n_loc / 64, 2 modalities); a CTA owns the 64 rows of one arrival flag: 8 warps x 8 rows, a
-// warp moves a row in 16-byte pieces (lane = piece).  Destinations are visited in the order rank,
-// rank - 1, rank - 2, ...; the CTA raises the flag of a destination as soon as ITS 64 rows are there.
+// warp moves a row in 16-byte pieces (lane = piece).
+//
+// PUSH_LOCAL : cast (and optionally normalise) the source rows into the local 16-bit copy and into this
+//              rank's own gathered slot, then raise the own flags.  HBM-bound, a few microseconds; the
+//              forward of this rank is launched behind it on the same stream.
+// PUSH_REMOTE: copy the rows of the local 16-bit copy into the gathered slot of every PEER, destinations
+//              in the order rank - 1, rank - 2, ...; the flag of a destination goes up as soon as this
+//              CTA's 64 rows are there.  NVLink-bound; launched on a side stream so that it runs UNDER
+//              the forward (which polls the peers' flags tile by tile).  It waits for nothing, and its
+//              whole grid is resident before the forward is launched.
+template <bool REMOTE>
 __global__ void __launch_bounds__(PUSH_THREADS) cast_push_kernel(const PushParams p) {
   const int mod = blockIdx.y;
-  const int blk = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t step = *p.epoch + 1u;
   const long long slot = step & 1u;
   const int D = p.D;
   const int esz = p.x_dtype == NANS_F32 ? 4 : 2;
-  // byte offset of this modality's slot, then of global row (rank * n_loc + r) in it
+  // byte offset of this modality's slot; global row (rank * n_loc + r) inside it
   const long long mod_off = p.feat_off + (static_cast<long long>(mod) * 2 + slot) * p.slot_rows * D * 2;
+  const int nblk = p.n_loc / PUSH_ROWS;
 
-  for (int k = 0; k < p.world; ++k) {
-    int dst = p.rank - k;
-    if (dst < 0) dst += p.world;
-    uint8_t* dbase = p.base[dst] + mod_off;
-    for (int i = 0; i < PUSH_ROWS / (PUSH_THREADS / 32); ++i) {
-      const int r = blk * PUSH_ROWS + i * (PUSH_THREADS / 32) + warp;
-      const uint8_t* srow = static_cast<const uint8_t*>(p.src[mod]) + static_cast<long long>(r) * p.ld_x * esz;
-      float inv = 1.0f;
-      if (p.normalize) {
-        float ss = 0.f;
-        for (int e0 = lane * 8; e0 < D; e0 += 256) {
-          float f[8];
-          load8(srow, p.x_dtype, e0, f);
+  for (int blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+    for (int k = REMOTE ? 1 : 0; k < (REMOTE ? p.world : 1); ++k) {
+      int dst = p.rank - k;
+      if (dst < 0) dst += p.world;
+      uint8_t* dbase = p.base[dst] + mod_off;
+      for (int i = 0; i < PUSH_ROWS / (PUSH_THREADS / 32); ++i) {
+        const int r = blk * PUSH_ROWS + i * (PUSH_THREADS / 32) + warp;
+        uint8_t* drow = dbase + (static_cast<long long>(p.rank) * p.n_loc + r) * D * 2;
+        uint8_t* lrow = static_cast<uint8_t*>(p.loc16[mod]) + static_cast<long long>(r) * D * 2;
+        if (REMOTE) {
+          // the 64 rows of this block (64 * D * 2 bytes) stay in L1 across the destination loop
+          for (int e0 = lane * 8; e0 < D; e0 += 256)
+            *reinterpret_cast<uint4*>(drow + e0 * 2) = *reinterpret_cast<const uint4*>(lrow + e0 * 2);
+        } else {
+          const uint8_t* srow = static_cast<const uint8_t*>(p.src[mod]) + static_cast<long long>(r) * p.ld_x * esz;
+          float inv = 1.0f;
+          if (p.normalize) {
+            float ss = 0.f;
+            for (int e0 = lane * 8; e0 < D; e0 += 256) {
+              float f[8];
+              load8(srow, p.x_dtype, e0, f);
 #pragma unroll
-          for (int e = 0; e < 8; ++e) ss = fmaf(f[e], f[e], ss);
-        }
-        inv = 1.0f / sqrtf(warp_sum(ss));  // same arithmetic as l2norm_cast_kernel
-      }
-      uint8_t* drow = dbase + (static_cast<long long>(p.rank) * p.n_loc + r) * D * 2;
-      uint8_t* lrow = static_cast<uint8_t*>(p.loc16[mod]) + static_cast<long long>(r) * D * 2;
-      for (int e0 = lane * 8; e0 < D; e0 += 256) {
-        // the source row is re-read per destination: after the first pass it sits in L1/L2, and holding
-        // a whole 64-row block in registers across the destination loop would cap D
-        float f[8];
-        load8(srow, p.x_dtype, e0, f);
-        if (p.normalize) {
+              for (int e = 0; e < 8; ++e) ss = fmaf(f[e], f[e], ss);
+            }
+            inv = 1.0f / sqrtf(warp_sum(ss));  // same arithmetic as l2norm_cast_kernel
+          }
+          for (int e0 = lane * 8; e0 < D; e0 += 256) {
+            float f[8];
+            load8(srow, p.x_dtype, e0, f);
+            if (p.normalize) {
 #pragma unroll
-          for (int e = 0; e < 8; ++e) f[e] *= inv;
+              for (int e = 0; e < 8; ++e) f[e] *= inv;
+            }
+            const uint4 v = pack8(f, p.feat_dtype);
+            *reinterpret_cast<uint4*>(drow + e0 * 2) = v;
+            *reinterpret_cast<uint4*>(lrow + e0 * 2) = v;
+          }
         }
-        const uint4 v = pack8(f, p.feat_dtype);
-        *reinterpret_cast<uint4*>(drow + e0 * 2) = v;
-        if (k == 0) *reinterpret_cast<uint4*>(lrow + e0 * 2) = v;
       }
-    }
-    // this CTA's 64 rows are on their way to `dst`: order them before the flag at system scope
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      uint32_t* flag = reinterpret_cast<uint32_t*>(p.base[dst] + p.fflag_off) +
-                       (static_cast<long long>(mod) * p.world + p.rank) * (p.n_loc / PUSH_ROWS) + blk;
-      st_release_sys(flag, step);
+      // this CTA's 64 rows are on their way to `dst`: order them before the flag at system scope
+      __threadfence_system();
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        uint32_t* flag = reinterpret_cast<uint32_t*>(p.base[dst] + p.fflag_off) +
+                         (static_cast<long long>(mod) * p.world + p.rank) * nblk + blk;
+        st_release_sys(flag, step);
+      }
     }
   }
+}
+
+int fill_push_params(PushParams& p, const nans_xchg_t* x) {
+  p.n_loc = static_cast<int>(x->n_loc);
+  p.D = static_cast<int>(x->D);
+  p.world = x->world;
+  p.rank = x->rank;
+  p.feat_off = x->feat_off;
+  p.fflag_off = x->fflag_off;
+  p.slot_rows = static_cast<long long>(x->world) * x->n_loc;
+  p.epoch = x->epoch;
+  for (int r = 0; r < NANS_MAX_PEERS; ++r) p.base[r] = r < x->world ? static_cast<uint8_t*>(x->base[r]) : nullptr;
+  return NANS_OK;
+}
+
+int check_xchg(const nans_xchg_t* x, const char* who) {
+  NANS_REQUIRE(x != nullptr && x->world >= 1 && x->world <= NANS_MAX_PEERS && x->rank >= 0 && x->rank < x->world,
+               "%s: bad exchange descriptor", who);
+  NANS_REQUIRE(x->n_loc > 0 && x->n_loc % 256 == 0 && x->D > 0 && x->D % 8 == 0, "%s: bad sizes", who);
+  NANS_REQUIRE(x->epoch != nullptr, "%s: null step counter", who);
+  for (int r = 0; r < x->world; ++r) NANS_REQUIRE(x->base[r] != nullptr, "%s: peer %d is not mapped", who, r);
+  return NANS_OK;
 }
 
 }  // namespace
@@ -216,23 +253,21 @@ extern "C" int nans_xchg_layout(nans_xchg_t* x, int64_t n_loc, int64_t D) {
   return NANS_OK;
 }
 
-extern "C" int nans_xchg_cast_push(const nans_xchg_t* x, const void* img, const void* txt, int x_dtype,
-                                   int64_t ld_x, int feat_dtype, int normalize, void* I16_loc, void* T16_loc,
-                                   void* stream) {
+extern "C" int nans_xchg_cast_local(const nans_xchg_t* x, const void* img, const void* txt, int x_dtype,
+                                    int64_t ld_x, int feat_dtype, int normalize, void* I16_loc, void* T16_loc,
+                                    void* stream) {
   int rc = check_device();
   if (rc != NANS_OK) return rc;
-  NANS_REQUIRE(x != nullptr && x->world >= 1 && x->world <= NANS_MAX_PEERS && x->rank >= 0 && x->rank < x->world,
-               "xchg_cast_push: bad exchange descriptor");
-  NANS_REQUIRE(x_dtype == NANS_F32 || x_dtype == NANS_F16 || x_dtype == NANS_BF16, "xchg_cast_push: bad x_dtype");
-  NANS_REQUIRE(feat_dtype == NANS_F16 || feat_dtype == NANS_BF16, "xchg_cast_push: feat_dtype must be NANS_F16 or NANS_BF16");
-  const int64_t n_loc = x->n_loc, D = x->D;
-  NANS_REQUIRE(n_loc > 0 && n_loc % 256 == 0 && D > 0 && D % 8 == 0 && ld_x >= D, "xchg_cast_push: bad sizes");
-  NANS_REQUIRE(img && txt && I16_loc && T16_loc && x->epoch, "xchg_cast_push: null pointer");
+  if ((rc = check_xchg(x, "xchg_cast_local")) != NANS_OK) return rc;
+  NANS_REQUIRE(x_dtype == NANS_F32 || x_dtype == NANS_F16 || x_dtype == NANS_BF16, "xchg_cast_local: bad x_dtype");
+  NANS_REQUIRE(feat_dtype == NANS_F16 || feat_dtype == NANS_BF16, "xchg_cast_local: feat_dtype must be NANS_F16 or NANS_BF16");
+  NANS_REQUIRE(ld_x >= x->D, "xchg_cast_local: leading dimension smaller than D");
+  NANS_REQUIRE(img && txt && I16_loc && T16_loc, "xchg_cast_local: null pointer");
   NANS_REQUIRE((reinterpret_cast<uintptr_t>(img) & 15) == 0 && (reinterpret_cast<uintptr_t>(txt) & 15) == 0 &&
                    (ld_x * (x_dtype == NANS_F32 ? 4 : 2)) % 16 == 0,
-               "xchg_cast_push: feature rows must be 16-byte aligned");
-  for (int r = 0; r < x->world; ++r) NANS_REQUIRE(x->base[r] != nullptr, "xchg_cast_push: peer %d is not mapped", r);
+               "xchg_cast_local: feature rows must be 16-byte aligned");
   PushParams p;
+  fill_push_params(p, x);
   p.src[0] = img;
   p.src[1] = txt;
   p.loc16[0] = I16_loc;
@@ -240,18 +275,41 @@ extern "C" int nans_xchg_cast_push(const nans_xchg_t* x, const void* img, const 
   p.x_dtype = x_dtype;
   p.feat_dtype = feat_dtype;
   p.normalize = normalize ? 1 : 0;
-  p.n_loc = static_cast<int>(n_loc);
-  p.D = static_cast<int>(D);
   p.ld_x = ld_x;
-  p.world = x->world;
-  p.rank = x->rank;
-  p.feat_off = x->feat_off;
-  p.fflag_off = x->fflag_off;
-  p.slot_rows = static_cast<long long>(x->world) * n_loc;
-  p.epoch = x->epoch;
-  for (int r = 0; r < NANS_MAX_PEERS; ++r) p.base[r] = r < x->world ? static_cast<uint8_t*>(x->base[r]) : nullptr;
-  const dim3 grid(static_cast<unsigned>(n_loc / PUSH_ROWS), 2);
-  cast_push_kernel<<<grid, PUSH_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  const dim3 grid(static_cast<unsigned>(x->n_loc / PUSH_ROWS), 2);
+  cast_push_kernel<false><<<grid, PUSH_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(p);
   NANS_CUDA_OK(cudaGetLastError());
   return NANS_OK;
+}
+
+extern "C" int nans_xchg_push(const nans_xchg_t* x, const void* I16_loc, const void* T16_loc, void* stream) {
+  int rc = check_device();
+  if (rc != NANS_OK) return rc;
+  if ((rc = check_xchg(x, "xchg_push")) != NANS_OK) return rc;
+  NANS_REQUIRE(I16_loc && T16_loc, "xchg_push: null pointer");
+  if (x->world == 1) return NANS_OK;
+  PushParams p;
+  fill_push_params(p, x);
+  p.src[0] = p.src[1] = nullptr;
+  p.loc16[0] = const_cast<void*>(I16_loc);
+  p.loc16[1] = const_cast<void*>(T16_loc);
+  p.x_dtype = p.feat_dtype = NANS_F16;  // unused: 16-bit rows are copied as they are
+  p.normalize = 0;
+  p.ld_x = x->D;
+  // The whole grid must be resident at once (the forward launched behind it may wait for peers whose
+  // own push kernels, in turn, must not be held up by anything): 8 CTAs of 256 threads per SM at most.
+  const int64_t blocks = x->n_loc / PUSH_ROWS;
+  const int64_t cap = static_cast<int64_t>(sm_count()) * 4 / 2;  // per modality; half of what fits
+  const dim3 grid(static_cast<unsigned>(blocks < cap ? blocks : cap), 2);
+  cast_push_kernel<true><<<grid, PUSH_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  NANS_CUDA_OK(cudaGetLastError());
+  return NANS_OK;
+}
+
+extern "C" int nans_xchg_cast_push(const nans_xchg_t* x, const void* img, const void* txt, int x_dtype,
+                                   int64_t ld_x, int feat_dtype, int normalize, void* I16_loc, void* T16_loc,
+                                   void* stream) {
+  int rc = nans_xchg_cast_local(x, img, txt, x_dtype, ld_x, feat_dtype, normalize, I16_loc, T16_loc, stream);
+  if (rc != NANS_OK) return rc;
+  return nans_xchg_push(x, I16_loc, T16_loc, stream);
 }

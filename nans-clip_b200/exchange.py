@@ -80,6 +80,9 @@ class PeerExchange:
         self.desc: Optional[XchgDesc] = None
         self.epoch = torch.zeros(1, dtype=torch.int32, device=self.dev)   # steps completed (device word)
         self.forwards = 0                        # host mirror of the number of forwards issued
+        self.push_stream = torch.cuda.Stream(self.dev)   # the NVLink push runs under the forward
+        self.fork = torch.cuda.Event()
+        self.join = torch.cuda.Event()
         self.broken = False
 
     # ---- allocation / mapping (collective over the group) -------------------------------------

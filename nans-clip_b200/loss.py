@@ -90,12 +90,20 @@ class _ClipLossFn(torch.autograd.Function):
         ex = exchange.for_group(cfg.group) if (W > 1 and full_img.is_cuda and exchange.eligible(n_loc, D, W)) else None
         desc = ex.ensure(n_loc, D) if ex is not None else None
         if desc is not None:
-            I16, T16 = K.xchg_cast_push(desc, full_img.detach(), full_txt.detach(), cfg.feat_dtype)
+            # main stream: cast (local) -> forward -> finalize + lse push -> wait for the peers' lse;
+            # side stream: the NVLink push of the features, launched BEFORE the forward and running under it
+            I16, T16 = K.xchg_cast_local(desc, full_img.detach(), full_txt.detach(), cfg.feat_dtype)
+            main = torch.cuda.current_stream(dev)
+            ex.fork.record(main)
+            ex.push_stream.wait_event(ex.fork)
+            K.xchg_push(desc, I16, T16, stream=ex.push_stream)
+            ex.join.record(ex.push_stream)
             nslots = K.fwd_xchg_slots(n_loc, W, D)
             ws = K.fwd_workspace(n_loc, nslots, dev)
             K.fwd_xchg(desc, I16, T16, s_dev, cfg.report_acc, ws)
             K.fwd_finalize_push(desc, nslots, s_dev, cfg.report_acc, ws)
             lse_all, res, lse_minmax, step = K.exchange_finish_xchg(desc, dev)
+            main.wait_event(ex.join)   # the push has read I16 / T16: they may be reused from here on
             ex.forwards += 1
             loss, dscale, acc_i2t, acc_t2i = res[0], res[1], res[2], res[3]
             stats = I32 = T32 = None

@@ -16,7 +16,7 @@ if W > 1:
     dist.init_process_group("nccl", device_id=dev)
     group = dist.group.WORLD
 n_loc = bench.N_GLOBAL // W
-img, txt = bench.synth_features(n_loc, rank, bench.D)
+img, txt = bench.synth_features(n_loc, rank * n_loc, bench.D)
 I = img.to(dev).requires_grad_(True); T = txt.to(dev).requires_grad_(True)
 s = torch.tensor(bench.LOGIT_SCALE, device=dev, requires_grad=True)
 
