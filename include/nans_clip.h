@@ -275,22 +275,23 @@ int nans_peer_zero(void* ptr, size_t bytes, void* stream);
 /* Fills the layout fields (n_loc, D, *_off, lse_len, bytes) of `x` for a job of x->world ranks. */
 int nans_xchg_layout(nans_xchg_t* x, int64_t n_loc, int64_t D);
 
-/* Kernel (1) fused with the feature exchange, in two launches so that the NVLink traffic runs UNDER the
- * forward:
- *   nans_xchg_cast_local: casts (optionally L2-normalises) this rank's image and text rows to the 16-bit
- *       operand type into a local copy (I16_loc / T16_loc, [n_loc, D] contiguous: the row operand of the
- *       strips) and into slot (step & 1) of this rank's OWN gathered buffers, and raises the own flags.
- *       img / txt: [n_loc, D] of x_dtype (NANS_F32/F16/BF16), row pitch ld_x.  HBM-bound.
- *   nans_xchg_push: copies the local 16-bit rows into the same slot of every PEER's gathered buffers
- *       (plain st.global on peer-mapped memory), peers in the order rank-1, rank-2, ... so that each
- *       destination is served by one source at a time, and raises the peers' flags block by block.
- *       NVLink-bound.  Meant for a SIDE stream, launched BEFORE the forward (which goes on the main
- *       stream behind nans_xchg_cast_local): the forward then consumes remote tiles as they land.  The
- *       caller joins the side stream before the local copies are released or overwritten.
+/* Kernel (1) fused with the feature exchange, in two independent launches so that the NVLink traffic runs
+ * UNDER the forward.  Both read the same source rows img / txt ([n_loc, D] of x_dtype NANS_F32/F16/BF16,
+ * row pitch ld_x) and cast (optionally L2-normalise) them to the 16-bit operand type:
+ *   nans_xchg_cast_local: into a local copy (I16_loc / T16_loc, [n_loc, D] contiguous: the row operand of
+ *       the strips) and into slot (step & 1) of this rank's OWN gathered buffers; raises the own flags.
+ *       HBM-bound, a few microseconds.  Main stream; the forward goes behind it.
+ *   nans_xchg_push: into the same slot of every PEER's gathered buffers (plain st.global on peer-mapped
+ *       memory), peers in the order rank-1, rank-2, ... so that each destination is served by one source
+ *       at a time; raises the peers' flags block by block.  NVLink-bound.  Meant for a SIDE stream that
+ *       forks BEFORE nans_xchg_cast_local is launched: its (capped) grid is then resident before the
+ *       forward's one-CTA-per-SM grid arrives, and the forward consumes remote tiles as they land.  It
+ *       waits for nothing.  The caller joins the side stream before the sources may change.
  *   nans_xchg_cast_push: both on one stream (no overlap; tests, simple callers). */
 int nans_xchg_cast_local(const nans_xchg_t* x, const void* img, const void* txt, int x_dtype, int64_t ld_x,
                          int feat_dtype, int normalize, void* I16_loc, void* T16_loc, void* stream);
-int nans_xchg_push(const nans_xchg_t* x, const void* I16_loc, const void* T16_loc, void* stream);
+int nans_xchg_push(const nans_xchg_t* x, const void* img, const void* txt, int x_dtype, int64_t ld_x,
+                   int feat_dtype, int normalize, void* stream);
 int nans_xchg_cast_push(const nans_xchg_t* x, const void* img, const void* txt, int x_dtype, int64_t ld_x,
                         int feat_dtype, int normalize, void* I16_loc, void* T16_loc, void* stream);
 

@@ -79,17 +79,21 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8], int feat_dtype) {
   return make_uint4(w[0], w[1], w[2], w[3]);
 }
 
-// grid = (n_loc / 64, 2 modalities); a CTA owns the 64 rows of one arrival flag: 8 warps x 8 rows, a
-// warp moves a row in 16-byte pieces (lane = piece).
+// grid = (blocks, 2 modalities); a CTA owns the 64 rows of one arrival flag at a time: 8 warps x 8 rows,
+// a warp moves a row in 16-byte pieces (lane = piece).  Both variants read the SOURCE rows and cast
+// (optionally normalise) them, so neither depends on the other:
 //
-// PUSH_LOCAL : cast (and optionally normalise) the source rows into the local 16-bit copy and into this
-//              rank's own gathered slot, then raise the own flags.  HBM-bound, a few microseconds; the
-//              forward of this rank is launched behind it on the same stream.
-// PUSH_REMOTE: copy the rows of the local 16-bit copy into the gathered slot of every PEER, destinations
-//              in the order rank - 1, rank - 2, ...; the flag of a destination goes up as soon as this
-//              CTA's 64 rows are there.  NVLink-bound; launched on a side stream so that it runs UNDER
-//              the forward (which polls the peers' flags tile by tile).  It waits for nothing, and its
-//              whole grid is resident before the forward is launched.
+// PUSH_LOCAL : into the local 16-bit copy and this rank's own gathered slot, then the own flags.
+//              HBM-bound, a few microseconds; the forward of this rank is launched behind it on the same
+//              stream.
+// PUSH_REMOTE: into the gathered slot of every PEER, destinations in the order rank - 1, rank - 2, ...;
+//              the flag of a destination goes up as soon as this CTA's 64 rows are there.  NVLink-bound;
+//              launched on a side stream that forks BEFORE the local cast, so that its whole (capped) grid
+//              is resident while only the small local-cast kernel runs, and it then runs UNDER the forward,
+//              which polls the peers' flags tile by tile.  It waits for nothing.  (Launched behind the
+//              local cast instead, its CTAs competed with the forward's one-CTA-per-SM grid for residency,
+//              the forward of every rank spun on flags its peers' starved push kernels never raised, and
+//              the bounded waits trapped.)
 template <bool REMOTE>
 __global__ void __launch_bounds__(PUSH_THREADS) cast_push_kernel(const PushParams p) {
   const int mod = blockIdx.y;
@@ -110,35 +114,30 @@ __global__ void __launch_bounds__(PUSH_THREADS) cast_push_kernel(const PushParam
       for (int i = 0; i < PUSH_ROWS / (PUSH_THREADS / 32); ++i) {
         const int r = blk * PUSH_ROWS + i * (PUSH_THREADS / 32) + warp;
         uint8_t* drow = dbase + (static_cast<long long>(p.rank) * p.n_loc + r) * D * 2;
-        uint8_t* lrow = static_cast<uint8_t*>(p.loc16[mod]) + static_cast<long long>(r) * D * 2;
-        if (REMOTE) {
-          // the 64 rows of this block (64 * D * 2 bytes) stay in L1 across the destination loop
-          for (int e0 = lane * 8; e0 < D; e0 += 256)
-            *reinterpret_cast<uint4*>(drow + e0 * 2) = *reinterpret_cast<const uint4*>(lrow + e0 * 2);
-        } else {
-          const uint8_t* srow = static_cast<const uint8_t*>(p.src[mod]) + static_cast<long long>(r) * p.ld_x * esz;
-          float inv = 1.0f;
-          if (p.normalize) {
-            float ss = 0.f;
-            for (int e0 = lane * 8; e0 < D; e0 += 256) {
-              float f[8];
-              load8(srow, p.x_dtype, e0, f);
-#pragma unroll
-              for (int e = 0; e < 8; ++e) ss = fmaf(f[e], f[e], ss);
-            }
-            inv = 1.0f / sqrtf(warp_sum(ss));  // same arithmetic as l2norm_cast_kernel
-          }
+        const uint8_t* srow = static_cast<const uint8_t*>(p.src[mod]) + static_cast<long long>(r) * p.ld_x * esz;
+        float inv = 1.0f;
+        if (p.normalize) {
+          float ss = 0.f;
           for (int e0 = lane * 8; e0 < D; e0 += 256) {
             float f[8];
             load8(srow, p.x_dtype, e0, f);
-            if (p.normalize) {
 #pragma unroll
-              for (int e = 0; e < 8; ++e) f[e] *= inv;
-            }
-            const uint4 v = pack8(f, p.feat_dtype);
-            *reinterpret_cast<uint4*>(drow + e0 * 2) = v;
-            *reinterpret_cast<uint4*>(lrow + e0 * 2) = v;
+            for (int e = 0; e < 8; ++e) ss = fmaf(f[e], f[e], ss);
           }
+          inv = 1.0f / sqrtf(warp_sum(ss));  // same arithmetic as l2norm_cast_kernel
+        }
+        for (int e0 = lane * 8; e0 < D; e0 += 256) {
+          // the source rows of a block are re-read per destination: after the first pass they sit in L1 / L2
+          float f[8];
+          load8(srow, p.x_dtype, e0, f);
+          if (p.normalize) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] *= inv;
+          }
+          const uint4 v = pack8(f, p.feat_dtype);
+          *reinterpret_cast<uint4*>(drow + e0 * 2) = v;
+          if (!REMOTE)
+            *reinterpret_cast<uint4*>(static_cast<uint8_t*>(p.loc16[mod]) + static_cast<long long>(r) * D * 2 + e0 * 2) = v;
         }
       }
       // this CTA's 64 rows are on their way to `dst`: order them before the flag at system scope
@@ -151,6 +150,16 @@ __global__ void __launch_bounds__(PUSH_THREADS) cast_push_kernel(const PushParam
       }
     }
   }
+}
+
+// CTAs per modality.  Both kernels of a step are in flight together and must fit the machine at once
+// (8 CTAs of 256 threads per SM) with room to spare, so that every CTA of the remote push is resident
+// before the forward is launched: local 1.5 per SM, remote 1 per SM (296 CTAs x 256 threads x 16 bytes in
+// flight are far more than NVLink needs).
+unsigned push_grid_x(int64_t n_loc, bool remote) {
+  const int64_t blocks = n_loc / PUSH_ROWS;
+  const int64_t cap = remote ? sm_count() : static_cast<int64_t>(sm_count()) * 3 / 2;
+  return static_cast<unsigned>(blocks < cap ? blocks : cap);
 }
 
 int fill_push_params(PushParams& p, const nans_xchg_t* x) {
@@ -253,19 +262,20 @@ extern "C" int nans_xchg_layout(nans_xchg_t* x, int64_t n_loc, int64_t D) {
   return NANS_OK;
 }
 
-extern "C" int nans_xchg_cast_local(const nans_xchg_t* x, const void* img, const void* txt, int x_dtype,
-                                    int64_t ld_x, int feat_dtype, int normalize, void* I16_loc, void* T16_loc,
-                                    void* stream) {
+static int launch_cast_push(bool remote, const nans_xchg_t* x, const void* img, const void* txt, int x_dtype,
+                            int64_t ld_x, int feat_dtype, int normalize, void* I16_loc, void* T16_loc, void* stream) {
+  const char* who = remote ? "xchg_push" : "xchg_cast_local";
   int rc = check_device();
   if (rc != NANS_OK) return rc;
-  if ((rc = check_xchg(x, "xchg_cast_local")) != NANS_OK) return rc;
-  NANS_REQUIRE(x_dtype == NANS_F32 || x_dtype == NANS_F16 || x_dtype == NANS_BF16, "xchg_cast_local: bad x_dtype");
-  NANS_REQUIRE(feat_dtype == NANS_F16 || feat_dtype == NANS_BF16, "xchg_cast_local: feat_dtype must be NANS_F16 or NANS_BF16");
-  NANS_REQUIRE(ld_x >= x->D, "xchg_cast_local: leading dimension smaller than D");
-  NANS_REQUIRE(img && txt && I16_loc && T16_loc, "xchg_cast_local: null pointer");
+  if ((rc = check_xchg(x, who)) != NANS_OK) return rc;
+  NANS_REQUIRE(x_dtype == NANS_F32 || x_dtype == NANS_F16 || x_dtype == NANS_BF16, "%s: bad x_dtype", who);
+  NANS_REQUIRE(feat_dtype == NANS_F16 || feat_dtype == NANS_BF16, "%s: feat_dtype must be NANS_F16 or NANS_BF16", who);
+  NANS_REQUIRE(ld_x >= x->D, "%s: leading dimension smaller than D", who);
+  NANS_REQUIRE(img && txt && (remote || (I16_loc && T16_loc)), "%s: null pointer", who);
   NANS_REQUIRE((reinterpret_cast<uintptr_t>(img) & 15) == 0 && (reinterpret_cast<uintptr_t>(txt) & 15) == 0 &&
                    (ld_x * (x_dtype == NANS_F32 ? 4 : 2)) % 16 == 0,
-               "xchg_cast_local: feature rows must be 16-byte aligned");
+               "%s: feature rows must be 16-byte aligned", who);
+  if (remote && x->world == 1) return NANS_OK;
   PushParams p;
   fill_push_params(p, x);
   p.src[0] = img;
@@ -276,34 +286,33 @@ extern "C" int nans_xchg_cast_local(const nans_xchg_t* x, const void* img, const
   p.feat_dtype = feat_dtype;
   p.normalize = normalize ? 1 : 0;
   p.ld_x = ld_x;
-  const dim3 grid(static_cast<unsigned>(x->n_loc / PUSH_ROWS), 2);
-  cast_push_kernel<false><<<grid, PUSH_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  const dim3 grid(push_grid_x(x->n_loc, remote), 2);
+  if (remote) {
+    // same shared-memory carve-out as the forward (which takes nearly all of it): an SM does not have to
+    // drain and reconfigure before a forward CTA can join the push CTAs already resident there
+    static bool carveout_set = false;
+    if (!carveout_set) {
+      cudaFuncSetAttribute(cast_push_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                           cudaSharedmemCarveoutMaxShared);
+      carveout_set = true;
+    }
+    cast_push_kernel<true><<<grid, PUSH_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  } else {
+    cast_push_kernel<false><<<grid, PUSH_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  }
   NANS_CUDA_OK(cudaGetLastError());
   return NANS_OK;
 }
 
-extern "C" int nans_xchg_push(const nans_xchg_t* x, const void* I16_loc, const void* T16_loc, void* stream) {
-  int rc = check_device();
-  if (rc != NANS_OK) return rc;
-  if ((rc = check_xchg(x, "xchg_push")) != NANS_OK) return rc;
-  NANS_REQUIRE(I16_loc && T16_loc, "xchg_push: null pointer");
-  if (x->world == 1) return NANS_OK;
-  PushParams p;
-  fill_push_params(p, x);
-  p.src[0] = p.src[1] = nullptr;
-  p.loc16[0] = const_cast<void*>(I16_loc);
-  p.loc16[1] = const_cast<void*>(T16_loc);
-  p.x_dtype = p.feat_dtype = NANS_F16;  // unused: 16-bit rows are copied as they are
-  p.normalize = 0;
-  p.ld_x = x->D;
-  // The whole grid must be resident at once (the forward launched behind it may wait for peers whose
-  // own push kernels, in turn, must not be held up by anything): 8 CTAs of 256 threads per SM at most.
-  const int64_t blocks = x->n_loc / PUSH_ROWS;
-  const int64_t cap = static_cast<int64_t>(sm_count()) * 4 / 2;  // per modality; half of what fits
-  const dim3 grid(static_cast<unsigned>(blocks < cap ? blocks : cap), 2);
-  cast_push_kernel<true><<<grid, PUSH_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(p);
-  NANS_CUDA_OK(cudaGetLastError());
-  return NANS_OK;
+extern "C" int nans_xchg_cast_local(const nans_xchg_t* x, const void* img, const void* txt, int x_dtype,
+                                    int64_t ld_x, int feat_dtype, int normalize, void* I16_loc, void* T16_loc,
+                                    void* stream) {
+  return launch_cast_push(false, x, img, txt, x_dtype, ld_x, feat_dtype, normalize, I16_loc, T16_loc, stream);
+}
+
+extern "C" int nans_xchg_push(const nans_xchg_t* x, const void* img, const void* txt, int x_dtype, int64_t ld_x,
+                              int feat_dtype, int normalize, void* stream) {
+  return launch_cast_push(true, x, img, txt, x_dtype, ld_x, feat_dtype, normalize, nullptr, nullptr, stream);
 }
 
 extern "C" int nans_xchg_cast_push(const nans_xchg_t* x, const void* img, const void* txt, int x_dtype,
@@ -311,5 +320,5 @@ extern "C" int nans_xchg_cast_push(const nans_xchg_t* x, const void* img, const 
                                    void* stream) {
   int rc = nans_xchg_cast_local(x, img, txt, x_dtype, ld_x, feat_dtype, normalize, I16_loc, T16_loc, stream);
   if (rc != NANS_OK) return rc;
-  return nans_xchg_push(x, I16_loc, T16_loc, stream);
+  return nans_xchg_push(x, img, txt, x_dtype, ld_x, feat_dtype, normalize, stream);
 }

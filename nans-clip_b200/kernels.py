@@ -245,14 +245,34 @@ def _desc_ref(desc):
     return ctypes.byref(desc)
 
 
-def xchg_cast_local(desc, img: torch.Tensor, txt: torch.Tensor, feat_dtype: torch.dtype, normalize: bool = False):
-    """Kernel (1) into the local 16-bit copies (returned: I16, T16) and this rank's own gathered slot."""
+def _xchg_sources(desc, img: torch.Tensor, txt: torch.Tensor):
     _require_cuda(img, txt)
     img, txt = _rowmajor(img), _rowmajor(txt)
     n_loc, D = img.shape
     assert txt.shape == (n_loc, D) and img.dtype == txt.dtype and (n_loc, D) == (desc.n_loc, desc.D)
     if img.stride(0) != txt.stride(0):
         img, txt = img.contiguous(), txt.contiguous()
+    return img, txt
+
+
+def xchg_push(desc, img: torch.Tensor, txt: torch.Tensor, feat_dtype: torch.dtype, normalize: bool = False,
+              stream: "torch.cuda.Stream | None" = None):
+    """Kernel (1) into every PEER's gathered slot over NVLink (`stream`: a side stream forked before
+    xchg_cast_local, so that the traffic runs under the forward; default the current stream).  Returns the
+    (possibly re-laid-out) sources it reads: keep them alive until the side stream has been joined."""
+    img, txt = _xchg_sources(desc, img, txt)
+    with _on_device(img.device) as cur:
+        check(_lib.load().nans_xchg_push(_desc_ref(desc), img.data_ptr(), txt.data_ptr(), dtype_code(img.dtype),
+                                         img.stride(0), dtype_code(feat_dtype), 1 if normalize else 0,
+                                         stream.cuda_stream if stream is not None else cur))
+    _count(1 if desc.world > 1 else 0)
+    return img, txt
+
+
+def xchg_cast_local(desc, img: torch.Tensor, txt: torch.Tensor, feat_dtype: torch.dtype, normalize: bool = False):
+    """Kernel (1) into the local 16-bit copies (returned: I16, T16) and this rank's own gathered slot."""
+    img, txt = _xchg_sources(desc, img, txt)
+    n_loc, D = img.shape
     I16 = torch.empty((n_loc, D), dtype=feat_dtype, device=img.device)
     T16 = torch.empty((n_loc, D), dtype=feat_dtype, device=img.device)
     with _on_device(img.device) as stream:
@@ -263,21 +283,10 @@ def xchg_cast_local(desc, img: torch.Tensor, txt: torch.Tensor, feat_dtype: torc
     return I16, T16
 
 
-def xchg_push(desc, I16: torch.Tensor, T16: torch.Tensor, stream: "torch.cuda.Stream | None" = None) -> None:
-    """The local 16-bit rows into every peer's gathered slot over NVLink (`stream`: a side stream so that
-    it runs under the forward; default the current stream)."""
-    _require_cuda(I16, T16)
-    assert I16.is_contiguous() and T16.is_contiguous() and I16.shape == T16.shape == (desc.n_loc, desc.D)
-    with _on_device(I16.device) as cur:
-        check(_lib.load().nans_xchg_push(_desc_ref(desc), I16.data_ptr(), T16.data_ptr(),
-                                         stream.cuda_stream if stream is not None else cur))
-    _count(1 if desc.world > 1 else 0)
-
-
 def xchg_cast_push(desc, img: torch.Tensor, txt: torch.Tensor, feat_dtype: torch.dtype, normalize: bool = False):
     """xchg_cast_local + xchg_push on the current stream (no overlap)."""
     I16, T16 = xchg_cast_local(desc, img, txt, feat_dtype, normalize)
-    xchg_push(desc, I16, T16)
+    xchg_push(desc, img, txt, feat_dtype, normalize)
     return I16, T16
 
 

@@ -21,6 +21,7 @@ loss, accuracy and gradients are invariant to it, so columns stay in rank order 
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 from typing import Optional
 
@@ -90,20 +91,28 @@ class _ClipLossFn(torch.autograd.Function):
         ex = exchange.for_group(cfg.group) if (W > 1 and full_img.is_cuda and exchange.eligible(n_loc, D, W)) else None
         desc = ex.ensure(n_loc, D) if ex is not None else None
         if desc is not None:
-            # main stream: cast (local) -> forward -> finalize + lse push -> wait for the peers' lse;
-            # side stream: the NVLink push of the features, launched BEFORE the forward and running under it
-            I16, T16 = K.xchg_cast_local(desc, full_img.detach(), full_txt.detach(), cfg.feat_dtype)
+            # side stream (forked FIRST, so that its grid is resident before the forward's arrives): the
+            # NVLink push of the features into the peers' buffers, running under the forward;
+            # main stream: cast (local) -> forward -> finalize + lse push -> wait for the peers' lse
+            src_i, src_t = full_img.detach(), full_txt.detach()
             main = torch.cuda.current_stream(dev)
-            ex.fork.record(main)
-            ex.push_stream.wait_event(ex.fork)
-            K.xchg_push(desc, I16, T16, stream=ex.push_stream)
-            ex.join.record(ex.push_stream)
+            if os.environ.get("NANS_PUSH_OVERLAP", "1") != "0":
+                ex.fork.record(main)
+                ex.push_stream.wait_event(ex.fork)
+                keep = K.xchg_push(desc, src_i, src_t, cfg.feat_dtype, stream=ex.push_stream)
+                ex.join.record(ex.push_stream)
+                I16, T16 = K.xchg_cast_local(desc, src_i, src_t, cfg.feat_dtype)
+            else:   # serial: push, then forward (no two kernels of this rank ever have to co-reside)
+                I16, T16 = K.xchg_cast_push(desc, src_i, src_t, cfg.feat_dtype)
+                keep = None
             nslots = K.fwd_xchg_slots(n_loc, W, D)
             ws = K.fwd_workspace(n_loc, nslots, dev)
             K.fwd_xchg(desc, I16, T16, s_dev, cfg.report_acc, ws)
             K.fwd_finalize_push(desc, nslots, s_dev, cfg.report_acc, ws)
             lse_all, res, lse_minmax, step = K.exchange_finish_xchg(desc, dev)
-            main.wait_event(ex.join)   # the push has read I16 / T16: they may be reused from here on
+            if keep is not None:
+                main.wait_event(ex.join)   # the push has read its sources: they may change from here on
+                del keep
             ex.forwards += 1
             loss, dscale, acc_i2t, acc_t2i = res[0], res[1], res[2], res[3]
             stats = I32 = T32 = None
