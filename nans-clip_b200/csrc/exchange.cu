@@ -95,7 +95,7 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8], int feat_dtype) {
 //              the forward of every rank spun on flags its peers' starved push kernels never raised, and
 //              the bounded waits trapped.)
 template <bool REMOTE>
-__global__ void __launch_bounds__(PUSH_THREADS) cast_push_kernel(const PushParams p) {
+__global__ void __launch_bounds__(PUSH_THREADS, 4) cast_push_kernel(const PushParams p) {
   const int mod = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t step = *p.epoch + 1u;
@@ -106,59 +106,78 @@ __global__ void __launch_bounds__(PUSH_THREADS) cast_push_kernel(const PushParam
   const long long mod_off = p.feat_off + (static_cast<long long>(mod) * 2 + slot) * p.slot_rows * D * 2;
   const int nblk = p.n_loc / PUSH_ROWS;
 
+  constexpr int RPW = PUSH_ROWS / (PUSH_THREADS / 32);  // rows per warp: 8, rows warp, warp + 8, ...
+  constexpr int RIF = 4;                                // rows in flight per warp (32 registers of payload)
   for (int blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+    const int r0 = blk * PUSH_ROWS + warp;
+    const uint8_t* srow0 = static_cast<const uint8_t*>(p.src[mod]) + static_cast<long long>(r0) * p.ld_x * esz;
+    const long long sstep = static_cast<long long>(PUSH_THREADS / 32) * p.ld_x * esz;  // bytes between a warp's rows
+    float inv[RPW];
+#pragma unroll
+    for (int i = 0; i < RPW; ++i) inv[i] = 1.0f;
+    if (p.normalize) {
+#pragma unroll
+      for (int i = 0; i < RPW; ++i) {
+        float ss = 0.f;
+        for (int e0 = lane * 8; e0 < D; e0 += 256) {
+          float f[8];
+          load8(srow0 + i * sstep, p.x_dtype, e0, f);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) ss = fmaf(f[e], f[e], ss);
+        }
+        inv[i] = 1.0f / sqrtf(warp_sum(ss));  // same arithmetic as l2norm_cast_kernel
+      }
+    }
     for (int k = REMOTE ? 1 : 0; k < (REMOTE ? p.world : 1); ++k) {
       int dst = p.rank - k;
       if (dst < 0) dst += p.world;
-      uint8_t* dbase = p.base[dst] + mod_off;
-      for (int i = 0; i < PUSH_ROWS / (PUSH_THREADS / 32); ++i) {
-        const int r = blk * PUSH_ROWS + i * (PUSH_THREADS / 32) + warp;
-        uint8_t* drow = dbase + (static_cast<long long>(p.rank) * p.n_loc + r) * D * 2;
-        const uint8_t* srow = static_cast<const uint8_t*>(p.src[mod]) + static_cast<long long>(r) * p.ld_x * esz;
-        float inv = 1.0f;
-        if (p.normalize) {
-          float ss = 0.f;
-          for (int e0 = lane * 8; e0 < D; e0 += 256) {
-            float f[8];
-            load8(srow, p.x_dtype, e0, f);
+      uint8_t* drow0 = p.base[dst] + mod_off + (static_cast<long long>(p.rank) * p.n_loc + r0) * D * 2;
+      uint8_t* lrow0 = REMOTE ? nullptr : static_cast<uint8_t*>(p.loc16[mod]) + static_cast<long long>(r0) * D * 2;
+      const long long dstep = static_cast<long long>(PUSH_THREADS / 32) * D * 2;
 #pragma unroll
-            for (int e = 0; e < 8; ++e) ss = fmaf(f[e], f[e], ss);
-          }
-          inv = 1.0f / sqrtf(warp_sum(ss));  // same arithmetic as l2norm_cast_kernel
-        }
+      for (int ib = 0; ib < RPW; ib += RIF) {
         for (int e0 = lane * 8; e0 < D; e0 += 256) {
-          // the source rows of a block are re-read per destination: after the first pass they sit in L1 / L2
-          float f[8];
-          load8(srow, p.x_dtype, e0, f);
-          if (p.normalize) {
+          // RIF of the warp's rows in flight at once (the loop is latency-bound otherwise); the source
+          // rows are re-read per destination: after the first pass they sit in L1 / L2
+          float f[RIF][8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) f[e] *= inv;
+          for (int i = 0; i < RIF; ++i) load8(srow0 + (ib + i) * sstep, p.x_dtype, e0, f[i]);
+#pragma unroll
+          for (int i = 0; i < RIF; ++i) {
+            if (p.normalize) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) f[i][e] *= inv[ib + i];
+            }
+            const uint4 v = pack8(f[i], p.feat_dtype);
+            *reinterpret_cast<uint4*>(drow0 + (ib + i) * dstep + e0 * 2) = v;
+            if (!REMOTE) *reinterpret_cast<uint4*>(lrow0 + (ib + i) * dstep + e0 * 2) = v;
           }
-          const uint4 v = pack8(f, p.feat_dtype);
-          *reinterpret_cast<uint4*>(drow + e0 * 2) = v;
-          if (!REMOTE)
-            *reinterpret_cast<uint4*>(static_cast<uint8_t*>(p.loc16[mod]) + static_cast<long long>(r) * D * 2 + e0 * 2) = v;
         }
       }
-      // this CTA's 64 rows are on their way to `dst`: order them before the flag at system scope
-      __threadfence_system();
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        uint32_t* flag = reinterpret_cast<uint32_t*>(p.base[dst] + p.fflag_off) +
-                         (static_cast<long long>(mod) * p.world + p.rank) * nblk + blk;
-        st_release_sys(flag, step);
+      if (REMOTE) {
+        // This CTA's 64 rows are on their way to `dst`.  The barrier orders every thread's stores before
+        // thread 0, whose release store at system scope is cumulative over them: one fence per (CTA,
+        // destination) instead of one per thread (256 membar.sys per block made the kernel 4x slower).
+        __syncthreads();
+        if (threadIdx.x == 0) {
+          uint32_t* flag = reinterpret_cast<uint32_t*>(p.base[dst] + p.fflag_off) +
+                           (static_cast<long long>(mod) * p.world + p.rank) * nblk + blk;
+          st_release_sys(flag, step);
+        }
       }
+      // LOCAL: no flag — the forward of this rank is launched behind this kernel on the same stream and
+      // never polls its own rank's tiles
     }
   }
 }
 
 // CTAs per modality.  Both kernels of a step are in flight together and must fit the machine at once
-// (8 CTAs of 256 threads per SM) with room to spare, so that every CTA of the remote push is resident
-// before the forward is launched: local 1.5 per SM, remote 1 per SM (296 CTAs x 256 threads x 16 bytes in
-// flight are far more than NVLink needs).
+// (4 CTAs of 256 threads x <= 64 registers per SM) with room to spare, so that every CTA of the remote push
+// is resident before the forward is launched: local 1 per SM per modality, remote 1 per 2 SMs per modality
+// (148 CTAs x 256 threads x 4 rows x 16 bytes in flight are far more than NVLink needs).
 unsigned push_grid_x(int64_t n_loc, bool remote) {
   const int64_t blocks = n_loc / PUSH_ROWS;
-  const int64_t cap = remote ? sm_count() : static_cast<int64_t>(sm_count()) * 3 / 2;
+  const int64_t cap = remote ? sm_count() / 2 : sm_count();
   return static_cast<unsigned>(blocks < cap ? blocks : cap);
 }
 

@@ -317,10 +317,11 @@ __global__ void __launch_bounds__(256) clip_fwd_finalize_kernel(const FinParams 
   }
   // every thread's stores (block partials; in push mode also the lse values written into the peers'
   // tables) are made visible — at system scope when they crossed NVLink — before this block is counted
-  if (p.xw > 0) __threadfence_system();
-  else __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) {
+    // cumulative over the block's stores (ordered before this thread by the barrier): one fence per block
+    if (p.xw > 0) __threadfence_system();
+    else __threadfence();
     const unsigned done = atomicAdd(p.counter, 1u);
     is_last = (done == gridDim.x - 1);
   }
@@ -343,10 +344,10 @@ __global__ void __launch_bounds__(256) clip_fwd_finalize_kernel(const FinParams 
     if (threadIdx.x == 0) *p.counter = 0;
     if (p.xw > 0) {
       // all blocks' pushes happen-before their counter increment (fence.sys above), which this block
-      // observed; its own scalar pushes are fenced here: then one release store per peer raises the flag
-      __threadfence_system();
+      // observed; its own scalar pushes are ordered by the barrier before the release stores (one per peer)
       __syncthreads();
       if (threadIdx.x < p.xw) {
+        __threadfence_system();
         const uint32_t step = *p.xepoch + 1u;
         uint32_t* flag = reinterpret_cast<uint32_t*>(p.xbase[threadIdx.x] + p.xlflag_off) + p.xrank;
         st_release_sys(flag, step);
@@ -367,16 +368,21 @@ __global__ void __launch_bounds__(256) clip_fwd_finalize_kernel(const FinParams 
 // own lse table, filled by the peers' finalize kernels over NVLink; the block first waits for the W
 // arrival flags of step *epoch + 1, reads the slot of that step, and at the end publishes the step
 // (step_out for this call's backward, *epoch for the next forward).
+// Several blocks (gridDim.x <= 32) share the copy; `scratch` (null for one block) is a zero-initialised
+// counter word followed, at word 2, by one (min, max) pair per block: the last block to finish reduces them.
 __global__ void __launch_bounds__(1024) clip_exchange_finish_kernel(const float* __restrict__ gathered, int W,
                                                                     int n_loc, int pad, float* __restrict__ lse_all,
                                                                     long long ld, float* __restrict__ out,
                                                                     int* __restrict__ minmax,
                                                                     const uint32_t* __restrict__ lflags,
                                                                     uint32_t* __restrict__ epoch,
-                                                                    uint32_t* __restrict__ step_out) {
+                                                                    uint32_t* __restrict__ step_out,
+                                                                    uint32_t* __restrict__ scratch) {
   __shared__ float slo[32], shi[32];
+  __shared__ bool is_last;
   const long long L = 2ll * pad + 8;
   const int total = W * n_loc;
+  const int nb = gridDim.x;
   uint32_t step = 0;
   if (lflags != nullptr) {
     step = *epoch + 1u;
@@ -387,8 +393,8 @@ __global__ void __launch_bounds__(1024) clip_exchange_finish_kernel(const float*
   float lo = INFINITY, hi = -INFINITY;
 #pragma unroll
   for (int strip = 0; strip < 2; ++strip) {
-#pragma unroll 8
-    for (int idx = threadIdx.x; idx < total; idx += 1024) {
+#pragma unroll 4
+    for (int idx = blockIdx.x * 1024 + threadIdx.x; idx < total; idx += nb * 1024) {
       const int rank = idx / n_loc;
       const int row = idx - rank * n_loc;
       const float v = __ldcg(gathered + rank * L + static_cast<long long>(strip) * pad + row);  // L2: peer-written
@@ -415,6 +421,30 @@ __global__ void __launch_bounds__(1024) clip_exchange_finish_kernel(const float*
       lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
       hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
     }
+  }
+  if (nb > 1) {
+    float* part = reinterpret_cast<float*>(scratch + 2);
+    if (threadIdx.x == 0) {
+      part[2 * blockIdx.x] = lo;
+      part[2 * blockIdx.x + 1] = hi;
+      __threadfence();
+      is_last = atomicAdd(scratch, 1u) == static_cast<unsigned>(nb - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    if (threadIdx.x < 32) {
+      lo = threadIdx.x < nb ? *(volatile float*)&part[2 * threadIdx.x] : INFINITY;
+      hi = threadIdx.x < nb ? *(volatile float*)&part[2 * threadIdx.x + 1] : -INFINITY;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+      }
+      if (threadIdx.x == 0) *scratch = 0;
+    }
+  }
+  if (threadIdx.x < 32) {
     // lanes 0..5: sum of partial scalar k over the ranks, in rank order (deterministic)
     float sum = 0.f;
     if (threadIdx.x < 6)
@@ -871,7 +901,7 @@ extern "C" int nans_clip_loss_exchange_finish(const float* gathered, int64_t wor
   NANS_REQUIRE(gathered && lse_all && out && lse_minmax, "loss_exchange_finish: null pointer");
   clip_exchange_finish_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(
       gathered, static_cast<int>(world), static_cast<int>(n_loc), static_cast<int>(pad), lse_all,
-      static_cast<long long>(ld), out, lse_minmax, nullptr, nullptr, nullptr);
+      static_cast<long long>(ld), out, lse_minmax, nullptr, nullptr, nullptr, nullptr);
   NANS_CUDA_OK(cudaGetLastError());
   return NANS_OK;
 }
@@ -888,10 +918,15 @@ extern "C" int nans_clip_loss_exchange_finish_xchg(const nans_xchg_t* x, float* 
                "loss_exchange_finish_xchg: bad sizes");
   NANS_REQUIRE(lse_all && out && lse_minmax && step_out, "loss_exchange_finish_xchg: null pointer");
   uint8_t* own = static_cast<uint8_t*>(x->base[x->rank]);
-  clip_exchange_finish_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(
+  // the flag words take the first 64 bytes of their 1 KB region; words 64.. are this kernel's scratch
+  // (block counter + per-block min / max), zero from the allocation and reset by the kernel itself
+  const int64_t total = x->world * x->n_loc;
+  const unsigned nb = static_cast<unsigned>(total >= 16384 ? 16 : (total >= 4096 ? 4 : 1));
+  uint32_t* scratch = reinterpret_cast<uint32_t*>(own + x->lflag_off) + 64;
+  clip_exchange_finish_kernel<<<nb, 1024, 0, static_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const float*>(own + x->lse_off), x->world, static_cast<int>(x->n_loc), static_cast<int>(pad),
       lse_all, static_cast<long long>(ld), out, lse_minmax, reinterpret_cast<const uint32_t*>(own + x->lflag_off),
-      x->epoch, step_out);
+      x->epoch, step_out, nb > 1 ? scratch : nullptr);
   NANS_CUDA_OK(cudaGetLastError());
   return NANS_OK;
 }

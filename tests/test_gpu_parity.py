@@ -691,7 +691,7 @@ def test_rank_strip_at_bench_sizes(dev, W, rank, n_loc, d, chunk):
 
 @pytest.mark.parametrize("W,n_loc,d,s,in_dt", [(2, 256, 128, 20.0, torch.float32), (4, 512, 512, 14.2857, torch.float32),
                                                (8, 256, 72, 50.0, torch.float16), (3, 768, 768, 14.2857, torch.float32),
-                                               (2, 256, 1024, 5.0, torch.bfloat16)])
+                                               (2, 256, 1024, 5.0, torch.bfloat16), (4, 1024, 64, 14.2857, torch.float32)])
 def test_push_exchange_emulated_ranks(dev, W, n_loc, d, s, in_dt):
     """The NVLink push data plane (csrc/exchange.cu + the exchange modes of kernels (2)/(3)) with the W
     ranks of a job EMULATED one after the other on this GPU: W exchange buffers in one process stand for
