@@ -384,14 +384,15 @@ def loss_step_bench(args, dist, W, rank, dev, n_global, d, with_e2e, kernel_roof
         from nans_clip_b200 import exchange
         ex = exchange.for_group(group)
         push_active = ex is not None and not ex.broken and ex.shape == (n_loc, d)
-        exchange_kind = ("NVLink push into peer-mapped buffers (CUDA IPC), flag-driven forward, no collective per step"
+        exchange_kind = ("NVLink push into peer-mapped buffers (CUDA IPC; rows and flags by copy-engine copies under "
+                         "the forward), flag-driven forward, no collective per step"
                          if push_active else "NCCL all-gather (ProcessGroupNCCL), overlapped with the local block")
     # A whole step (cast + push, forward, lse exchange, backward) is plain kernels on one stream with the
     # step counter in device memory, so it can be captured once and replayed.  NCCL collectives inside a
     # captured step hung on this image (round 1), so the NCCL path is timed eagerly.
+    graphs = []
     if args.graph and (dist is None or push_active):
         try:
-            g = torch.cuda.CUDAGraph()
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
@@ -401,27 +402,40 @@ def loss_step_bench(args, dist, W, rank, dev, n_global, d, with_e2e, kernel_roof
             torch.cuda.synchronize()
             if dist is not None:
                 dist.barrier()
-            # thread_local: ProcessGroupNCCL's watchdog thread polls CUDA events while this thread captures
-            with torch.cuda.graph(g, capture_error_mode="thread_local"):
-                step()
+            # The push exchange double-buffers by step parity and its copy-engine copies carry host
+            # addresses, so ONE captured step is only valid for every other step: two graphs are captured
+            # (even step, odd step) and replayed alternately, each still ONE step between flush and events.
+            # thread_local: ProcessGroupNCCL's watchdog thread polls CUDA events while this thread captures.
+            for _ in range(2 if push_active else 1):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                    step()
+                graphs.append(g)
             torch.cuda.synchronize()
-            run_step, graphed = g.replay, True
-            for _ in range(2):
-                run_step()
-            torch.cuda.synchronize()
+            graphed = True
         except Exception as exc:  # fall back to eager launches, say so in the line
             print(f"[bench] CUDA graph capture failed, timing eager launches: {exc!r}", file=sys.stderr)
-            run_step, graphed = step, False
+            graphs, graphed = [], False
         if dist is not None:   # every rank must time the same thing
             flag = torch.tensor([1 if graphed else 0], device=dev)
             dist.all_reduce(flag, op=dist.ReduceOp.MIN)
             if int(flag.item()) == 0:
-                run_step, graphed = step, False
+                graphs, graphed = [], False
+    replayed = [0]
+    if graphed:
+        def run_step():
+            graphs[replayed[0] % len(graphs)].replay()
+            replayed[0] += 1
+        for _ in range(2):
+            run_step()
+        torch.cuda.synchronize()
     sampler = ClockSampler(sampler_index).start()
     ms = timed_steps(run_step, args.steps, 0, flush, dist, dev) / args.steps
     clocks = sampler.stop()
+    if graphed and len(graphs) == 2 and replayed[0] % 2:
+        run_step()   # leave the exchange on the parity the host expects for the eager steps that follow
     out = {"ms_per_step": ms, "launches_per_step": launches_per_step, "graphed": graphed, "clocks": clocks,
-           "n_loc": n_loc, "exchange": exchange_kind}
+           "n_loc": n_loc, "exchange": exchange_kind, "graphs": len(graphs)}
     if graphed:   # also the eager number, for the record
         out["eager_ms_per_step"] = timed_steps(step, args.steps, 2, flush, dist, dev) / args.steps
     if with_e2e:
@@ -703,7 +717,9 @@ def bench_main(args):
                        "global_batch": N_GLOBAL, "D": D, "operand_dtype": "fp16 (fp32 accumulate)",
                        "logit_scale": LOGIT_SCALE, "parallelism": f"dp{W}",
                        "l2": "flushed (256 MB write) before every timed step",
-                       "launch": "cuda-graph replay of one captured step" if r["graphed"] else "eager",
+                       "launch": ("cuda-graph replay, one captured step per launch" +
+                                  (" (two graphs, even / odd step of the double-buffered exchange, alternating)"
+                                   if r["graphs"] == 2 else "") if r["graphed"] else "eager"),
                        "exchange": r["exchange"],
                        "step_algorithmic_tflop": step_alg / 1e12},
             "algorithmic_tflops": step_alg / (ms / 1e3) / 1e12,
@@ -798,10 +814,15 @@ def main():
     ap.add_argument("--contract-test-n", type=int, default=0,
                     help="tests/test_bench_contract.py only: reference arm at a reduced global batch (the line's "
                          "config.workload says so); never used by a measurement")
-    ap.add_argument("--graph", action="store_true", help="1 GPU only: time a CUDA-graph replay of the step (value only)")
+    ap.add_argument("--graph", dest="graph", action="store_true", default=None,
+                    help="time CUDA-graph replays of the captured step (default at N > 1 when the push exchange is "
+                         "active: the step is launch-bound there; the eager time is reported beside it)")
+    ap.add_argument("--no-graph", dest="graph", action="store_false")
     args = ap.parse_args()
     if args.workload and not args.only:
         args.only = args.workload
+    if args.graph is None:
+        args.graph = int(os.environ.get("WORLD_SIZE", "1")) > 1
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference_arm(args)

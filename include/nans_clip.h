@@ -295,6 +295,21 @@ int nans_xchg_push(const nans_xchg_t* x, const void* img, const void* txt, int x
 int nans_xchg_cast_push(const nans_xchg_t* x, const void* img, const void* txt, int x_dtype, int64_t ld_x,
                         int feat_dtype, int normalize, void* I16_loc, void* T16_loc, void* stream);
 
+/* The same exchange with the remote half on the COPY ENGINES (the default of the python layer): no SM
+ * takes part in the NVLink traffic, so it neither slows the forward it runs under nor depends on being
+ * co-resident with it.
+ *   nans_xchg_cast_local_dma: nans_xchg_cast_local into ONE buffer loc16 = [2][n_loc][D] (image rows, then
+ *       text rows) plus the flag source stepvals[2][n_loc / 64] (each word = this step's number).
+ *   nans_xchg_push_dma: per peer (rank-1, rank-2, ...) two cudaMemcpy2DAsync on `stream` (a side stream
+ *       behind the local cast): the rows into the peer's slot, then the flag words into its flag table.
+ * `slot` = the HOST's parity of this forward ((forwards issued before + 1) & 1): copy destinations are
+ * host addresses.  The kernels use the device's step counter; nans_xchg_cast_local_dma traps when the two
+ * disagree (a CUDA graph holding an ODD number of steps was replayed) instead of reading a stale slot. */
+int nans_xchg_cast_local_dma(const nans_xchg_t* x, const void* img, const void* txt, int x_dtype, int64_t ld_x,
+                             int feat_dtype, int normalize, void* loc16, uint32_t* stepvals, int slot,
+                             void* stream);
+int nans_xchg_push_dma(const nans_xchg_t* x, const void* loc16, const uint32_t* stepvals, int slot, void* stream);
+
 /* Kernel (2) over the gathered buffers: both strips of this rank against all world * n_loc columns in
  * ONE launch.  Every unit walks the column tiles source by source starting with its own rank's (local,
  * already there) and waits for a tile's flags right before its TMA loads.  Fills workspace slots

@@ -15,6 +15,7 @@
 // Roofline: NVLink.  Bytes that must cross the link per rank and step: 2 modalities x (world - 1) x
 // n_loc x D x 2 B (56 MiB at world 8, n_loc 4096, D 512: 76 us at the measured 770 GB/s per direction),
 // hidden behind the forward, which needs 2 x that time for the same columns.
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -35,6 +36,8 @@ struct PushParams {
   long long feat_off, fflag_off;
   long long slot_rows;  // world * n_loc
   const uint32_t* epoch;
+  uint32_t* stepvals;   // LOCAL variant: [2][n_loc / 64] words = this step's number (source of the DMA'd flags)
+  int expect_slot;      // LOCAL variant: the slot the host issued this step's DMA copies for, or -1
   uint8_t* base[NANS_MAX_PEERS];
 };
 
@@ -108,6 +111,15 @@ __global__ void __launch_bounds__(PUSH_THREADS, 4) cast_push_kernel(const PushPa
 
   constexpr int RPW = PUSH_ROWS / (PUSH_THREADS / 32);  // rows per warp: 8, rows warp, warp + 8, ...
   constexpr int RIF = 4;                                // rows in flight per warp (32 registers of payload)
+  if (!REMOTE) {
+    // The host addresses the DMA copies of this step (nans_xchg_push_dma) by ITS count of forwards; the
+    // kernels address the slot by the device's.  They differ when a CUDA graph with an odd number of steps
+    // is replayed: fail loudly instead of reading the wrong slot.
+    if (p.expect_slot >= 0 && static_cast<int>(slot) != p.expect_slot) __trap();
+    if (p.stepvals != nullptr)
+      for (int b = blockIdx.x * PUSH_THREADS + threadIdx.x; b < nblk; b += gridDim.x * PUSH_THREADS)
+        p.stepvals[mod * nblk + b] = step;
+  }
   for (int blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
     const int r0 = blk * PUSH_ROWS + warp;
     const uint8_t* srow0 = static_cast<const uint8_t*>(p.src[mod]) + static_cast<long long>(r0) * p.ld_x * esz;
@@ -177,7 +189,10 @@ __global__ void __launch_bounds__(PUSH_THREADS, 4) cast_push_kernel(const PushPa
 // (148 CTAs x 256 threads x 4 rows x 16 bytes in flight are far more than NVLink needs).
 unsigned push_grid_x(int64_t n_loc, bool remote) {
   const int64_t blocks = n_loc / PUSH_ROWS;
-  const int64_t cap = remote ? sm_count() / 2 : sm_count();
+  int64_t cap = remote ? sm_count() / 2 : sm_count();
+  if (remote) {
+    if (const char* e = getenv("NANS_PUSH_CTAS")) cap = atoi(e) > 0 ? atoi(e) : cap;  // bring-up: CTAs per modality
+  }
   return static_cast<unsigned>(blocks < cap ? blocks : cap);
 }
 
@@ -282,7 +297,8 @@ extern "C" int nans_xchg_layout(nans_xchg_t* x, int64_t n_loc, int64_t D) {
 }
 
 static int launch_cast_push(bool remote, const nans_xchg_t* x, const void* img, const void* txt, int x_dtype,
-                            int64_t ld_x, int feat_dtype, int normalize, void* I16_loc, void* T16_loc, void* stream) {
+                            int64_t ld_x, int feat_dtype, int normalize, void* I16_loc, void* T16_loc, void* stream,
+                            uint32_t* stepvals = nullptr, int expect_slot = -1) {
   const char* who = remote ? "xchg_push" : "xchg_cast_local";
   int rc = check_device();
   if (rc != NANS_OK) return rc;
@@ -305,6 +321,8 @@ static int launch_cast_push(bool remote, const nans_xchg_t* x, const void* img, 
   p.feat_dtype = feat_dtype;
   p.normalize = normalize ? 1 : 0;
   p.ld_x = ld_x;
+  p.stepvals = stepvals;
+  p.expect_slot = expect_slot;
   const dim3 grid(push_grid_x(x->n_loc, remote), 2);
   if (remote) {
     // same shared-memory carve-out as the forward (which takes nearly all of it): an SM does not have to
@@ -340,4 +358,48 @@ extern "C" int nans_xchg_cast_push(const nans_xchg_t* x, const void* img, const 
   int rc = nans_xchg_cast_local(x, img, txt, x_dtype, ld_x, feat_dtype, normalize, I16_loc, T16_loc, stream);
   if (rc != NANS_OK) return rc;
   return nans_xchg_push(x, img, txt, x_dtype, ld_x, feat_dtype, normalize, stream);
+}
+
+// ---- the feature push on the COPY ENGINES -----------------------------------------------------------
+// nans_xchg_cast_local_dma: nans_xchg_cast_local into ONE local buffer loc16 = [2 modalities][n_loc][D]
+// (image rows, then text rows), plus the flag source stepvals[2][n_loc / 64] (every word = this step's
+// number).  `slot` is the host's parity of this forward (number of forwards issued before it + 1, & 1);
+// the kernel traps if the device's step counter disagrees (see cast_push_kernel).
+extern "C" int nans_xchg_cast_local_dma(const nans_xchg_t* x, const void* img, const void* txt, int x_dtype,
+                                        int64_t ld_x, int feat_dtype, int normalize, void* loc16,
+                                        uint32_t* stepvals, int slot, void* stream) {
+  NANS_REQUIRE(x != nullptr && loc16 != nullptr && stepvals != nullptr && (slot == 0 || slot == 1),
+               "xchg_cast_local_dma: bad arguments");
+  uint8_t* l = static_cast<uint8_t*>(loc16);
+  return launch_cast_push(false, x, img, txt, x_dtype, ld_x, feat_dtype, normalize, l,
+                          l + static_cast<size_t>(x->n_loc) * x->D * 2, stream, stepvals, slot);
+}
+
+// nans_xchg_push_dma: per peer, in the order rank - 1, rank - 2, ..., TWO strided copies on `stream`:
+// the rank's image + text rows (loc16) into slot `slot` of the peer's gathered buffers, then the flag
+// words (stepvals) into the peer's flag table.  cudaMemcpy2DAsync on peer-mapped addresses: the copy
+// engines move the data over NVLink, no SM is involved, nothing can starve or be starved by the forward
+// running meanwhile, and copies of one stream complete in order (flags after the rows they announce).
+extern "C" int nans_xchg_push_dma(const nans_xchg_t* x, const void* loc16, const uint32_t* stepvals, int slot,
+                                  void* stream) {
+  int rc = check_device();
+  if (rc != NANS_OK) return rc;
+  if ((rc = check_xchg(x, "xchg_push_dma")) != NANS_OK) return rc;
+  NANS_REQUIRE(loc16 && stepvals && (slot == 0 || slot == 1), "xchg_push_dma: bad arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t row_bytes = static_cast<size_t>(x->D) * 2;
+  const size_t N = static_cast<size_t>(x->world) * x->n_loc;
+  const size_t blk_bytes = static_cast<size_t>(x->n_loc) * row_bytes;         // one modality of this rank
+  const size_t mod_pitch = 2 * N * row_bytes;                                 // image slot 0 -> text slot 0
+  const size_t nflag = static_cast<size_t>(x->n_loc / NANS_XCHG_FLAG_ROWS);
+  for (int k = 1; k < x->world; ++k) {
+    const int dst = (x->rank - k + x->world) % x->world;
+    uint8_t* d = static_cast<uint8_t*>(x->base[dst]);
+    uint8_t* drows = d + x->feat_off + (static_cast<size_t>(slot) * N + static_cast<size_t>(x->rank) * x->n_loc) * row_bytes;
+    NANS_CUDA_OK(cudaMemcpy2DAsync(drows, mod_pitch, loc16, blk_bytes, blk_bytes, 2, cudaMemcpyDeviceToDevice, st));
+    uint8_t* dflag = d + x->fflag_off + static_cast<size_t>(x->rank) * nflag * 4;
+    NANS_CUDA_OK(cudaMemcpy2DAsync(dflag, static_cast<size_t>(x->world) * nflag * 4, stepvals, nflag * 4, nflag * 4, 2,
+                                   cudaMemcpyDeviceToDevice, st));
+  }
+  return NANS_OK;
 }

@@ -283,6 +283,29 @@ def xchg_cast_local(desc, img: torch.Tensor, txt: torch.Tensor, feat_dtype: torc
     return I16, T16
 
 
+def xchg_cast_local_dma(desc, img: torch.Tensor, txt: torch.Tensor, feat_dtype: torch.dtype, slot: int,
+                        normalize: bool = False):
+    """xchg_cast_local into one [2, n_loc, D] buffer + the flag source words.  Returns (loc16, stepvals);
+    loc16[0] / loc16[1] are the image / text row operands."""
+    img, txt = _xchg_sources(desc, img, txt)
+    n_loc, D = img.shape
+    loc16 = torch.empty((2, n_loc, D), dtype=feat_dtype, device=img.device)
+    stepvals = torch.empty((2, n_loc // 64), dtype=torch.int32, device=img.device)
+    with _on_device(img.device) as stream:
+        check(_lib.load().nans_xchg_cast_local_dma(_desc_ref(desc), img.data_ptr(), txt.data_ptr(), dtype_code(img.dtype),
+                                                   img.stride(0), dtype_code(feat_dtype), 1 if normalize else 0,
+                                                   loc16.data_ptr(), stepvals.data_ptr(), int(slot), stream))
+    _count(1)
+    return loc16, stepvals
+
+
+def xchg_push_dma(desc, loc16: torch.Tensor, stepvals: torch.Tensor, slot: int, stream: "torch.cuda.Stream") -> None:
+    """The rows and their flags into every peer's buffers with copy-engine copies on `stream`."""
+    _require_cuda(loc16, stepvals)
+    check(_lib.load().nans_xchg_push_dma(_desc_ref(desc), loc16.data_ptr(), stepvals.data_ptr(), int(slot),
+                                         stream.cuda_stream))
+
+
 def xchg_cast_push(desc, img: torch.Tensor, txt: torch.Tensor, feat_dtype: torch.dtype, normalize: bool = False):
     """xchg_cast_local + xchg_push on the current stream (no overlap)."""
     I16, T16 = xchg_cast_local(desc, img, txt, feat_dtype, normalize)

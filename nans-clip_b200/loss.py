@@ -91,20 +91,31 @@ class _ClipLossFn(torch.autograd.Function):
         ex = exchange.for_group(cfg.group) if (W > 1 and full_img.is_cuda and exchange.eligible(n_loc, D, W)) else None
         desc = ex.ensure(n_loc, D) if ex is not None else None
         if desc is not None:
-            # side stream (forked FIRST, so that its grid is resident before the forward's arrives): the
-            # NVLink push of the features into the peers' buffers, running under the forward;
-            # main stream: cast (local) -> forward -> finalize + lse push -> wait for the peers' lse
+            # main stream: cast (local) -> forward -> finalize + lse push -> wait for the peers' lse;
+            # side stream: the rows and their flags into the peers' buffers.  Default: copy-engine copies
+            # behind the local cast (no SM involved: nothing to co-schedule with the forward).
             src_i, src_t = full_img.detach(), full_txt.detach()
             main = torch.cuda.current_stream(dev)
-            if os.environ.get("NANS_PUSH_OVERLAP", "1") != "0":
+            mode = os.environ.get("NANS_PUSH", "dma")
+            keep = None
+            if mode == "dma":
+                slot = (ex.forwards + 1) & 1
+                loc16, stepvals = K.xchg_cast_local_dma(desc, src_i, src_t, cfg.feat_dtype, slot)
+                I16, T16 = loc16[0], loc16[1]
+                ex.fork.record(main)
+                ex.push_stream.wait_event(ex.fork)
+                K.xchg_push_dma(desc, loc16, stepvals, slot, ex.push_stream)
+                ex.join.record(ex.push_stream)
+                keep = (loc16, stepvals)
+            elif mode == "sm":
+                # push kernel on the SMs, forked FIRST so that its grid is resident before the forward's
                 ex.fork.record(main)
                 ex.push_stream.wait_event(ex.fork)
                 keep = K.xchg_push(desc, src_i, src_t, cfg.feat_dtype, stream=ex.push_stream)
                 ex.join.record(ex.push_stream)
                 I16, T16 = K.xchg_cast_local(desc, src_i, src_t, cfg.feat_dtype)
-            else:   # serial: push, then forward (no two kernels of this rank ever have to co-reside)
+            else:   # "serial": push kernel, then forward
                 I16, T16 = K.xchg_cast_push(desc, src_i, src_t, cfg.feat_dtype)
-                keep = None
             nslots = K.fwd_xchg_slots(n_loc, W, D)
             ws = K.fwd_workspace(n_loc, nslots, dev)
             K.fwd_xchg(desc, I16, T16, s_dev, cfg.report_acc, ws)

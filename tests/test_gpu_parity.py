@@ -692,7 +692,8 @@ def test_rank_strip_at_bench_sizes(dev, W, rank, n_loc, d, chunk):
 @pytest.mark.parametrize("W,n_loc,d,s,in_dt", [(2, 256, 128, 20.0, torch.float32), (4, 512, 512, 14.2857, torch.float32),
                                                (8, 256, 72, 50.0, torch.float16), (3, 768, 768, 14.2857, torch.float32),
                                                (2, 256, 1024, 5.0, torch.bfloat16), (4, 1024, 64, 14.2857, torch.float32)])
-def test_push_exchange_emulated_ranks(dev, W, n_loc, d, s, in_dt):
+@pytest.mark.parametrize("push", ["sm", "dma"])
+def test_push_exchange_emulated_ranks(dev, W, n_loc, d, s, in_dt, push):
     """The NVLink push data plane (csrc/exchange.cu + the exchange modes of kernels (2)/(3)) with the W
     ranks of a job EMULATED one after the other on this GPU: W exchange buffers in one process stand for
     the peer-mapped buffers, every phase runs for all ranks before the next one starts (so no kernel ever
@@ -713,7 +714,17 @@ def test_push_exchange_emulated_ranks(dev, W, n_loc, d, s, in_dt):
         I, T = synth(N, d, 500 + 10 * W + step, 0.5, torch.bfloat16 if in_dt == torch.bfloat16 else torch.float16)
         want = OL.global_loss_and_grads(I, T, s, torch.float64)
         rows = [slice(r * n_loc, (r + 1) * n_loc) for r in range(W)]
-        loc = [K.xchg_cast_push(descs[r], I[rows[r]].to(dev).to(in_dt), T[rows[r]].to(dev).to(in_dt), feat) for r in range(W)]
+        if push == "sm":     # push kernel (st.global on the peers' buffers)
+            loc = [K.xchg_cast_push(descs[r], I[rows[r]].to(dev).to(in_dt), T[rows[r]].to(dev).to(in_dt), feat)
+                   for r in range(W)]
+        else:                # copy engines: strided copies of the rows, then of the flag words
+            loc = []
+            for r in range(W):
+                l16, sv = K.xchg_cast_local_dma(descs[r], I[rows[r]].to(dev).to(in_dt), T[rows[r]].to(dev).to(in_dt),
+                                                feat, (step + 1) & 1)
+                K.xchg_push_dma(descs[r], l16, sv, (step + 1) & 1, torch.cuda.current_stream())
+                assert bool((sv == step + 1).all())
+                loc.append((l16[0], l16[1]))
         for r in range(W):   # the local copies are the cast rows
             assert torch.equal(loc[r][0].float().cpu(), I[rows[r]]) and torch.equal(loc[r][1].float().cpu(), T[rows[r]])
         wss = [K.fwd_workspace(n_loc, nslots, dev) for _ in range(W)]

@@ -57,7 +57,7 @@ if rank == 0:
     evs.sort(key=lambda e: e.time_range.start)
     # last step only: events after the last big gap
     os.makedirs("gpurun_out", exist_ok=True)
-    with open(f"gpurun_out/timeline_W{W}.txt", "w") as f:
+    with open(f"gpurun_out/timeline_W{W}{os.environ.get('TL_TAG', '')}.txt", "w") as f:
         t0 = None; prev_end = None
         for e in evs:
             st, en = e.time_range.start, e.time_range.end
