@@ -308,7 +308,8 @@ int nans_xchg_cast_push(const nans_xchg_t* x, const void* img, const void* txt, 
 int nans_xchg_cast_local_dma(const nans_xchg_t* x, const void* img, const void* txt, int x_dtype, int64_t ld_x,
                              int feat_dtype, int normalize, void* loc16, uint32_t* stepvals, int slot,
                              void* stream);
-int nans_xchg_push_dma(const nans_xchg_t* x, const void* loc16, const uint32_t* stepvals, int slot, void* stream);
+int nans_xchg_push_dma(const nans_xchg_t* x, const void* loc16, const uint32_t* stepvals, int slot, void* stream,
+                       void* stream_b /* optional second stream: every other peer, a second copy engine */);
 
 /* Kernel (2) over the gathered buffers: both strips of this rank against all world * n_loc columns in
  * ONE launch.  Every unit walks the column tiles source by source starting with its own rank's (local,

@@ -380,13 +380,13 @@ extern "C" int nans_xchg_cast_local_dma(const nans_xchg_t* x, const void* img, c
 // words (stepvals) into the peer's flag table.  cudaMemcpy2DAsync on peer-mapped addresses: the copy
 // engines move the data over NVLink, no SM is involved, nothing can starve or be starved by the forward
 // running meanwhile, and copies of one stream complete in order (flags after the rows they announce).
+// `stream_b` (optional): a second stream for every other peer, so that two copy engines work at once.
 extern "C" int nans_xchg_push_dma(const nans_xchg_t* x, const void* loc16, const uint32_t* stepvals, int slot,
-                                  void* stream) {
+                                  void* stream, void* stream_b) {
   int rc = check_device();
   if (rc != NANS_OK) return rc;
   if ((rc = check_xchg(x, "xchg_push_dma")) != NANS_OK) return rc;
   NANS_REQUIRE(loc16 && stepvals && (slot == 0 || slot == 1), "xchg_push_dma: bad arguments");
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
   const size_t row_bytes = static_cast<size_t>(x->D) * 2;
   const size_t N = static_cast<size_t>(x->world) * x->n_loc;
   const size_t blk_bytes = static_cast<size_t>(x->n_loc) * row_bytes;         // one modality of this rank
@@ -394,6 +394,8 @@ extern "C" int nans_xchg_push_dma(const nans_xchg_t* x, const void* loc16, const
   const size_t nflag = static_cast<size_t>(x->n_loc / NANS_XCHG_FLAG_ROWS);
   for (int k = 1; k < x->world; ++k) {
     const int dst = (x->rank - k + x->world) % x->world;
+    // two streams = two copy engines: peers k = 1, 3, 5, ... on the first, 2, 4, 6, ... on the second
+    cudaStream_t st = static_cast<cudaStream_t>((stream_b != nullptr && (k & 1) == 0) ? stream_b : stream);
     uint8_t* d = static_cast<uint8_t*>(x->base[dst]);
     uint8_t* drows = d + x->feat_off + (static_cast<size_t>(slot) * N + static_cast<size_t>(x->rank) * x->n_loc) * row_bytes;
     NANS_CUDA_OK(cudaMemcpy2DAsync(drows, mod_pitch, loc16, blk_bytes, blk_bytes, 2, cudaMemcpyDeviceToDevice, st));

@@ -46,6 +46,7 @@ struct FwdParams {
   int xslot_rows;                // rows of one slot of the gathered tensor (= N)
   const uint32_t* xflags[2];     // per strip: arrival flags of its column modality
   const uint32_t* xepoch;        // device word: completed steps; this launch belongs to step *xepoch + 1
+  long long* xwait_ns;           // diagnostics (NANS_XCHG_PROBE): per-CTA flag-wait nanoseconds, or null
 };
 
 template <bool WITH_ACC>
@@ -153,6 +154,7 @@ clip_fwd_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
     a.xstep = *p.xepoch + 1u;
     a.xrow_off = static_cast<int>(a.xstep & 1u) * p.xslot_rows;
     a.xflags = p.xflags[strip];
+    a.xwait_ns = p.xwait_ns;
     a.tile_begin = 0;
     a.tile_end = p.xw * a.xsub_count;
   } else {
@@ -532,7 +534,12 @@ int choose_nsplit(int64_t n_loc, int64_t ncols, int nstrips) {
   return best;
 }
 
-// exchange mode: a split is a sub-range of every source rank's tiles, so ns <= tiles per source
+// exchange mode: a split is a sub-range of every source rank's tiles, so ns <= tiles per source.
+// Every unit visits ALL sources, i.e. it cannot finish before the last source has arrived, and it holds
+// its SMs while it waits: units beyond the first wave would only start after that.  (With the usual 0.75
+// tiles of per-unit overhead the model chose 16 splits = 7 waves at n_loc = 4096, world 8: the first wave
+// sat on the SMs until the last peer's rows were in, 400 us instead of 200.)  3 tiles per unit (pipeline
+// fill, epilogue, a wave's launch) make one wave win wherever one wave is possible.
 int choose_nsplit_xchg(int64_t n_loc, int64_t world) {
   const bool pair = fwd_pair_mode();
   const int64_t base = 2 * ceil_div(n_loc, pair ? 2 * BM : BM);
@@ -543,7 +550,7 @@ int choose_nsplit_xchg(int64_t n_loc, int64_t world) {
   const int64_t max_ns = src_tiles < 32 ? src_tiles : 32;
   for (int64_t ns = 1; ns <= max_ns; ++ns) {
     const double waves = static_cast<double>(ceil_div(base * ns, sms));
-    const double cost = waves * (static_cast<double>(world * ceil_div(src_tiles, ns)) + 0.75);
+    const double cost = waves * (static_cast<double>(world * ceil_div(src_tiles, ns)) + 3.0);
     if (cost < best_cost - 1e-9) {
       best_cost = cost;
       best = static_cast<int>(ns);
@@ -633,6 +640,9 @@ extern "C" int nans_clip_loss_fwd_xchg(const nans_xchg_t* x, const void* I16_loc
   p.xflags[0] = fflags + blocks;  // strip 0 reads the TEXT columns (modality 1)
   p.xflags[1] = fflags;           // strip 1 reads the IMAGE columns (modality 0)
   p.xepoch = x->epoch;
+  // diagnostics: NANS_XCHG_PROBE=<device address of a zeroed int64[grid] array> (tools/xchg_probe.py)
+  p.xwait_ns = nullptr;
+  if (const char* e = getenv("NANS_XCHG_PROBE")) p.xwait_ns = reinterpret_cast<long long*>(strtoull(e, nullptr, 0));
 
   const bool with_acc = (flags & NANS_LOSS_WITH_ACC) != 0;
   void (*kern)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const FwdParams);
@@ -757,6 +767,7 @@ extern "C" int nans_clip_loss_fwd_phase_rows(const void* I_loc, const void* T_lo
   p.xrank = p.xsrc_tiles = p.xslot_rows = 0;
   p.xflags[0] = p.xflags[1] = nullptr;
   p.xepoch = nullptr;
+  p.xwait_ns = nullptr;
 
   const bool with_acc = (flags & NANS_LOSS_WITH_ACC) != 0;
   void (*kern)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const FwdParams);

@@ -83,6 +83,7 @@ struct SweepArgs {
   int xrow_off = 0;                  // row of column 0 in the gathered tensor map (slot of this step)
   const uint32_t* xflags = nullptr;  // [xw][xsrc_tiles * 4] arrival flags of the column operand's modality
   uint32_t xstep = 0;
+  long long* xwait_ns = nullptr;     // diagnostics: per CTA, nanoseconds the producer spent waiting for flags
 };
 
 // swept index t of a unit -> tile of the column operand (in logical, global column tiles)
@@ -201,9 +202,16 @@ __device__ __forceinline__ uint8_t* run(const SweepArgs& a, Epi& epi) {
       if (a.xw > 0 && tile / a.xsrc_tiles != a.xrank) {
         // remote rows [col0, col0 + rows of this CTA's part of the tile): one flag per 64 rows
         constexpr int NFLAG = (CP ? BN / 2 : BN) / 64;
+        long long t0 = 0;
+        if (a.xwait_ns != nullptr) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
         if (lane < NFLAG) wait_flag_sys(a.xflags + (col0 - a.xrow_off) / 64 + lane, a.xstep);
         __syncwarp();
         fence_proxy_async_global();  // the peer's generic-proxy writes -> this CTA's TMA (async proxy) reads
+        if (a.xwait_ns != nullptr && lane == 0) {
+          long long t1;
+          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+          a.xwait_ns[blockIdx.x] += t1 - t0;
+        }
       }
       for (int c = 0; c < a.kchunks; ++c) {
         mbar_wait(&empty[stage], phase ^ 1u);

@@ -299,11 +299,13 @@ def xchg_cast_local_dma(desc, img: torch.Tensor, txt: torch.Tensor, feat_dtype: 
     return loc16, stepvals
 
 
-def xchg_push_dma(desc, loc16: torch.Tensor, stepvals: torch.Tensor, slot: int, stream: "torch.cuda.Stream") -> None:
-    """The rows and their flags into every peer's buffers with copy-engine copies on `stream`."""
+def xchg_push_dma(desc, loc16: torch.Tensor, stepvals: torch.Tensor, slot: int, stream: "torch.cuda.Stream",
+                  stream_b: "torch.cuda.Stream | None" = None) -> None:
+    """The rows and their flags into every peer's buffers with copy-engine copies on `stream` (and, for every
+    other peer, `stream_b`)."""
     _require_cuda(loc16, stepvals)
     check(_lib.load().nans_xchg_push_dma(_desc_ref(desc), loc16.data_ptr(), stepvals.data_ptr(), int(slot),
-                                         stream.cuda_stream))
+                                         stream.cuda_stream, stream_b.cuda_stream if stream_b is not None else None))
 
 
 def xchg_cast_push(desc, img: torch.Tensor, txt: torch.Tensor, feat_dtype: torch.dtype, normalize: bool = False):

@@ -104,7 +104,13 @@ class _ClipLossFn(torch.autograd.Function):
                 I16, T16 = loc16[0], loc16[1]
                 ex.fork.record(main)
                 ex.push_stream.wait_event(ex.fork)
-                K.xchg_push_dma(desc, loc16, stepvals, slot, ex.push_stream)
+                two = W > 2 and os.environ.get("NANS_PUSH_STREAMS", "2") == "2"
+                if two:
+                    ex.push_stream_b.wait_event(ex.fork)
+                K.xchg_push_dma(desc, loc16, stepvals, slot, ex.push_stream, ex.push_stream_b if two else None)
+                if two:
+                    ex.join_b.record(ex.push_stream_b)
+                    ex.push_stream.wait_event(ex.join_b)
                 ex.join.record(ex.push_stream)
                 keep = (loc16, stepvals)
             elif mode == "sm":

@@ -722,7 +722,7 @@ def test_push_exchange_emulated_ranks(dev, W, n_loc, d, s, in_dt, push):
             for r in range(W):
                 l16, sv = K.xchg_cast_local_dma(descs[r], I[rows[r]].to(dev).to(in_dt), T[rows[r]].to(dev).to(in_dt),
                                                 feat, (step + 1) & 1)
-                K.xchg_push_dma(descs[r], l16, sv, (step + 1) & 1, torch.cuda.current_stream())
+                K.xchg_push_dma(descs[r], l16, sv, (step + 1) & 1, torch.cuda.current_stream(), None)
                 assert bool((sv == step + 1).all())
                 loc.append((l16[0], l16[1]))
         for r in range(W):   # the local copies are the cast rows
