@@ -440,16 +440,58 @@ def loss_step_bench(args, dist, W, rank, dev, n_global, d, with_e2e, kernel_roof
         out["eager_ms_per_step"] = timed_steps(step, args.steps, 2, flush, dist, dev) / args.steps
     if with_e2e:
         img_h, txt_h = img.pin_memory(), txt.pin_memory()
+        loss_h = torch.zeros(1, dtype=torch.float32).pin_memory()
+        seen = []
 
-        def step_e2e():
-            i = img_h.to(dev, non_blocking=True).requires_grad_(True)
+        def step_e2e_body():
+            i = img_h.to(dev, non_blocking=True).requires_grad_(True)     # H2D of this step's features
             t = txt_h.to(dev, non_blocking=True).requires_grad_(True)
             s.grad = None
             loss, _ = clip_contrastive_loss(i, t, s, group=group, feat_dtype=feat_dt)
             loss.backward()
-            return float(loss.item())  # D2H read of the step's result
+            loss_h.copy_(loss.detach().reshape(1), non_blocking=True)     # D2H of the step's result
+            return i, t
 
-        out["e2e_ms"] = timed_steps(step_e2e, args.steps, min(args.warmup, 3), flush, dist, dev) / args.steps
+        def step_e2e():
+            step_e2e_body()
+            torch.cuda.current_stream().synchronize()
+            seen.append(float(loss_h[0]))                                 # the host reads the loss every step
+
+        e2e_step, e2e_graphed = step_e2e, False
+        if graphed:
+            # the same end-to-end step (H2D copies from pinned memory, the public call, backward, D2H of the
+            # loss) captured and replayed: at N > 1 the eager version is bound by ~0.5 ms of host launches
+            try:
+                egraphs = []
+                for _ in range(len(graphs)):
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                        step_e2e_body()
+                    egraphs.append(g)
+                torch.cuda.synchronize()
+                ecount = [0]
+
+                def step_e2e_graph():
+                    egraphs[ecount[0] % len(egraphs)].replay()
+                    ecount[0] += 1
+                    torch.cuda.current_stream().synchronize()
+                    seen.append(float(loss_h[0]))
+
+                e2e_step, e2e_graphed = step_e2e_graph, True
+            except Exception as exc:
+                print(f"[bench] e2e graph capture failed, timing the eager e2e step: {exc!r}", file=sys.stderr)
+            if dist is not None:
+                flag = torch.tensor([1 if e2e_graphed else 0], device=dev)
+                dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+                if int(flag.item()) == 0:
+                    e2e_step, e2e_graphed = step_e2e, False
+        out["e2e_ms"] = timed_steps(e2e_step, args.steps, min(args.warmup, 3), flush, dist, dev) / args.steps
+        if e2e_graphed and len(egraphs) == 2 and ecount[0] % 2:
+            e2e_step()
+        if e2e_graphed:
+            out["e2e_eager_ms"] = timed_steps(step_e2e, args.steps, 2, flush, dist, dev) / args.steps
+        out["e2e_graphed"] = e2e_graphed
+        out["e2e_loss_seen"] = seen[-1] if seen else None
     if kernel_rooflines:
         # ---- forward and backward kernels timed alone, on this rank ----
         with torch.no_grad():
@@ -726,7 +768,10 @@ def bench_main(args):
             # the step is timed alone between L2 flushes (milliseconds): the burst peak is its denominator
             "frac_of_bf16_peak_algorithmic": step_alg / (ms / 1e3) / 1e12 / (W * peaks["bf16_tflops"]),
             "e2e": {"value": N_GLOBAL / (e2e_ms / 1e3), "unit": "pairs/s", "ms_per_step": e2e_ms,
-                    "h2d_bytes_per_step": 2 * n_loc * D * 4, "d2h_bytes_per_step": 4},
+                    "h2d_bytes_per_step": 2 * n_loc * D * 4, "d2h_bytes_per_step": 4,
+                    "launch": ("cuda-graph replay of the whole step incl. the H2D / D2H copies" if r.get("e2e_graphed")
+                               else "eager"),
+                    "eager_ms_per_step": r.get("e2e_eager_ms"), "loss_read_back": r.get("e2e_loss_seen")},
             "gpu_launches": r["launches_per_step"] * args.steps,
             "gpu_launches_per_step": r["launches_per_step"],
             "roofline": r["roofline"], "roofline_fwd": r["roofline_fwd"],

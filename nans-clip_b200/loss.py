@@ -104,7 +104,7 @@ class _ClipLossFn(torch.autograd.Function):
                 I16, T16 = loc16[0], loc16[1]
                 ex.fork.record(main)
                 ex.push_stream.wait_event(ex.fork)
-                two = W > 2 and os.environ.get("NANS_PUSH_STREAMS", "2") == "2"
+                two = W > 2 and os.environ.get("NANS_PUSH_STREAMS", "1") == "2"
                 if two:
                     ex.push_stream_b.wait_event(ex.fork)
                 K.xchg_push_dma(desc, loc16, stepvals, slot, ex.push_stream, ex.push_stream_b if two else None)
