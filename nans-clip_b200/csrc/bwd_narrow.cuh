@@ -472,11 +472,11 @@ clip_bwd_np_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
 }
 
 // ================================================================================================
-// Persistent, load-balanced forms of the narrow-pair kernel (see the dispatch for when each is used).  The (strip, row block, tile)
-// space is linearised (row-block major, tiles inside) and cut into `npairs` equal contiguous ranges,
-// one per resident CTA pair, so that the SMs stay busy whatever 2 * nrb is (with one unit per CTA
-// pair, 64 units on 74 pairs leave 14 % of the machine idle at n_loc = 4096).  A pair's range
-// crosses row-block boundaries: each piece is a SEGMENT with its own A block, its own dA
+// Persistent, load-balanced form of the narrow-pair kernel (helper schedule; see the dispatch for when it
+// is used).  With one unit per CTA pair, 64 units on 74 pairs leave 14 % of the machine idle at
+// n_loc = 4096: every unit keeps its own pair for its first npp_t1 tiles, and the idle pairs share the
+// remaining tiles of ALL units, linearised (unit major, tiles inside) and cut into equal contiguous ranges.
+// A helper's range crosses unit boundaries: each piece is a SEGMENT with its own A block, its own dA
 // accumulation and a red.add write-out; the MMA1 / softmax / MMA2 pipeline runs straight through
 // segment boundaries (MMA1 of the next segment's first tile is issued before MMA2 of the previous
 // segment's last tile).  Extra barriers: a_empty (A may be overwritten), da_empty (dA drained).
@@ -488,19 +488,14 @@ struct NppCursor {
 // This pair's share: `nt` tile steps starting at linear index g0 of the space (unit, tile in window).
 __device__ __forceinline__ void npp_range(long long pair, const BwdParams& p, long long& g0, long long& nt,
                                           int& tile_lo, int& tile_hi) {
-  if (p.npp_t1 > 0) {
-    if (pair < p.npp_units) {  // main pair: the first npp_t1 tiles of its own unit
-      tile_lo = 0; tile_hi = p.npp_t1;
-      g0 = pair * p.npp_t1; nt = p.npp_t1;
-    } else {                   // helper pair: an equal share of the last tiles of ALL units
-      tile_lo = p.npp_t1; tile_hi = p.ntiles;
-      const long long tot = static_cast<long long>(p.npp_units) * (p.ntiles - p.npp_t1);
-      const long long h = pair - p.npp_units, nh = p.npairs - p.npp_units;
-      g0 = h * tot / nh; nt = (h + 1) * tot / nh - g0;
-    }
-  } else {
-    tile_lo = 0; tile_hi = p.ntiles;
-    g0 = pair * p.total_tiles / p.npairs; nt = (pair + 1) * p.total_tiles / p.npairs - g0;
+  if (pair < p.npp_units) {  // main pair: the first npp_t1 tiles of its own unit
+    tile_lo = 0; tile_hi = p.npp_t1;
+    g0 = pair * p.npp_t1; nt = p.npp_t1;
+  } else {                   // helper pair: an equal share of the last tiles of ALL units
+    tile_lo = p.npp_t1; tile_hi = p.ntiles;
+    const long long tot = static_cast<long long>(p.npp_units) * (p.ntiles - p.npp_t1);
+    const long long h = pair - p.npp_units, nh = p.npairs - p.npp_units;
+    g0 = h * tot / nh; nt = (h + 1) * tot / nh - g0;
   }
 }
 __device__ __forceinline__ NppCursor npp_begin(long long g0, long long nt, const BwdParams& p, int tile_lo,

@@ -142,7 +142,7 @@ int choose_bwd_nsplit(int64_t rows, int64_t N, int npass, int rows_per_unit, int
 }
 
 // ---- which kernel, which grid: everything that depends only on (gradient rows, N, D) --------------
-enum BwdKind { BWD_1CTA = 0, BWD_WIDE_PAIR = 1, BWD_NARROW = 2, BWD_NARROW_PERSISTENT = 3 };
+enum BwdKind { BWD_WIDE_PAIR = 1, BWD_NARROW = 2, BWD_NARROW_PERSISTENT = 3 };  // 0 was the retired single-CTA kernel
 
 struct BwdSchedule {
   int kind;
@@ -162,12 +162,7 @@ BwdSchedule plan_bwd_schedule(int64_t grad_row_count, int64_t N, int64_t D) {
   BwdSchedule sc{};
   const int kchunks = static_cast<int>(ceil_div(D, BK));
   const int npass = static_cast<int>(ceil_div(kchunks, SLICE / BK));
-  // CTA pairs (cta_group::2) by default; NANS_BWD_1CTA=1 selects the single-CTA kernel
-  bool use_pair = true;
-  {
-    const char* e = getenv("NANS_BWD_1CTA");
-    if (e && e[0] == '1') use_pair = false;
-  }
+  const bool use_pair = true;  // every kernel is a CTA-pair kernel (cta_group::2)
   // narrow pairs (64 rows per CTA, no S recompute per feature slice) whenever D <= 512;
   // NANS_BWD_NP=0 falls back to the 128-row pair kernel
   // D <= 768: dA of 64 rows fits TMEM beside two S buffers; D <= 1024: two passes of 512 features, A streamed
@@ -179,7 +174,7 @@ BwdSchedule plan_bwd_schedule(int64_t grad_row_count, int64_t N, int64_t D) {
     const char* e = getenv("NANS_BWD_NP");
     if (e && e[0] == '0') use_np = false;
   }
-  // persistent load-balanced form of the narrow-pair kernel: NANS_BWD_PERSIST=1
+  // persistent helper schedule of the narrow-pair kernel
   bool use_npp = false;
   int npp_t1 = 0, npp_units = 0;
   if (use_np) {
@@ -189,18 +184,15 @@ BwdSchedule plan_bwd_schedule(int64_t grad_row_count, int64_t N, int64_t D) {
     const int64_t units = 2 * ceil_div(grad_row_count, 2 * NP_ROWS);
     const int64_t slots = sm_count() / 2;
     const double fill = static_cast<double>(units) / static_cast<double>(ceil_div(units, slots) * slots);
-    // Equal contiguous ranges (NANS_BWD_PERSIST=1): measured at 2 GPUs (n_loc = 16384) 2.61 ms/step
-    // against 2.50 — the pairs no longer walk the column tiles in lockstep, so the column operands
-    // stop hitting in L2.  Opt-in only.
+    // (An "equal contiguous ranges" schedule was tried and retired: at 2 GPUs, n_loc = 16384, 2.61 ms/step
+    // against 2.50 — pairs that stop walking the column tiles in lockstep lose their L2 hits.)
     // Helper mode (default when there are FEWER units than CTA pairs, e.g. 64 units on 74 pairs at
     // n_loc = 4096): every unit keeps its own pair for the first T1 tiles (lockstep preserved) and the
     // idle pairs share the last ntiles - T1 tiles of all units.  NANS_BWD_PERSIST=0 disables it.
     const char* e = getenv("NANS_BWD_PERSIST");
     const int64_t nt256 = ceil_div(N, NP_KT);
     const bool force_helpers = e && e[0] == '2';  // tests: helper mode wherever it is feasible
-    if (e && e[0] == '1') {
-      use_npp = kchunks <= 8;
-    } else if (!(e && e[0] == '0') && kchunks <= 8 && units < slots && nt256 >= 2 &&
+    if (!(e && e[0] == '0') && kchunks <= 8 && units < slots && nt256 >= 2 &&
                (force_helpers || (fill < 0.95 && slots - units >= 2 && nt256 >= 32))) {
       // main pair: T1 tiles + start/drain (~3 tiles); helper: units * (nt - T1) / helpers tiles + ~1.2
       // tiles per unit boundary + the same start/drain  =>  T1 = units * (nt + 1.2) / slots
@@ -214,37 +206,29 @@ BwdSchedule plan_bwd_schedule(int64_t grad_row_count, int64_t N, int64_t D) {
       }
     }
   }
-  const BwdPlan plan = plan_bwd(kchunks);
   const PairPlan pplan = plan_pair(kchunks);
   const NpPlan nplan = plan_np(kchunks, np_tk, np_ares);
   const int64_t np_units = 2 * ceil_div(grad_row_count, 2 * NP_ROWS) * np_npass;
   const NpTail tail = plan_np_tail(np_units, ceil_div(N, np_tk), sm_count() / 2, np_tk == NP_KT ? 3.0 : 6.0);
   const int nsplit = use_npp    ? 2  /* outputs are always accumulated (zeroed below) */
                      : use_np   ? 1  /* per-unit: see plan_np_tail */
-                     : use_pair ? choose_bwd_nsplit(grad_row_count, N, npass, 2 * BM, sm_count() / 2)
-                                : choose_bwd_nsplit(grad_row_count, N, npass, BM, sm_count());
+                                : choose_bwd_nsplit(grad_row_count, N, npass, 2 * BM, sm_count() / 2);
   sc.kchunks = kchunks;
   sc.npp_t1 = npp_t1;
   sc.npp_units = npp_units;
   sc.tail = tail;
   sc.nsplit = nsplit;
-  sc.kind = use_npp ? BWD_NARROW_PERSISTENT : use_np ? BWD_NARROW : use_pair ? BWD_WIDE_PAIR : BWD_1CTA;
+  sc.kind = use_npp ? BWD_NARROW_PERSISTENT : use_np ? BWD_NARROW : BWD_WIDE_PAIR;
   sc.npass = (use_np || use_npp) ? np_npass : npass;
   sc.tile_cols = use_np ? np_tk : KT;
-  sc.a_resident = use_np ? np_ares : (use_pair ? pplan.a_resident : plan.a_resident);
+  sc.a_resident = use_np ? np_ares : pplan.a_resident;
   sc.nrb = static_cast<int>(ceil_div(grad_row_count, use_np ? 2 * NP_ROWS : (use_pair ? 2 * BM : BM)));
   sc.ntiles = static_cast<int>(ceil_div(N, sc.tile_cols));
-  sc.nr = use_np ? nplan.nr : (use_pair ? pplan.nr : plan.nr);
-  sc.smem_bytes = use_np ? nplan.bytes : (use_pair ? pplan.bytes : plan.bytes);
+  sc.nr = use_np ? nplan.nr : pplan.nr;
+  sc.smem_bytes = use_np ? nplan.bytes : pplan.bytes;
   sc.npairs = 0;
   if (use_npp) {
-    if (npp_t1 > 0) {
-      sc.npairs = sm_count() / 2;  // npp_units main pairs + the helpers
-    } else {
-      // equal ranges: at least ~4 tiles per pair, at most one pair per two SMs
-      const long long total = 2ll * sc.nrb * sc.ntiles;
-      sc.npairs = static_cast<int>(std::min<long long>(sm_count() / 2, std::max<long long>(1, total / 4)));
-    }
+    sc.npairs = sm_count() / 2;  // npp_units main pairs + the helpers
     sc.grid = static_cast<unsigned>(2 * sc.npairs);
   } else if (use_np) {
     sc.grid = static_cast<unsigned>(2 * (tail.n_full + (np_units - tail.n_full) * tail.ns_tail));
@@ -486,14 +470,10 @@ static int bwd_dispatch(const void* I_loc, const void* T_loc, int64_t ld_loc, co
                                         static_cast<int>(smem)));
       clip_bwd_np_kernel<128, true><<<sc.grid, NUM_THREADS, smem, st>>>(tmAn0, tmBk0, tmB0, tmAn1, tmBk1, tmB1, p);
     }
-  } else if (sc.kind == BWD_WIDE_PAIR) {
+  } else {
     auto kern = sc.a_resident ? clip_bwd_pair_kernel<true> : clip_bwd_pair_kernel<false>;
     NANS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     kern<<<sc.grid, NUM_THREADS, smem, st>>>(tmA0, tmBk0, tmB0, tmA1, tmBk1, tmB1, p);
-  } else {
-    auto kern = sc.a_resident ? clip_bwd_kernel<true> : clip_bwd_kernel<false>;
-    NANS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    kern<<<sc.grid, NUM_THREADS, smem, st>>>(tmA0, tmB0, tmA1, tmB1, p);
   }
   NANS_CUDA_OK(cudaGetLastError());
 

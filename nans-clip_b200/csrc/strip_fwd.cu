@@ -506,10 +506,8 @@ FwdWs carve_fwd_ws(void* ws, int64_t n_loc, int64_t total_slots) {
   return w;
 }
 
-bool fwd_pair_mode() {
-  const char* e = getenv("NANS_FWD_1CTA");
-  return !(e && e[0] == '1');
-}
+// every launch runs as CTA pairs (cta_group::2); the single-CTA instantiation of the sweep was retired in round 2
+constexpr bool fwd_pair_mode() { return true; }
 
 int strips_of(int flags) {
   return (flags & (NANS_LOSS_STRIP_IMG | NANS_LOSS_STRIP_TXT)) ? 1 : 2;
@@ -646,13 +644,8 @@ extern "C" int nans_clip_loss_fwd_xchg(const nans_xchg_t* x, const void* I16_loc
 
   const bool with_acc = (flags & NANS_LOSS_WITH_ACC) != 0;
   void (*kern)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const FwdParams);
-  if (pair) {
-    kern = plan.a_resident ? (with_acc ? clip_fwd_kernel<true, true, true> : clip_fwd_kernel<true, false, true>)
-                           : (with_acc ? clip_fwd_kernel<false, true, true> : clip_fwd_kernel<false, false, true>);
-  } else {
-    kern = plan.a_resident ? (with_acc ? clip_fwd_kernel<true, true, false> : clip_fwd_kernel<true, false, false>)
-                           : (with_acc ? clip_fwd_kernel<false, true, false> : clip_fwd_kernel<false, false, false>);
-  }
+  kern = plan.a_resident ? (with_acc ? clip_fwd_kernel<true, true, true> : clip_fwd_kernel<true, false, true>)
+                         : (with_acc ? clip_fwd_kernel<false, true, true> : clip_fwd_kernel<false, false, true>);
   NANS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(plan.bytes)));
   const unsigned grid = static_cast<unsigned>((pair ? 2 : 1) * 2 * p.nrb * p.nsplit);
   kern<<<grid, NUM_THREADS, plan.bytes, static_cast<cudaStream_t>(stream)>>>(tmA0, tmB0, tmA1, tmB1, p);
@@ -771,13 +764,8 @@ extern "C" int nans_clip_loss_fwd_phase_rows(const void* I_loc, const void* T_lo
 
   const bool with_acc = (flags & NANS_LOSS_WITH_ACC) != 0;
   void (*kern)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const FwdParams);
-  if (pair) {
-    kern = plan.a_resident ? (with_acc ? clip_fwd_kernel<true, true, true> : clip_fwd_kernel<true, false, true>)
-                           : (with_acc ? clip_fwd_kernel<false, true, true> : clip_fwd_kernel<false, false, true>);
-  } else {
-    kern = plan.a_resident ? (with_acc ? clip_fwd_kernel<true, true, false> : clip_fwd_kernel<true, false, false>)
-                           : (with_acc ? clip_fwd_kernel<false, true, false> : clip_fwd_kernel<false, false, false>);
-  }
+  kern = plan.a_resident ? (with_acc ? clip_fwd_kernel<true, true, true> : clip_fwd_kernel<true, false, true>)
+                         : (with_acc ? clip_fwd_kernel<false, true, true> : clip_fwd_kernel<false, false, true>);
   NANS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     static_cast<int>(plan.bytes)));
   const unsigned grid = static_cast<unsigned>((pair ? 2 : 1) * nstrips * p.nrb * p.nsplit);

@@ -474,10 +474,8 @@ __global__ void __launch_bounds__(FIN_WARPS * 32) topk_merge_kernel(const MergeP
   }
 }
 
-bool topk_pair_mode() {
-  const char* e = getenv("NANS_TOPK_1CTA");
-  return !(e && e[0] == '1');
-}
+// every launch runs as CTA pairs (cta_group::2); the single-CTA instantiation was retired in round 2
+constexpr bool topk_pair_mode() { return true; }
 
 // A cold candidate list spends its first ~16K columns almost entirely on the insertion path (an
 // exact cold pre-pass over 16K columns ran at 22 % tensor pipe).  So a long gallery is swept twice:
@@ -587,23 +585,13 @@ extern "C" int nans_topk_ip(const void* Q16, const void* G16, int feat_dtype, co
   const SmemPlan plan = plan_smem(kchunks, pair);
 
   void (*kern)(const CUtensorMap, const CUtensorMap, const TopkParams);
-  if (pair) {
-    if (k_cand == 16) kern = plan.a_resident ? topk_sweep_kernel<true, 16, true> : topk_sweep_kernel<false, 16, true>;
-    else kern = plan.a_resident ? topk_sweep_kernel<true, 32, true> : topk_sweep_kernel<false, 32, true>;
-  } else {
-    if (k_cand == 16) kern = plan.a_resident ? topk_sweep_kernel<true, 16, false> : topk_sweep_kernel<false, 16, false>;
-    else kern = plan.a_resident ? topk_sweep_kernel<true, 32, false> : topk_sweep_kernel<false, 32, false>;
-  }
+  if (k_cand == 16) kern = plan.a_resident ? topk_sweep_kernel<true, 16, true> : topk_sweep_kernel<false, 16, true>;
+  else kern = plan.a_resident ? topk_sweep_kernel<true, 32, true> : topk_sweep_kernel<false, 32, true>;
   NANS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     static_cast<int>(plan.bytes)));
   void (*fkern)(const CUtensorMap, const CUtensorMap, const TopkParams);
-  if (pair) {
-    if (k_cand == 16) fkern = plan.a_resident ? topk_floor_kernel<true, 16, true> : topk_floor_kernel<false, 16, true>;
-    else fkern = plan.a_resident ? topk_floor_kernel<true, 32, true> : topk_floor_kernel<false, 32, true>;
-  } else {
-    if (k_cand == 16) fkern = plan.a_resident ? topk_floor_kernel<true, 16, false> : topk_floor_kernel<false, 16, false>;
-    else fkern = plan.a_resident ? topk_floor_kernel<true, 32, false> : topk_floor_kernel<false, 32, false>;
-  }
+  if (k_cand == 16) fkern = plan.a_resident ? topk_floor_kernel<true, 16, true> : topk_floor_kernel<false, 16, true>;
+  else fkern = plan.a_resident ? topk_floor_kernel<true, 32, true> : topk_floor_kernel<false, 32, true>;
   NANS_CUDA_OK(cudaFuncSetAttribute(fkern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     static_cast<int>(plan.bytes)));
 

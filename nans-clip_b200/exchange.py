@@ -62,7 +62,7 @@ def make_desc(world: int, rank: int, bases, n_loc: int, D: int, epoch_ptr: int) 
 def eligible(n_loc: int, D: int, world: int) -> bool:
     """Shapes the push path serves: whole 256-column tiles per rank, the narrow-pair backward."""
     return world > 1 and world <= MAX_PEERS and n_loc > 0 and n_loc % 256 == 0 and D % 8 == 0 and D <= 1024 and \
-        not any(os.environ.get(v) for v in ("NANS_BWD_1CTA", "NANS_BWD_NP"))
+        os.environ.get("NANS_BWD_NP", "1") != "0"
 
 
 class PeerExchange:

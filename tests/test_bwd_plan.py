@@ -54,10 +54,10 @@ def test_schedule_invariants(rows, N, D, monkeypatch):
         assert p["ns_tail"] == 1 or units - p["n_full"] > 0
     if p["kind"] == 3:
         assert D <= 512 and p["zero"] == 2 and p["grid"] == 2 * p["npairs"] and p["npairs"] <= PAIRS
-        if p["t1"] > 0:   # helper schedule
-            assert p["punits"] == units < p["npairs"] == PAIRS
-            assert 1 <= p["t1"] < p["ntiles"]
-            assert p["punits"] * (p["ntiles"] - p["t1"]) >= p["npairs"] - p["punits"]   # no idle helper
+        # helper schedule (the only persistent one)
+        assert p["punits"] == units < p["npairs"] == PAIRS
+        assert 1 <= p["t1"] < p["ntiles"]
+        assert p["punits"] * (p["ntiles"] - p["t1"]) >= p["npairs"] - p["punits"]   # no idle helper
     if p["kind"] == 1:
         assert p["grid"] == 4 * p["nrb"] * p["npass"] * p["nsplit"] and p["zero"] == (2 if p["nsplit"] > 1 else 0)
 
@@ -76,14 +76,15 @@ def test_known_schedules(monkeypatch):
     assert (p["kind"], p["t1"], p["punits"], p["npairs"], p["zero"]) == (3, 112, 64, 74, 2)
     monkeypatch.setenv("NANS_BWD_PERSIST", "0")
     assert plan(4096, 32768, 512)["kind"] == 2
-    monkeypatch.setenv("NANS_BWD_PERSIST", "1")
-    p = plan(4096, 32768, 512)
-    assert (p["kind"], p["t1"], p["npairs"]) == (3, 0, 74)
     monkeypatch.delenv("NANS_BWD_PERSIST")
     monkeypatch.setenv("NANS_BWD_NP", "0")
     assert plan(4096, 32768, 512)["kind"] == 1
+    # the retired switches (single-CTA kernel, equal-range persistent schedule) no longer change anything
+    monkeypatch.delenv("NANS_BWD_NP")
     monkeypatch.setenv("NANS_BWD_1CTA", "1")
-    assert plan(4096, 32768, 512)["kind"] == 0
+    monkeypatch.setenv("NANS_BWD_PERSIST", "1")
+    p = plan(4096, 32768, 512)
+    assert (p["kind"], p["t1"]) == (3, 112)
 
 
 def test_bad_arguments_are_rejected():

@@ -1044,35 +1044,16 @@ def test_topk_full_gallery_properties(dev):
         assert int((mism & ~loose).sum()) == 0
 
 
-# --------------------------------------------------------------------------------------------
-# single-CTA fallbacks (NANS_*_1CTA=1): the CTA-pair kernels are the default everywhere above
-# --------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("n,d,s", [(300, 512, 14.2857), (1111, 768, 50.0), (513, 64, 5.0)])
-def test_single_cta_fallback_kernels(dev, monkeypatch, n, d, s):
-    from nans_clip_b200 import kernels as K
-    from oracle import clip_loss as OL
-    for var in ("NANS_FWD_1CTA", "NANS_BWD_1CTA", "NANS_TOPK_1CTA"):
-        monkeypatch.setenv(var, "1")
-    I, T = synth(n, d, 3 * n + d, 0.5)
-    want = OL.global_loss_and_grads(I, T, s, torch.float64)
-    loss, acc, dI, dT, ds = run_loss(dev, I, T, s)
-    assert abs(float(loss) - float(want["loss"])) <= TOL * abs(float(want["loss"])) + 1e-6 * s
-    assert grad_ok(dI, want["dI"], n, s) and grad_ok(dT, want["dT"], n, s)
-    assert abs(float(ds) - float(want["ds"])) <= TOL * abs(float(want["ds"])) + 1e-6
-    sc, idx = K.topk_ip(I.half().to(dev), T.half().to(dev), I.to(dev), T.to(dev), 10, 16, 0)
-    check_topk(idx.cpu(), sc.cpu(), T, I, 10)
-
-
-@pytest.mark.parametrize("persist", ["0", "1", "2"])
+@pytest.mark.parametrize("persist", ["0", "2"])
 @pytest.mark.parametrize("n,d,s,dt", [(300, 512, 14.2857, torch.float16), (1000, 256, 100.0, torch.float16),
                                       (2050, 448, 30.0, torch.bfloat16), (4099, 72, 5.0, torch.float16),
                                       (129, 512, 20.0, torch.float16)])
 def test_narrow_pair_backward_both_schedules(dev, monkeypatch, persist, n, d, s, dt):
     """NANS_BWD_PERSIST=0: one (row block, column split) unit per CTA pair, plain stores;
-    =1: the persistent schedule with equal contiguous tile ranges that cross row-block boundaries
-    (segments, red.add outputs); =2: the persistent helper schedule (every unit keeps a pair for its
-    first tiles, the idle pairs share the last tiles of all units) wherever it is feasible.  The
-    default is the helper schedule when there are fewer units than CTA pairs, else the first."""
+    =2: the persistent helper schedule (every unit keeps a pair for its first tiles, the idle pairs
+    share the last tiles of all units: segments that cross unit boundaries, red.add outputs) wherever
+    it is feasible.  The default is the helper schedule when there are fewer units than CTA pairs,
+    else the first."""
     from oracle import clip_loss as OL
     monkeypatch.setenv("NANS_BWD_PERSIST", persist)
     I, T = synth(n, d, 7 * n + d, 0.5)
@@ -1158,6 +1139,22 @@ def test_wide_pair_backward_fallback(dev, monkeypatch, n, d, s, dt):
     loss, acc, dI, dT, ds = run_loss(dev, I, T, s, dt=dt)
     tol = TOL if dt == torch.float16 else 3e-3
     assert grad_ok(dI, want["dI"], n, s, tol) and grad_ok(dT, want["dT"], n, s, tol)
+
+
+@pytest.mark.parametrize("n,d,s", [(700, 1536, 14.2857), (300, 2048, 30.0)])
+def test_wide_pair_backward_is_the_kernel_for_d_above_1024(dev, n, d, s):
+    """D > 1024 (no BASELINE config, but any D <= 8192 is accepted): dA of 64 rows no longer fits TMEM, the
+    128-row pair kernel with 256-feature passes runs by default."""
+    from nans_clip_b200 import _lib
+    from oracle import clip_loss as OL
+    import ctypes
+    out = (ctypes.c_int64 * 16)()
+    assert _lib.load().nans_clip_loss_bwd_plan(n, n, d, ctypes.cast(out, ctypes.c_void_p), 16) == 0 and out[0] == 1
+    I, T = synth(n, d, 13 * n + d, 0.5)
+    want = OL.global_loss_and_grads(I, T, s, torch.float64)
+    loss, acc, dI, dT, ds = run_loss(dev, I, T, s)
+    assert abs(float(loss) - float(want["loss"])) <= TOL * abs(float(want["loss"])) + 1e-6 * s
+    assert grad_ok(dI, want["dI"], n, s) and grad_ok(dT, want["dT"], n, s)
 
 
 # --------------------------------------------------------------------------------------------
