@@ -94,7 +94,8 @@ def np_(t):
 def gen_loss_w1():
     from cn_clip.training.train import get_loss
     cases = [("a", 48, 64, 0.0, 2.6593), ("b", 96, 128, 0.5, 2.6593), ("c", 33, 72, 0.5, 4.6052),
-             ("d", 200, 512, 0.5, 0.0), ("e", 1, 64, 0.5, 2.6593)]
+             ("d", 200, 512, 0.5, 0.0), ("e", 1, 64, 0.5, 2.6593),
+             ("f", 64, 1024, 0.5, 2.6593)]   # f: the loss shape of BASELINE.json configs[0] (batch 64, D = 1024)
     for name, n, d, corr, ls in cases:
         img, txt = synth(n, d, 1234 + n, corr)
         model = StubModel(img, txt, ls)
@@ -366,6 +367,9 @@ if __name__ == "__main__":
     install_shims()
     if len(sys.argv) > 1 and sys.argv[1] == "lora":
         gen_lora_loss()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "w1":
+        gen_loss_w1()
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "kd":
         gen_loss_kd()

@@ -112,7 +112,7 @@ def run_loss(dev, I, T, s, dt=torch.float16, **kw):
 
 
 @pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16], ids=["fp16", "bf16"])
-@pytest.mark.parametrize("name", ["a", "b", "c", "d", "e"])
+@pytest.mark.parametrize("name", ["a", "b", "c", "d", "e", "f"])
 def test_loss_matches_reference_get_loss(dev, golden_dir, name, dt):
     """Golden outputs of the reference's own get_loss (aggregate=False).  Every fixture runs in the
     product's default operand type (fp16) at the 1e-3 bar of BASELINE.json; bf16 operands are an extra

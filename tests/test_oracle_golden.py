@@ -20,7 +20,7 @@ def _t(a):
     return torch.from_numpy(np.asarray(a))
 
 
-@pytest.mark.parametrize("name", ["a", "b", "c", "d", "e"])
+@pytest.mark.parametrize("name", ["a", "b", "c", "d", "e", "f"])
 def test_local_loss_matches_reference(golden_dir, name):
     g = _load(golden_dir / f"loss_w1_{name}.npz")
     img, txt = _t(g["img"]).requires_grad_(True), _t(g["txt"]).requires_grad_(True)
