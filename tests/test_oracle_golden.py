@@ -208,4 +208,6 @@ def test_lora_label_smoothed_loss_matches_reference(golden_dir, name):
 
 def test_all_fixtures_are_covered(golden_dir):
     names = sorted(p.split("/")[-1] for p in glob.glob(str(golden_dir / "*.npz")))
-    assert len(names) == 24, names
+    # 25 fixtures checked against the oracle in this file + the 3 loss_kd_* ones, which pin the drop-in's
+    # distillation branch directly (tests/test_host_logic_gloo.py; the KD term is outside the fused path)
+    assert len(names) == 28, names
