@@ -294,6 +294,13 @@ int nans_xchg_push(const nans_xchg_t* x, const void* img, const void* txt, int x
                    int feat_dtype, int normalize, void* stream);
 int nans_xchg_cast_push(const nans_xchg_t* x, const void* img, const void* txt, int x_dtype, int64_t ld_x,
                         int feat_dtype, int normalize, void* I16_loc, void* T16_loc, void* stream);
+/* nans_xchg_push / nans_xchg_push_dma restricted to the peers rank - k, k in [k_begin, k_end) (1 <= k < world):
+ * the two engines can share the peers of one step (hybrid push: the copy engines serve the peers whose rows
+ * are needed first, a small push kernel — forked before the local cast — the ones needed last). */
+int nans_xchg_push_peers(const nans_xchg_t* x, const void* img, const void* txt, int x_dtype, int64_t ld_x,
+                         int feat_dtype, int normalize, int k_begin, int k_end, void* stream);
+int nans_xchg_push_dma_peers(const nans_xchg_t* x, const void* loc16, const uint32_t* stepvals, int slot,
+                             int k_begin, int k_end, void* stream, void* stream_b);
 
 /* The same exchange with the remote half on the COPY ENGINES (the default of the python layer): no SM
  * takes part in the NVLink traffic, so it neither slows the forward it runs under nor depends on being

@@ -36,6 +36,7 @@ struct PushParams {
   long long feat_off, fflag_off;
   long long slot_rows;  // world * n_loc
   const uint32_t* epoch;
+  int k_begin, k_end;   // REMOTE variant: peers rank - k for k in [k_begin, k_end)
   uint32_t* stepvals;   // LOCAL variant: [2][n_loc / 64] words = this step's number (source of the DMA'd flags)
   int expect_slot;      // LOCAL variant: the slot the host issued this step's DMA copies for, or -1
   uint8_t* base[NANS_MAX_PEERS];
@@ -140,7 +141,7 @@ __global__ void __launch_bounds__(PUSH_THREADS, 4) cast_push_kernel(const PushPa
         inv[i] = 1.0f / sqrtf(warp_sum(ss));  // same arithmetic as l2norm_cast_kernel
       }
     }
-    for (int k = REMOTE ? 1 : 0; k < (REMOTE ? p.world : 1); ++k) {
+    for (int k = REMOTE ? p.k_begin : 0; k < (REMOTE ? p.k_end : 1); ++k) {
       int dst = p.rank - k;
       if (dst < 0) dst += p.world;
       uint8_t* drow0 = p.base[dst] + mod_off + (static_cast<long long>(p.rank) * p.n_loc + r0) * D * 2;
@@ -298,7 +299,7 @@ extern "C" int nans_xchg_layout(nans_xchg_t* x, int64_t n_loc, int64_t D) {
 
 static int launch_cast_push(bool remote, const nans_xchg_t* x, const void* img, const void* txt, int x_dtype,
                             int64_t ld_x, int feat_dtype, int normalize, void* I16_loc, void* T16_loc, void* stream,
-                            uint32_t* stepvals = nullptr, int expect_slot = -1) {
+                            uint32_t* stepvals = nullptr, int expect_slot = -1, int k_begin = 1, int k_end = -1) {
   const char* who = remote ? "xchg_push" : "xchg_cast_local";
   int rc = check_device();
   if (rc != NANS_OK) return rc;
@@ -310,7 +311,10 @@ static int launch_cast_push(bool remote, const nans_xchg_t* x, const void* img, 
   NANS_REQUIRE((reinterpret_cast<uintptr_t>(img) & 15) == 0 && (reinterpret_cast<uintptr_t>(txt) & 15) == 0 &&
                    (ld_x * (x_dtype == NANS_F32 ? 4 : 2)) % 16 == 0,
                "%s: feature rows must be 16-byte aligned", who);
-  if (remote && x->world == 1) return NANS_OK;
+  if (k_end < 0) k_end = x->world;
+  NANS_REQUIRE(!remote || (k_begin >= 1 && k_end <= x->world), "%s: peer range [%d, %d) outside [1, world)", who,
+               k_begin, k_end);
+  if (remote && k_begin >= k_end) return NANS_OK;
   PushParams p;
   fill_push_params(p, x);
   p.src[0] = img;
@@ -323,6 +327,8 @@ static int launch_cast_push(bool remote, const nans_xchg_t* x, const void* img, 
   p.ld_x = ld_x;
   p.stepvals = stepvals;
   p.expect_slot = expect_slot;
+  p.k_begin = k_begin;
+  p.k_end = k_end;
   const dim3 grid(push_grid_x(x->n_loc, remote), 2);
   if (remote) {
     // same shared-memory carve-out as the forward (which takes nearly all of it): an SM does not have to
@@ -350,6 +356,13 @@ extern "C" int nans_xchg_cast_local(const nans_xchg_t* x, const void* img, const
 extern "C" int nans_xchg_push(const nans_xchg_t* x, const void* img, const void* txt, int x_dtype, int64_t ld_x,
                               int feat_dtype, int normalize, void* stream) {
   return launch_cast_push(true, x, img, txt, x_dtype, ld_x, feat_dtype, normalize, nullptr, nullptr, stream);
+}
+
+extern "C" int nans_xchg_push_peers(const nans_xchg_t* x, const void* img, const void* txt, int x_dtype,
+                                    int64_t ld_x, int feat_dtype, int normalize, int k_begin, int k_end,
+                                    void* stream) {
+  return launch_cast_push(true, x, img, txt, x_dtype, ld_x, feat_dtype, normalize, nullptr, nullptr, stream, nullptr,
+                          -1, k_begin, k_end);
 }
 
 extern "C" int nans_xchg_cast_push(const nans_xchg_t* x, const void* img, const void* txt, int x_dtype,
@@ -383,6 +396,11 @@ extern "C" int nans_xchg_cast_local_dma(const nans_xchg_t* x, const void* img, c
 // `stream_b` (optional): a second stream for every other peer, so that two copy engines work at once.
 extern "C" int nans_xchg_push_dma(const nans_xchg_t* x, const void* loc16, const uint32_t* stepvals, int slot,
                                   void* stream, void* stream_b) {
+  return nans_xchg_push_dma_peers(x, loc16, stepvals, slot, 1, x != nullptr ? x->world : 1, stream, stream_b);
+}
+
+extern "C" int nans_xchg_push_dma_peers(const nans_xchg_t* x, const void* loc16, const uint32_t* stepvals, int slot,
+                                        int k_begin, int k_end, void* stream, void* stream_b) {
   int rc = check_device();
   if (rc != NANS_OK) return rc;
   if ((rc = check_xchg(x, "xchg_push_dma")) != NANS_OK) return rc;
@@ -392,13 +410,22 @@ extern "C" int nans_xchg_push_dma(const nans_xchg_t* x, const void* loc16, const
   const size_t blk_bytes = static_cast<size_t>(x->n_loc) * row_bytes;         // one modality of this rank
   const size_t mod_pitch = 2 * N * row_bytes;                                 // image slot 0 -> text slot 0
   const size_t nflag = static_cast<size_t>(x->n_loc / NANS_XCHG_FLAG_ROWS);
-  for (int k = 1; k < x->world; ++k) {
+  const char* e2d = getenv("NANS_PUSH_2D");
+  const bool one_d = e2d != nullptr && e2d[0] == '0';
+  NANS_REQUIRE(k_begin >= 1 && k_end <= x->world, "xchg_push_dma: peer range outside [1, world)");
+  for (int k = k_begin; k < k_end; ++k) {
     const int dst = (x->rank - k + x->world) % x->world;
     // two streams = two copy engines: peers k = 1, 3, 5, ... on the first, 2, 4, 6, ... on the second
     cudaStream_t st = static_cast<cudaStream_t>((stream_b != nullptr && (k & 1) == 0) ? stream_b : stream);
     uint8_t* d = static_cast<uint8_t*>(x->base[dst]);
     uint8_t* drows = d + x->feat_off + (static_cast<size_t>(slot) * N + static_cast<size_t>(x->rank) * x->n_loc) * row_bytes;
-    NANS_CUDA_OK(cudaMemcpy2DAsync(drows, mod_pitch, loc16, blk_bytes, blk_bytes, 2, cudaMemcpyDeviceToDevice, st));
+    if (one_d) {   // NANS_PUSH_2D=0 (measurement): one linear copy per modality
+      NANS_CUDA_OK(cudaMemcpyAsync(drows, loc16, blk_bytes, cudaMemcpyDeviceToDevice, st));
+      NANS_CUDA_OK(cudaMemcpyAsync(drows + mod_pitch, static_cast<const uint8_t*>(loc16) + blk_bytes, blk_bytes,
+                                   cudaMemcpyDeviceToDevice, st));
+    } else {
+      NANS_CUDA_OK(cudaMemcpy2DAsync(drows, mod_pitch, loc16, blk_bytes, blk_bytes, 2, cudaMemcpyDeviceToDevice, st));
+    }
     uint8_t* dflag = d + x->fflag_off + static_cast<size_t>(x->rank) * nflag * 4;
     NANS_CUDA_OK(cudaMemcpy2DAsync(dflag, static_cast<size_t>(x->world) * nflag * 4, stepvals, nflag * 4, nflag * 4, 2,
                                    cudaMemcpyDeviceToDevice, st));

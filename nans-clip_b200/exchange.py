@@ -83,6 +83,7 @@ class PeerExchange:
         self.push_stream = torch.cuda.Stream(self.dev)   # the NVLink push runs under the forward
         self.push_stream_b = torch.cuda.Stream(self.dev)  # a second copy engine for every other peer
         self.fork = torch.cuda.Event()
+        self.fork2 = torch.cuda.Event()
         self.join = torch.cuda.Event()
         self.join_b = torch.cuda.Event()
         self.broken = False

@@ -256,16 +256,18 @@ def _xchg_sources(desc, img: torch.Tensor, txt: torch.Tensor):
 
 
 def xchg_push(desc, img: torch.Tensor, txt: torch.Tensor, feat_dtype: torch.dtype, normalize: bool = False,
-              stream: "torch.cuda.Stream | None" = None):
+              stream: "torch.cuda.Stream | None" = None, peers: "tuple[int, int] | None" = None):
     """Kernel (1) into every PEER's gathered slot over NVLink (`stream`: a side stream forked before
-    xchg_cast_local, so that the traffic runs under the forward; default the current stream).  Returns the
-    (possibly re-laid-out) sources it reads: keep them alive until the side stream has been joined."""
+    xchg_cast_local, so that the traffic runs under the forward; default the current stream).  `peers` =
+    (k_begin, k_end): only the peers rank - k for k in that range.  Returns the (possibly re-laid-out)
+    sources it reads: keep them alive until the side stream has been joined."""
     img, txt = _xchg_sources(desc, img, txt)
+    k0, k1 = peers if peers is not None else (1, int(desc.world))
     with _on_device(img.device) as cur:
-        check(_lib.load().nans_xchg_push(_desc_ref(desc), img.data_ptr(), txt.data_ptr(), dtype_code(img.dtype),
-                                         img.stride(0), dtype_code(feat_dtype), 1 if normalize else 0,
-                                         stream.cuda_stream if stream is not None else cur))
-    _count(1 if desc.world > 1 else 0)
+        check(_lib.load().nans_xchg_push_peers(_desc_ref(desc), img.data_ptr(), txt.data_ptr(), dtype_code(img.dtype),
+                                               img.stride(0), dtype_code(feat_dtype), 1 if normalize else 0, k0, k1,
+                                               stream.cuda_stream if stream is not None else cur))
+    _count(1 if k1 > k0 else 0)
     return img, txt
 
 
@@ -300,12 +302,14 @@ def xchg_cast_local_dma(desc, img: torch.Tensor, txt: torch.Tensor, feat_dtype: 
 
 
 def xchg_push_dma(desc, loc16: torch.Tensor, stepvals: torch.Tensor, slot: int, stream: "torch.cuda.Stream",
-                  stream_b: "torch.cuda.Stream | None" = None) -> None:
-    """The rows and their flags into every peer's buffers with copy-engine copies on `stream` (and, for every
-    other peer, `stream_b`)."""
+                  stream_b: "torch.cuda.Stream | None" = None, peers: "tuple[int, int] | None" = None) -> None:
+    """The rows and their flags into the peers' buffers with copy-engine copies on `stream` (and, for every
+    other peer, `stream_b`); `peers` = (k_begin, k_end) as in xchg_push."""
     _require_cuda(loc16, stepvals)
-    check(_lib.load().nans_xchg_push_dma(_desc_ref(desc), loc16.data_ptr(), stepvals.data_ptr(), int(slot),
-                                         stream.cuda_stream, stream_b.cuda_stream if stream_b is not None else None))
+    k0, k1 = peers if peers is not None else (1, int(desc.world))
+    check(_lib.load().nans_xchg_push_dma_peers(_desc_ref(desc), loc16.data_ptr(), stepvals.data_ptr(), int(slot), k0, k1,
+                                               stream.cuda_stream,
+                                               stream_b.cuda_stream if stream_b is not None else None))
 
 
 def xchg_cast_push(desc, img: torch.Tensor, txt: torch.Tensor, feat_dtype: torch.dtype, normalize: bool = False):

@@ -98,21 +98,25 @@ class _ClipLossFn(torch.autograd.Function):
             main = torch.cuda.current_stream(dev)
             mode = os.environ.get("NANS_PUSH", "dma")
             keep = None
-            if mode == "dma":
+            if mode in ("dma", "hybrid"):
                 slot = (ex.forwards + 1) & 1
+                # hybrid: the copy engines serve the peers whose rows are needed first (k = 1 .. kd), a small
+                # push kernel — forked FIRST, so that its grid is resident before the forward's — the rest
+                kd = W if mode == "dma" else min(W, 1 + int(os.environ.get("NANS_PUSH_DMA_PEERS", str((W + 1) // 2))))
+                if kd < W:
+                    ex.fork.record(main)
+                    ex.push_stream_b.wait_event(ex.fork)
+                    keep_sm = K.xchg_push(desc, src_i, src_t, cfg.feat_dtype, stream=ex.push_stream_b, peers=(kd, W))
+                    ex.join_b.record(ex.push_stream_b)
                 loc16, stepvals = K.xchg_cast_local_dma(desc, src_i, src_t, cfg.feat_dtype, slot)
                 I16, T16 = loc16[0], loc16[1]
-                ex.fork.record(main)
-                ex.push_stream.wait_event(ex.fork)
-                two = W > 2 and os.environ.get("NANS_PUSH_STREAMS", "1") == "2"
-                if two:
-                    ex.push_stream_b.wait_event(ex.fork)
-                K.xchg_push_dma(desc, loc16, stepvals, slot, ex.push_stream, ex.push_stream_b if two else None)
-                if two:
-                    ex.join_b.record(ex.push_stream_b)
+                ex.fork2.record(main)
+                ex.push_stream.wait_event(ex.fork2)
+                K.xchg_push_dma(desc, loc16, stepvals, slot, ex.push_stream, None, peers=(1, kd))
+                if kd < W:
                     ex.push_stream.wait_event(ex.join_b)
                 ex.join.record(ex.push_stream)
-                keep = (loc16, stepvals)
+                keep = (loc16, stepvals, keep_sm if kd < W else None)
             elif mode == "sm":
                 # push kernel on the SMs, forked FIRST so that its grid is resident before the forward's
                 ex.fork.record(main)

@@ -692,7 +692,7 @@ def test_rank_strip_at_bench_sizes(dev, W, rank, n_loc, d, chunk):
 @pytest.mark.parametrize("W,n_loc,d,s,in_dt", [(2, 256, 128, 20.0, torch.float32), (4, 512, 512, 14.2857, torch.float32),
                                                (8, 256, 72, 50.0, torch.float16), (3, 768, 768, 14.2857, torch.float32),
                                                (2, 256, 1024, 5.0, torch.bfloat16), (4, 1024, 64, 14.2857, torch.float32)])
-@pytest.mark.parametrize("push", ["sm", "dma"])
+@pytest.mark.parametrize("push", ["sm", "dma", "hybrid"])
 def test_push_exchange_emulated_ranks(dev, W, n_loc, d, s, in_dt, push):
     """The NVLink push data plane (csrc/exchange.cu + the exchange modes of kernels (2)/(3)) with the W
     ranks of a job EMULATED one after the other on this GPU: W exchange buffers in one process stand for
@@ -717,12 +717,15 @@ def test_push_exchange_emulated_ranks(dev, W, n_loc, d, s, in_dt, push):
         if push == "sm":     # push kernel (st.global on the peers' buffers)
             loc = [K.xchg_cast_push(descs[r], I[rows[r]].to(dev).to(in_dt), T[rows[r]].to(dev).to(in_dt), feat)
                    for r in range(W)]
-        else:                # copy engines: strided copies of the rows, then of the flag words
-            loc = []
+        else:                # copy engines: strided copies of the rows, then of the flag words;
+            loc = []         # hybrid: the first peers by copy engine, the last ones by the push kernel
+            kd = W if push == "dma" else 1 + (W + 1) // 2
             for r in range(W):
-                l16, sv = K.xchg_cast_local_dma(descs[r], I[rows[r]].to(dev).to(in_dt), T[rows[r]].to(dev).to(in_dt),
-                                                feat, (step + 1) & 1)
-                K.xchg_push_dma(descs[r], l16, sv, (step + 1) & 1, torch.cuda.current_stream(), None)
+                src_i, src_t = I[rows[r]].to(dev).to(in_dt), T[rows[r]].to(dev).to(in_dt)
+                if kd < W:
+                    K.xchg_push(descs[r], src_i, src_t, feat, peers=(kd, W))
+                l16, sv = K.xchg_cast_local_dma(descs[r], src_i, src_t, feat, (step + 1) & 1)
+                K.xchg_push_dma(descs[r], l16, sv, (step + 1) & 1, torch.cuda.current_stream(), None, peers=(1, min(kd, W)))
                 assert bool((sv == step + 1).all())
                 loc.append((l16[0], l16[1]))
         for r in range(W):   # the local copies are the cast rows
