@@ -190,8 +190,11 @@ __global__ void __cluster_dims__(CP ? 2 : 1, 1, 1) __launch_bounds__(NUM_THREADS
 topk_sweep_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmG,
                   const TopkParams p) {
   const int unit = CP ? (blockIdx.x >> 1) : blockIdx.x;
-  const int split = unit % p.nsplit;
-  const int qb = unit / p.nsplit;
+  // split-major unit order: the CTA pairs that run together belong to the SAME gallery split and walk its
+  // tiles in lockstep, so a tile is fetched from HBM once per wave instead of once per query block
+  // (query-block-major order: ncu dram__bytes_read 17.7 GB for a 1 GB gallery at Q = 30000, L2 hit 79 %)
+  const int split = unit / p.nqb;
+  const int qb = unit - split * p.nqb;
 
   SweepArgs a;
   a.tmA = &tmQ;
