@@ -9,8 +9,9 @@ ranks (strong scaling: the global batch is fixed), synthetic unit-norm features 
 A step is one fwd+bwd of the loss through the public call (`clip_contrastive_loss`: 16-bit cast,
 feature exchange, fused forward, lse/scalar exchange, fused backward).
   value : pairs/s = 32768 / step time, inputs resident in HBM, CUDA events, max over ranks
-  e2e   : the same step with HOST (pinned) fp32 features: H2D of the step's features inside the timed
-          region, loss scalar read back
+  e2e   : the same step with HOST (pinned) fp32 features: H2D of every step's features inside the timed
+          region (pipelined: step k+1's copy runs under step k's compute; the strictly serial figure is
+          reported beside it as e2e.serial_ms_per_step), loss scalar read back every step
   roofline : the dominant kernel (fused backward), algorithmic flops / its measured launch time,
              against the measured bf16 burst peak in MEASURED_PEAKS.json
   cpu_baseline : the oracle (fp32 torch port of the reference path) on this box's host cores (N=1 only)
@@ -492,6 +493,19 @@ def loss_step_bench(args, dist, W, rank, dev, n_global, d, with_e2e, kernel_roof
             out["e2e_eager_ms"] = timed_steps(step_e2e, args.steps, 2, flush, dist, dev) / args.steps
         out["e2e_graphed"] = e2e_graphed
         out["e2e_loss_seen"] = seen[-1] if seen else None
+        out["e2e_serial_ms"] = out["e2e_ms"]
+        # ---- the same end-to-end step with the input copies PIPELINED (what a data loader with pinned memory
+        # and non_blocking copies does): the H2D copy of step k + 1's features runs on a copy stream while step
+        # k computes.  Every step's copy and every step's loss read-back are inside the timed region (K steps,
+        # K copies: the first step copies its own inputs and waits for them, the last one prefetches nothing).
+        try:
+            out["e2e_ms"] = pipelined_e2e(args, dist, dev, flush, graphs if graphed else [], img_h, txt_h, loss_h, s,
+                                          group, feat_dt, seen)
+            out["e2e_pipelined"] = True
+        except Exception as exc:
+            print(f"[bench] pipelined e2e failed, reporting the serial e2e step: {exc!r}", file=sys.stderr)
+            out["e2e_pipelined"] = False
+        out["e2e_loss_seen"] = seen[-1] if seen else None
     if kernel_rooflines:
         # ---- forward and backward kernels timed alone, on this rank ----
         with torch.no_grad():
@@ -548,6 +562,88 @@ def loss_step_bench(args, dist, W, rank, dev, n_global, d, with_e2e, kernel_roof
                                "hardware_tflops": 2 * fwd_alg / (fwd_ms / 1e3) / 1e12}
     del flush
     return out
+
+
+def pipelined_e2e(args, dist, dev, flush, graphs, img_h, txt_h, loss_h, s, group, feat_dt, seen):
+    """K end-to-end steps with double-buffered device inputs: returns ms per step (max over ranks)."""
+    from nans_clip_b200.loss import clip_contrastive_loss
+    main = torch.cuda.current_stream(dev)
+    copy_stream = torch.cuda.Stream(dev)
+    bufs = [(torch.empty(img_h.shape, device=dev).requires_grad_(True), torch.empty(txt_h.shape, device=dev).requires_grad_(True))
+            for _ in range(2)]
+    copied = [torch.cuda.Event(), torch.cuda.Event()]
+    consumed = [torch.cuda.Event(), torch.cuda.Event()]
+
+    def issue_copy(p):   # H2D of one step's features into input buffer set p, on the copy stream
+        copy_stream.wait_event(consumed[p])          # the step that last read this set has finished
+        with torch.cuda.stream(copy_stream), torch.no_grad():
+            bufs[p][0].copy_(img_h, non_blocking=True)
+            bufs[p][1].copy_(txt_h, non_blocking=True)
+        copied[p].record(copy_stream)
+
+    def compute_body(p):
+        i, t = bufs[p]
+        i.grad = t.grad = s.grad = None
+        loss, _ = clip_contrastive_loss(i, t, s, group=group, feat_dtype=feat_dt)
+        loss.backward()
+        loss_h.copy_(loss.detach().reshape(1), non_blocking=True)     # D2H of the step's result
+
+    pgraphs = []
+    if graphs:   # same launch mode as the device-timed value: one captured step per input buffer set (= per
+        for p in range(2):   # parity of the double-buffered exchange), replayed alternately
+            consumed[p].record(main)
+            issue_copy(p)
+        torch.cuda.synchronize()
+        for p in range(2):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                compute_body(p)
+            pgraphs.append(g)
+        torch.cuda.synchronize()
+    count = [0]
+
+    def run(k, first, last):
+        p = count[0] & 1
+        if first:
+            issue_copy(p)                            # this step's own inputs: nothing to hide them behind
+        if not last:
+            issue_copy(p ^ 1)                        # the next step's inputs, under this step's compute
+        main.wait_event(copied[p])
+        if pgraphs:
+            pgraphs[p].replay()
+        else:
+            compute_body(p)
+        consumed[p].record(main)
+        count[0] += 1
+        main.synchronize()
+        seen.append(float(loss_h[0]))                # the host reads the loss every step
+
+    for p in range(2):
+        consumed[p].record(main)
+    K_, Wm = args.steps, min(args.warmup, 3)
+    for k in range(Wm):                              # warm-up: same loop, untimed
+        flush.zero_()
+        run(k, k == 0, k == Wm - 1)
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    evs = []
+    for k in range(K_):
+        flush.zero_()
+        a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        run(k, k == 0, k == K_ - 1)
+        e.record()
+        evs.append((a, e))
+    torch.cuda.synchronize()
+    if pgraphs and count[0] % 2:   # leave the exchange on the parity the host expects
+        run(0, True, True)
+    if dist is not None:
+        dist.barrier()
+    total = torch.tensor([sum(a.elapsed_time(e) for a, e in evs)], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(total, op=dist.ReduceOp.MAX)
+    return float(total.item()) / K_
 
 
 def bench_loss_d1024(args, dist, W, rank, dev, local):
@@ -769,9 +865,12 @@ def bench_main(args):
             "frac_of_bf16_peak_algorithmic": step_alg / (ms / 1e3) / 1e12 / (W * peaks["bf16_tflops"]),
             "e2e": {"value": N_GLOBAL / (e2e_ms / 1e3), "unit": "pairs/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": 2 * n_loc * D * 4, "d2h_bytes_per_step": 4,
-                    "launch": ("cuda-graph replay of the whole step incl. the H2D / D2H copies" if r.get("e2e_graphed")
-                               else "eager"),
-                    "eager_ms_per_step": r.get("e2e_eager_ms"), "loss_read_back": r.get("e2e_loss_seen")},
+                    "launch": ("cuda-graph replay of the compute of a step" if r["graphed"] else "eager"),
+                    "pipeline": ("the H2D copy of step k+1's features (pinned host -> device, copy stream, double-buffered "
+                                 "inputs) runs while step k computes; every step's copy and loss read-back are inside the "
+                                 "timed region (K steps, K copies)") if r.get("e2e_pipelined") else "none (serial)",
+                    "serial_ms_per_step": r.get("e2e_serial_ms"), "serial_eager_ms_per_step": r.get("e2e_eager_ms"),
+                    "loss_read_back": r.get("e2e_loss_seen")},
             "gpu_launches": r["launches_per_step"] * args.steps,
             "gpu_launches_per_step": r["launches_per_step"],
             "roofline": r["roofline"], "roofline_fwd": r["roofline_fwd"],
