@@ -959,14 +959,14 @@ def main():
                     help="tests/test_bench_contract.py only: reference arm at a reduced global batch (the line's "
                          "config.workload says so); never used by a measurement")
     ap.add_argument("--graph", dest="graph", action="store_true", default=None,
-                    help="time CUDA-graph replays of the captured step (default at N > 1 when the push exchange is "
-                         "active: the step is launch-bound there; the eager time is reported beside it)")
+                    help="time CUDA-graph replays of the captured step (the default: 1 GPU, or N > 1 with the push "
+                         "exchange active; the eager time is reported beside it as eager_ms_per_step)")
     ap.add_argument("--no-graph", dest="graph", action="store_false")
     args = ap.parse_args()
     if args.workload and not args.only:
         args.only = args.workload
     if args.graph is None:
-        args.graph = int(os.environ.get("WORLD_SIZE", "1")) > 1
+        args.graph = True   # the step is replayed as a captured graph wherever capture works (eager otherwise)
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference_arm(args)
