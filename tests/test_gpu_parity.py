@@ -917,6 +917,31 @@ def test_topk_nan_rows_still_emit_valid_ids(dev):
     assert torch.equal(i[ok] - 7000, ri[:, :10])
 
 
+@pytest.mark.parametrize("G,k", [(5000, 50), (20000, 100), (40, 50), (3000, 33)])
+def test_topk_beyond_32(dev, G, k):
+    """--top-k above 32 (the reference accepts any k, make_topk_predictions.py:29-33): partitioned search +
+    verified merge, incl. a query whose whole top-k sits in ONE contiguous cluster of the gallery (every
+    first-level partition list would be truncated: forces the refinement) and a gallery smaller than k."""
+    from nans_clip_b200.retrieval import GalleryShard
+    D, Q = 64, 40
+    g = torch.Generator().manual_seed(G + k)
+    gal = torch.nn.functional.normalize(torch.randn(G, D, generator=g), dim=-1)
+    qry = torch.nn.functional.normalize(torch.randn(Q, D, generator=g), dim=-1)
+    if G >= 3000:   # rows 1000 .. 1000 + 2k are near-copies of query 0
+        gal[1000:1000 + 2 * k] = torch.nn.functional.normalize(qry[0][None, :] + 0.05 * torch.randn(2 * k, D, generator=g), dim=-1)
+    gal, qry = gal.half().float(), qry.half().float()
+    s, i = GalleryShard(gal, dev, torch.float16, 1000000).search(qry, k)
+    s, i = s.cpu(), i.cpu()
+    assert s.shape == (Q, k) and i.shape == (Q, k)
+    kk = min(k, G)
+    assert bool((i[:, :kk] >= 1000000).all()) and all(len(set(r[:kk])) == kk for r in i.tolist())
+    if G < k:
+        assert bool((i[:, G:] == -1).all()) and bool(torch.isinf(s[:, G:]).all())
+    if G >= 3000:
+        assert bool(((i[0] - 1000000 >= 1000) & (i[0] - 1000000 < 1000 + 2 * k)).all())   # the cluster, nothing else
+    check_topk(i - 1000000, s, gal, qry, k)
+
+
 def test_topk_exact_ties_keep_gallery_order(dev):
     from nans_clip_b200 import kernels as K
     g = torch.Generator().manual_seed(1)
@@ -971,6 +996,31 @@ def test_cli_dropin_writes_the_reference_output(dev, golden_dir, tmp_path):
     got = [json.loads(l) for l in open(out2)]
     assert [o["image_id"] for o in got] == g["i2t_image_ids"].tolist()
     assert [o["text_ids"] for o in got] == g["i2t_text_ids"].tolist()
+
+
+def test_cli_accepts_top_k_above_32(dev, golden_dir, tmp_path):
+    """The reference CLI takes any --top-k (make_topk_predictions.py:29-33); so does the drop-in."""
+    from nans_clip_b200.eval import make_topk_predictions as t2i
+    from oracle import topk as OT
+    g = np.load(golden_dir / "topk_c.npz")
+    fi, ft = tmp_path / "img.jsonl", tmp_path / "txt.jsonl"
+    with open(fi, "w") as f:
+        for iid, feat in zip(g["image_ids"].tolist(), g["gallery"].tolist()):
+            f.write(json.dumps({"image_id": iid, "feature": feat}) + "\n")
+    with open(ft, "w") as f:
+        for tid, feat in zip(g["text_ids"].tolist(), g["queries"].tolist()):
+            f.write(json.dumps({"text_id": tid, "feature": feat}) + "\n")
+    out = tmp_path / "t2i.jsonl"
+    k = min(40, len(g["image_ids"]))
+    t2i.main(["--image-feats", str(fi), "--text-feats", str(ft), "--top-k", "40", "--output", str(out)])
+    got = [json.loads(l) for l in open(out)]
+    rs, ri = OT.topk_vectorised(torch.from_numpy(g["gallery"]), torch.from_numpy(g["queries"]), k + 1)
+    pos_of = {int(i): n for n, i in enumerate(g["image_ids"].tolist())}
+    idx = torch.tensor([[pos_of[i] for i in o["image_ids"]] for o in got])
+    assert idx.shape[1] == k and all(len(set(o["image_ids"])) == k for o in got)
+    mism = idx != ri[:, :k]
+    loose = OT.excusable(rs[:, :k + 1] if rs.shape[1] > k else torch.cat([rs, torch.full((rs.shape[0], 1), -1e30)], 1), 1e-4)
+    assert int((mism & ~loose).sum()) == 0
 
 
 def test_cli_reads_binary_feature_shards(dev, golden_dir, tmp_path):
