@@ -538,10 +538,15 @@ def loss_step_bench(args, dist, W, rank, dev, n_global, d, with_e2e, kernel_roof
             lse_pad = torch.empty((2, pad), dtype=torch.float32, device=dev)[:, :n_global]
             lse_pad.copy_(lse_all)
             gout = torch.ones(1, device=dev)
+            # lse min / max in the kernel's order-preserving int encoding (the step gets them from the
+            # exchange-finish launch): the timed launch is the backward kernel alone, as in the step
+            bits = torch.stack([lse_pad.min(), lse_pad.max()]).view(torch.int32)
+            mm = torch.where(bits >= 0, bits, bits ^ 0x7fffffff).contiguous()
 
             def bwd_only():
                 K.bwd(I16, T16, T_all, I_all, label_begin=rank * n_loc, s_dev=s_dev, lse_all=lse_pad,
-                      grad_out=gout, grad_mult=1.0, row_begin=0, row_count=n_loc, out_dtype=torch.float32)
+                      grad_out=gout, grad_mult=1.0, row_begin=0, row_count=n_loc, out_dtype=torch.float32,
+                      lse_minmax=mm)
 
             kb = max(3, min(args.steps, 10))
             bwd_ms = timed_steps(bwd_only, kb, 2, flush, None, dev) / kb
