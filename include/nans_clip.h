@@ -300,7 +300,7 @@ int nans_xchg_cast_push(const nans_xchg_t* x, const void* img, const void* txt, 
 int nans_xchg_push_peers(const nans_xchg_t* x, const void* img, const void* txt, int x_dtype, int64_t ld_x,
                          int feat_dtype, int normalize, int k_begin, int k_end, void* stream);
 int nans_xchg_push_dma_peers(const nans_xchg_t* x, const void* loc16, const uint32_t* stepvals, int slot,
-                             int k_begin, int k_end, void* stream, void* stream_b);
+                             int k_begin, int k_end, void* stream);
 
 /* The same exchange with the remote half on the COPY ENGINES (the default of the python layer): no SM
  * takes part in the NVLink traffic, so it neither slows the forward it runs under nor depends on being
@@ -315,8 +315,7 @@ int nans_xchg_push_dma_peers(const nans_xchg_t* x, const void* loc16, const uint
 int nans_xchg_cast_local_dma(const nans_xchg_t* x, const void* img, const void* txt, int x_dtype, int64_t ld_x,
                              int feat_dtype, int normalize, void* loc16, uint32_t* stepvals, int slot,
                              void* stream);
-int nans_xchg_push_dma(const nans_xchg_t* x, const void* loc16, const uint32_t* stepvals, int slot, void* stream,
-                       void* stream_b /* optional second stream: every other peer, a second copy engine */);
+int nans_xchg_push_dma(const nans_xchg_t* x, const void* loc16, const uint32_t* stepvals, int slot, void* stream);
 
 /* Kernel (2) over the gathered buffers: both strips of this rank against all world * n_loc columns in
  * ONE launch.  Every unit walks the column tiles source by source starting with its own rank's (local,

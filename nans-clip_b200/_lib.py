@@ -77,9 +77,9 @@ _SIGNATURES = {
     "nans_xchg_push": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_void_p]),
     "nans_xchg_cast_local_dma": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_void_p, c_void_p,
                                          c_int, c_void_p]),
-    "nans_xchg_push_dma": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    "nans_xchg_push_dma": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "nans_xchg_push_peers": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_int, c_int, c_void_p]),
-    "nans_xchg_push_dma_peers": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "nans_xchg_push_dma_peers": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "nans_xchg_cast_push": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_void_p, c_void_p,
                                     c_void_p]),
     "nans_clip_loss_fwd_xchg_slots": (c_int64, [c_int64, c_int64, c_int64]),

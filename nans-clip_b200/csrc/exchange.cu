@@ -393,14 +393,13 @@ extern "C" int nans_xchg_cast_local_dma(const nans_xchg_t* x, const void* img, c
 // words (stepvals) into the peer's flag table.  cudaMemcpy2DAsync on peer-mapped addresses: the copy
 // engines move the data over NVLink, no SM is involved, nothing can starve or be starved by the forward
 // running meanwhile, and copies of one stream complete in order (flags after the rows they announce).
-// `stream_b` (optional): a second stream for every other peer, so that two copy engines work at once.
 extern "C" int nans_xchg_push_dma(const nans_xchg_t* x, const void* loc16, const uint32_t* stepvals, int slot,
-                                  void* stream, void* stream_b) {
-  return nans_xchg_push_dma_peers(x, loc16, stepvals, slot, 1, x != nullptr ? x->world : 1, stream, stream_b);
+                                  void* stream) {
+  return nans_xchg_push_dma_peers(x, loc16, stepvals, slot, 1, x != nullptr ? x->world : 1, stream);
 }
 
 extern "C" int nans_xchg_push_dma_peers(const nans_xchg_t* x, const void* loc16, const uint32_t* stepvals, int slot,
-                                        int k_begin, int k_end, void* stream, void* stream_b) {
+                                        int k_begin, int k_end, void* stream) {
   int rc = check_device();
   if (rc != NANS_OK) return rc;
   if ((rc = check_xchg(x, "xchg_push_dma")) != NANS_OK) return rc;
@@ -410,22 +409,15 @@ extern "C" int nans_xchg_push_dma_peers(const nans_xchg_t* x, const void* loc16,
   const size_t blk_bytes = static_cast<size_t>(x->n_loc) * row_bytes;         // one modality of this rank
   const size_t mod_pitch = 2 * N * row_bytes;                                 // image slot 0 -> text slot 0
   const size_t nflag = static_cast<size_t>(x->n_loc / NANS_XCHG_FLAG_ROWS);
-  const char* e2d = getenv("NANS_PUSH_2D");
-  const bool one_d = e2d != nullptr && e2d[0] == '0';
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
   NANS_REQUIRE(k_begin >= 1 && k_end <= x->world, "xchg_push_dma: peer range outside [1, world)");
   for (int k = k_begin; k < k_end; ++k) {
     const int dst = (x->rank - k + x->world) % x->world;
-    // two streams = two copy engines: peers k = 1, 3, 5, ... on the first, 2, 4, 6, ... on the second
-    cudaStream_t st = static_cast<cudaStream_t>((stream_b != nullptr && (k & 1) == 0) ? stream_b : stream);
     uint8_t* d = static_cast<uint8_t*>(x->base[dst]);
     uint8_t* drows = d + x->feat_off + (static_cast<size_t>(slot) * N + static_cast<size_t>(x->rank) * x->n_loc) * row_bytes;
-    if (one_d) {   // NANS_PUSH_2D=0 (measurement): one linear copy per modality
-      NANS_CUDA_OK(cudaMemcpyAsync(drows, loc16, blk_bytes, cudaMemcpyDeviceToDevice, st));
-      NANS_CUDA_OK(cudaMemcpyAsync(drows + mod_pitch, static_cast<const uint8_t*>(loc16) + blk_bytes, blk_bytes,
-                                   cudaMemcpyDeviceToDevice, st));
-    } else {
-      NANS_CUDA_OK(cudaMemcpy2DAsync(drows, mod_pitch, loc16, blk_bytes, blk_bytes, 2, cudaMemcpyDeviceToDevice, st));
-    }
+    // one strided copy for both modalities (measured: 8 MiB in 20 us; two linear 4 MiB copies took 12 + 13 us,
+    // and a second stream did not run concurrently: P2P copies of one direction share a copy engine)
+    NANS_CUDA_OK(cudaMemcpy2DAsync(drows, mod_pitch, loc16, blk_bytes, blk_bytes, 2, cudaMemcpyDeviceToDevice, st));
     uint8_t* dflag = d + x->fflag_off + static_cast<size_t>(x->rank) * nflag * 4;
     NANS_CUDA_OK(cudaMemcpy2DAsync(dflag, static_cast<size_t>(x->world) * nflag * 4, stepvals, nflag * 4, nflag * 4, 2,
                                    cudaMemcpyDeviceToDevice, st));

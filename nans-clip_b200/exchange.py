@@ -81,7 +81,7 @@ class PeerExchange:
         self.epoch = torch.zeros(1, dtype=torch.int32, device=self.dev)   # steps completed (device word)
         self.forwards = 0                        # host mirror of the number of forwards issued
         self.push_stream = torch.cuda.Stream(self.dev)   # the NVLink push runs under the forward
-        self.push_stream_b = torch.cuda.Stream(self.dev)  # a second copy engine for every other peer
+        self.push_stream_b = torch.cuda.Stream(self.dev)  # hybrid push: the stream of the small push kernel
         self.fork = torch.cuda.Event()
         self.fork2 = torch.cuda.Event()
         self.join = torch.cuda.Event()

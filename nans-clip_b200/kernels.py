@@ -302,14 +302,13 @@ def xchg_cast_local_dma(desc, img: torch.Tensor, txt: torch.Tensor, feat_dtype: 
 
 
 def xchg_push_dma(desc, loc16: torch.Tensor, stepvals: torch.Tensor, slot: int, stream: "torch.cuda.Stream",
-                  stream_b: "torch.cuda.Stream | None" = None, peers: "tuple[int, int] | None" = None) -> None:
-    """The rows and their flags into the peers' buffers with copy-engine copies on `stream` (and, for every
-    other peer, `stream_b`); `peers` = (k_begin, k_end) as in xchg_push."""
+                  peers: "tuple[int, int] | None" = None) -> None:
+    """The rows and their flags into the peers' buffers with copy-engine copies on `stream`; `peers` =
+    (k_begin, k_end) as in xchg_push."""
     _require_cuda(loc16, stepvals)
     k0, k1 = peers if peers is not None else (1, int(desc.world))
     check(_lib.load().nans_xchg_push_dma_peers(_desc_ref(desc), loc16.data_ptr(), stepvals.data_ptr(), int(slot), k0, k1,
-                                               stream.cuda_stream,
-                                               stream_b.cuda_stream if stream_b is not None else None))
+                                               stream.cuda_stream))
 
 
 def xchg_cast_push(desc, img: torch.Tensor, txt: torch.Tensor, feat_dtype: torch.dtype, normalize: bool = False):

@@ -112,7 +112,7 @@ class _ClipLossFn(torch.autograd.Function):
                 I16, T16 = loc16[0], loc16[1]
                 ex.fork2.record(main)
                 ex.push_stream.wait_event(ex.fork2)
-                K.xchg_push_dma(desc, loc16, stepvals, slot, ex.push_stream, None, peers=(1, kd))
+                K.xchg_push_dma(desc, loc16, stepvals, slot, ex.push_stream, peers=(1, kd))
                 if kd < W:
                     ex.push_stream.wait_event(ex.join_b)
                 ex.join.record(ex.push_stream)

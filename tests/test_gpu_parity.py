@@ -725,7 +725,7 @@ def test_push_exchange_emulated_ranks(dev, W, n_loc, d, s, in_dt, push):
                 if kd < W:
                     K.xchg_push(descs[r], src_i, src_t, feat, peers=(kd, W))
                 l16, sv = K.xchg_cast_local_dma(descs[r], src_i, src_t, feat, (step + 1) & 1)
-                K.xchg_push_dma(descs[r], l16, sv, (step + 1) & 1, torch.cuda.current_stream(), None, peers=(1, min(kd, W)))
+                K.xchg_push_dma(descs[r], l16, sv, (step + 1) & 1, torch.cuda.current_stream(), peers=(1, min(kd, W)))
                 assert bool((sv == step + 1).all())
                 loc.append((l16[0], l16[1]))
         for r in range(W):   # the local copies are the cast rows
