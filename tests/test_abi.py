@@ -86,3 +86,24 @@ def test_forward_slot_and_workspace_queries_are_consistent():
     assert lib.nans_clip_loss_fwd_phase_slots(0, 10, 512) == 0
     assert lib.nans_clip_loss_bwd_workspace_bytes(4096, 32768, 512) >= 2 * 4096 * 512 * 4
     assert lib.nans_topk_ip_workspace_bytes(30000, 1000000, 512, 16) > 0
+
+
+def test_exchange_layout_needs_no_device_and_is_well_formed():
+    """nans_xchg_layout (host only): regions in order, aligned, non-overlapping; sizes follow the job."""
+    from nans_clip_b200 import exchange as X
+    for W, n_loc, D in ((2, 256, 64), (8, 4096, 512), (8, 8192, 768), (16, 256, 1024)):
+        d = X.make_desc(W, 1, [4096 * (r + 1) for r in range(W)], n_loc, D, 64)
+        N, pad = W * n_loc, (n_loc + 3) // 4 * 4
+        assert (d.world, d.rank, d.n_loc, d.D) == (W, 1, n_loc, D)
+        assert d.feat_off == 0 and d.lse_len == 2 * pad + 8
+        assert d.lse_off >= 2 * 2 * N * D * 2 and d.lse_off % 1024 == 0
+        assert d.fflag_off >= d.lse_off + 2 * W * d.lse_len * 4 and d.fflag_off % 1024 == 0
+        assert d.lflag_off >= d.fflag_off + 2 * W * (n_loc // 64) * 4 and d.lflag_off % 1024 == 0
+        assert d.bytes == d.lflag_off + 1024 == X.layout_bytes(W, n_loc, D)
+        assert [d.base[r] for r in range(W)] == [4096 * (r + 1) for r in range(W)]
+    with pytest.raises(_lib.NansError):
+        X.layout_bytes(4, 300, 64)        # rows per rank must be whole 256-column tiles
+    with pytest.raises(_lib.NansError):
+        X.layout_bytes(17, 256, 64)       # more peers than NANS_MAX_PEERS
+    assert X.eligible(4096, 512, 8) and not X.eligible(4096, 512, 1) and not X.eligible(4000, 512, 8)
+    assert not X.eligible(4096, 2048, 8)  # D > 1024: the narrow backward's exchange mode does not cover it

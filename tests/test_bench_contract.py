@@ -46,3 +46,20 @@ def test_both_arms_print_the_same_workload_string():
 
 def test_reference_arm_other_ranks_are_silent():
     assert _run({"RANK": "3", "WORLD_SIZE": "8", "LOCAL_RANK": "3"}, "--gpus", "8").strip() == ""
+
+
+def test_rank_shards_of_the_synthetic_batch_concatenate_to_the_full_batch():
+    """bench.py's parity_check compares every rank's gradient slice with the single-GPU run on the full
+    batch: that only means something if rank r's synthetic shard IS rows [r n_loc, (r+1) n_loc) of it."""
+    sys.path.insert(0, str(ROOT))
+    import importlib
+    import torch
+    bench = importlib.import_module("bench")
+    full_i, full_t = bench.synth_features(16384, 0, 64)
+    for W in (2, 4, 8):
+        n_loc = 16384 // W
+        parts = [bench.synth_features(n_loc, r * n_loc, 64) for r in range(W)]
+        assert torch.equal(torch.cat([p[0] for p in parts]), full_i)
+        assert torch.equal(torch.cat([p[1] for p in parts]), full_t)
+    assert torch.equal(full_i.bfloat16().float(), full_i)                # 16-bit exact, unit norm up to rounding
+    assert float((full_i.norm(dim=-1) - 1).abs().max()) < 1e-2
